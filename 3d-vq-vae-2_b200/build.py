@@ -1,0 +1,57 @@
+"""Builds libvqvae3d_b200.so (sm_100a only) in-tree with nvcc.
+
+    python 3d-vq-vae-2_b200/build.py [--force] [--verbose]
+
+The library has a pure C ABI (include/vqvae3d_b200.h) and links the CUDA runtime
+statically, so it depends on neither libtorch nor Python.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "vqvae", "libvqvae3d_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static", "--fmad=true"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(HERE, "..", "include", "vqvae3d_b200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + [f for f in FLAGS if f != "--use_fast_math=false"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,252 @@
+// conv_kernels.cu -- direct 3-D convolution, trilinear x2 upsampling and the Huber epilogue.
+//
+// vq3d_conv3d is the shape-generic path: any (C1+C2 -> Cout, k in 1..4, stride 1|2, circular
+// or zero padding) with the Fixup input transform ELU(x+a)+b and the output transform
+// *scale + b + bias[co] + residual fused in.  It covers every nn.Conv3d call site of
+// vqvae/layers.py (134-171, 249-274, 377, 490, 508, 535) including the torch.cat + 1x1
+// `proj` (385, 512) without materialising the concatenation.  Layers that dominate time get
+// dedicated fused kernels (preact_kernels.cu); this one is what the rest falls back to.
+//
+// Mapping: one thread = one output voxel x CO_T output channels; blockIdx.y walks C_out in
+// chunks of CO_T.  Weights of the chunk are staged transposed in shared memory
+// ([ci][tap][CO_T]) so that the inner product reads them as 128-bit warp broadcasts.
+#include "vq3d_rt.h"
+
+namespace vq3d {
+
+constexpr int kConvThreads = 128;
+constexpr int kConvWeightFloats = 10240;   // 40 KB weight stage
+
+struct ConvParams {
+    int B, H, W, Z, C1, C2, Cout, k, stride, pad, circ, pre_act, post_act;
+    int Ho, Wo, Zo;
+    const float *x1, *x2, *w, *bias, *pre_a, *pre_b, *post_scale, *post_b, *residual;
+    float *y;
+};
+
+template <int CO_T>
+__global__ void __launch_bounds__(kConvThreads)
+conv3d_generic_kernel(ConvParams p) {
+    __shared__ __align__(16) float s_w[kConvWeightFloats];
+    const int Cin = p.C1 + p.C2;
+    const int k = p.k, k3 = k * k * k;
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const int64_t So = (int64_t)p.Ho * p.Wo * p.Zo;
+    const int64_t total = (int64_t)p.B * So;
+    const int64_t v = (int64_t)blockIdx.x * kConvThreads + threadIdx.x;
+    const bool active = v < total;
+    const int co0 = blockIdx.y * CO_T;
+
+    int b = 0, oh = 0, ow = 0, oz = 0;
+    if (active) {
+        b = (int)(v / So);
+        int64_t r = v - (int64_t)b * So;
+        oh = (int)(r / ((int64_t)p.Wo * p.Zo));
+        r -= (int64_t)oh * p.Wo * p.Zo;
+        ow = (int)(r / p.Zo);
+        oz = (int)(r - (int64_t)ow * p.Zo);
+    }
+    const float pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = 0.0f;
+
+    int cic = kConvWeightFloats / (k3 * CO_T);
+    if (cic > Cin) cic = Cin;
+    for (int ci0 = 0; ci0 < Cin; ci0 += cic) {
+        const int nci = min(cic, Cin - ci0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nci * k3 * CO_T; i += kConvThreads) {
+            const int j = i % CO_T;
+            const int t = (i / CO_T) % k3;
+            const int cl = i / (CO_T * k3);
+            const int co = co0 + j;
+            s_w[i] = co < p.Cout ? p.w[((size_t)co * Cin + (ci0 + cl)) * k3 + t] : 0.0f;
+        }
+        __syncthreads();
+        if (active) {
+            for (int cl = 0; cl < nci; ++cl) {
+                const int ci = ci0 + cl;
+                const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S
+                                             : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+                const float *wp = s_w + (size_t)cl * k3 * CO_T;
+                for (int kh = 0; kh < k; ++kh) {
+                    int ih = oh * p.stride - p.pad + kh;
+                    if (p.circ) ih = wrap(ih, p.H);
+                    else if (ih < 0 || ih >= p.H) continue;
+                    for (int kw = 0; kw < k; ++kw) {
+                        int iw = ow * p.stride - p.pad + kw;
+                        if (p.circ) iw = wrap(iw, p.W);
+                        else if (iw < 0 || iw >= p.W) continue;
+                        const float *row = src + ((size_t)ih * p.W + iw) * p.Z;
+                        for (int kz = 0; kz < k; ++kz) {
+                            int iz = oz * p.stride - p.pad + kz;
+                            if (p.circ) iz = wrap(iz, p.Z);
+                            else if (iz < 0 || iz >= p.Z) continue;
+                            float xv = __ldg(row + iz);
+                            xv = p.pre_act ? elu1(xv + pa) + pb : xv + pb;
+                            const float *wt = wp + ((kh * k + kw) * k + kz) * CO_T;
+#pragma unroll
+                            for (int j = 0; j < CO_T; ++j) acc[j] = __fmaf_rn(wt[j], xv, acc[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+        const float sc = ld_scalar(p.post_scale, 1.0f), sb = ld_scalar(p.post_b, 0.0f);
+        const int64_t r = v - (int64_t)b * So;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+            const int co = co0 + j;
+            if (co < p.Cout) {
+                const size_t o = ((size_t)b * p.Cout + co) * So + r;
+                float yv = __fmaf_rn(acc[j], sc, sb);
+                if (p.bias) yv += __ldg(p.bias + co);
+                if (p.residual) yv += __ldg(p.residual + o);
+                if (p.post_act) yv = elu1(yv);
+                p.y[o] = yv;
+            }
+        }
+    }
+}
+
+// nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False): src = o/2 - 0.25 clamped at 0
+__device__ __forceinline__ void up_taps(int o, int n, int &i0, int &i1, float &l1) {
+    float src = 0.5f * (float)o - 0.25f;
+    if (src < 0.0f) src = 0.0f;
+    i0 = (int)src;
+    l1 = src - (float)i0;
+    i1 = i0 + (i0 < n - 1 ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const float *__restrict__ x, int64_t BC, int H, int W, int Z, int pre_act, const float *pre_a,
+                  const float *pre_b, float *__restrict__ y) {
+    const int Ho = 2 * H, Wo = 2 * W, Zo = 2 * Z;
+    const int64_t So = (int64_t)Ho * Wo * Zo, S = (int64_t)H * W * Z;
+    const int64_t total = BC * So;
+    const float pa = ld_scalar(pre_a, 0.0f), pb = ld_scalar(pre_b, 0.0f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bc = i / So;
+        int64_t r = i - bc * So;
+        const int oh = (int)(r / ((int64_t)Wo * Zo));
+        r -= (int64_t)oh * Wo * Zo;
+        const int ow = (int)(r / Zo), oz = (int)(r - (int64_t)ow * Zo);
+        int h0, h1, w0, w1, z0, z1;
+        float lh, lw, lz;
+        up_taps(oh, H, h0, h1, lh);
+        up_taps(ow, W, w0, w1, lw);
+        up_taps(oz, Z, z0, z1, lz);
+        const float *src = x + bc * S;
+        float vals[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int hh = (t & 4) ? h1 : h0, ww = (t & 2) ? w1 : w0, zz = (t & 1) ? z1 : z0;
+            float xv = __ldg(src + ((size_t)hh * W + ww) * Z + zz);
+            vals[t] = pre_act ? elu1(xv + pa) + pb : xv + pb;
+        }
+        const float a00 = vals[0] * (1.0f - lz) + vals[1] * lz, a01 = vals[2] * (1.0f - lz) + vals[3] * lz;
+        const float a10 = vals[4] * (1.0f - lz) + vals[5] * lz, a11 = vals[6] * (1.0f - lz) + vals[7] * lz;
+        const float b0 = a00 * (1.0f - lw) + a01 * lw, b1 = a10 * (1.0f - lw) + a11 * lw;
+        y[i] = b0 * (1.0f - lh) + b1 * lh;
+    }
+}
+
+// model.py:120-152 fused: ELU, depth mask, cylinder mask, smooth-L1 sum
+__global__ void __launch_bounds__(256)
+huber_elu_mask_kernel(const float *__restrict__ dec, const float *__restrict__ x, const int *__restrict__ num_valid,
+                      const uint8_t *__restrict__ mask_hw, int64_t B, int HW, int Z, double *sum, double *count) {
+    __shared__ double red[32];
+    const int64_t total = B * (int64_t)HW * Z;
+    double acc = 0.0, cnt = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i % Z);
+        const int64_t r = i / Z;
+        const int hw = (int)(r % HW);
+        const int b = (int)(r / HW);
+        if (mask_hw && !mask_hw[hw]) continue;
+        float loc = elu1(dec[i]);
+        if (num_valid && z >= num_valid[b]) loc = 0.0f;
+        const float d = fabsf(loc - x[i]);
+        acc += (double)(d < 1.0f ? 0.5f * d * d : d - 0.5f);
+        cnt += 1.0;
+    }
+    // block reduce (all threads reach here)
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    __shared__ double red2[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp] = acc; red2[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[w]; c += red2[w]; }
+        atomicAdd(sum, a);
+        atomicAdd(count, c);
+    }
+}
+
+}  // namespace vq3d
+
+using namespace vq3d;
+
+extern "C" int vq3d_abi_version(void) { return VQ3D_ABI_VERSION; }
+extern "C" const char *vq3d_last_error(void) { return err_buf(); }
+extern "C" int vq3d_is_cuda_build(void) {
+#ifdef VQ3D_EMU
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+extern "C" int vq3d_conv3d(const vq3d_conv_desc *d, void *stream) {
+    if (!d) return fail(VQ3D_ERR_INVALID, "conv3d: null descriptor");
+    if (!d->x1 || !d->w || !d->y) return fail(VQ3D_ERR_INVALID, "conv3d: null x1/w/y");
+    if (d->C2 > 0 && !d->x2) return fail(VQ3D_ERR_INVALID, "conv3d: C2 > 0 but x2 is NULL");
+    if (d->B < 1 || d->H < 1 || d->W < 1 || d->Z < 1 || d->C1 < 1 || d->C2 < 0 || d->Cout < 1)
+        return fail(VQ3D_ERR_INVALID, "conv3d: bad sizes");
+    if (d->k < 1 || d->k > 4 || (d->stride != 1 && d->stride != 2) || d->pad < 0 || d->pad >= d->k)
+        return fail(VQ3D_ERR_INVALID, "conv3d: unsupported k=%d stride=%d pad=%d", d->k, d->stride, d->pad);
+    if (d->pad_circular && (d->pad > d->H || d->pad > d->W || d->pad > d->Z))
+        return fail(VQ3D_ERR_INVALID, "conv3d: circular padding larger than the input");
+    ConvParams p;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z; p.C1 = d->C1; p.C2 = d->C2; p.Cout = d->Cout;
+    p.k = d->k; p.stride = d->stride; p.pad = d->pad; p.circ = d->pad_circular; p.pre_act = d->pre_act; p.post_act = d->post_act;
+    p.Ho = (d->H + 2 * d->pad - d->k) / d->stride + 1;
+    p.Wo = (d->W + 2 * d->pad - d->k) / d->stride + 1;
+    p.Zo = (d->Z + 2 * d->pad - d->k) / d->stride + 1;
+    if (p.Ho < 1 || p.Wo < 1 || p.Zo < 1) return fail(VQ3D_ERR_INVALID, "conv3d: empty output");
+    p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.bias = d->bias; p.pre_a = d->pre_a; p.pre_b = d->pre_b;
+    p.post_scale = d->post_scale; p.post_b = d->post_b; p.residual = d->residual; p.y = d->y;
+    const int64_t total = (int64_t)p.B * p.Ho * p.Wo * p.Zo;
+    const unsigned gx = (unsigned)ceil_div(total, kConvThreads);
+    if (p.Cout >= 8) return launch("conv3d<8>", conv3d_generic_kernel<8>, dim3(gx, (unsigned)ceil_div(p.Cout, 8)), dim3(kConvThreads), 0, stream, p);
+    if (p.Cout >= 3) return launch("conv3d<4>", conv3d_generic_kernel<4>, dim3(gx, (unsigned)ceil_div(p.Cout, 4)), dim3(kConvThreads), 0, stream, p);
+    if (p.Cout == 2) return launch("conv3d<2>", conv3d_generic_kernel<2>, dim3(gx, 1), dim3(kConvThreads), 0, stream, p);
+    return launch("conv3d<1>", conv3d_generic_kernel<1>, dim3(gx, 1), dim3(kConvThreads), 0, stream, p);
+}
+
+extern "C" int vq3d_upsample2x(const float *x, int64_t B, int C, int H, int W, int Z, int pre_act, const float *pre_a,
+                               const float *pre_b, float *y, void *stream) {
+    if (!x || !y || B < 1 || C < 1 || H < 1 || W < 1 || Z < 1) return fail(VQ3D_ERR_INVALID, "upsample2x: bad arguments");
+    const int64_t total = B * C * (int64_t)H * W * Z * 8;
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+    return launch("upsample2x", upsample2x_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, B * C, H, W, Z, pre_act, pre_a, pre_b, y);
+}
+
+extern "C" int vq3d_huber_elu_mask(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                                   int64_t B, int H, int W, int Z, double *sum, double *count, void *stream) {
+    if (!decoded || !x || !sum || !count || B < 1 || H < 1 || W < 1 || Z < 1) return fail(VQ3D_ERR_INVALID, "huber: bad arguments");
+    const int64_t total = B * (int64_t)H * W * Z;
+    int64_t blocks = ceil_div(total, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    return launch("huber_elu_mask", huber_elu_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x,
+                  (const int *)num_valid, mask_hw, B, H * W, Z, sum, count);
+}

@@ -1,0 +1,206 @@
+"""Tensor-level wrappers over the C ABI (include/vqvae3d_b200.h).
+
+PyTorch is used only for device memory and the current stream; all arithmetic happens in
+libvqvae3d_b200.so.  Every wrapper insists on CUDA fp32 tensors -- there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+Tensor = torch.Tensor
+
+
+class Ops:
+    """Product instance: `default()`.  (tests/emu subclasses this to drive the host
+    emulator build of the same kernels; the product never does.)"""
+
+    def __init__(self, lib: Optional[C.CDLL] = None):
+        self._lib = lib
+
+    # -- plumbing ---------------------------------------------------------------------
+    @property
+    def lib(self) -> C.CDLL:
+        if self._lib is None:
+            self._lib = _cabi.lib()
+        return self._lib
+
+    def stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def _t(self, t: Optional[Tensor], dtype=torch.float32) -> Optional[Tensor]:
+        if t is None:
+            return None
+        if not t.is_cuda:
+            raise RuntimeError("3d-vq-vae-2_b200 runs on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if t.dtype != dtype:
+            raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+        return t if t.is_contiguous() else t.contiguous()
+
+    @staticmethod
+    def _p(t: Optional[Tensor]) -> Optional[int]:
+        return None if t is None else t.data_ptr()
+
+    def _check(self, rc: int, allow_unsupported: bool = False) -> bool:
+        if rc == _cabi.OK:
+            return True
+        if allow_unsupported and rc == _cabi.ERR_UNSUPPORTED:
+            return False
+        raise RuntimeError("libvqvae3d_b200: " + self.lib.vq3d_last_error().decode())
+
+    # -- quantizer --------------------------------------------------------------------
+    def vq_assign(self, x: Tensor, embed: Tensor, want_stats: bool):
+        """x (B, D, *spatial) fp32 -> quant (same shape), idx (B, *spatial) int64,
+        sqerr double[1], stats = flat [K | K*D] fp32 buffer (counts then dw) | None."""
+        x = self._t(x.detach())
+        embed = self._t(embed)
+        B, D = x.shape[0], x.shape[1]
+        S = x[0, 0].numel()
+        K = embed.shape[0]
+        quant = torch.empty_like(x)
+        idx = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.int64, device=x.device)
+        sqerr = torch.zeros(1, dtype=torch.float64, device=x.device)
+        counts = dw = stats = None
+        if want_stats:
+            stats = torch.zeros(K * (D + 1), dtype=torch.float32, device=x.device)   # one flat all-reduce buffer
+            counts, dw = stats[:K], stats[K:]
+        self._check(self.lib.vq3d_vq_assign(self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx),
+                                            self._p(sqerr), self._p(counts), self._p(dw), self.stream()))
+        return quant, idx, sqerr, stats
+
+    def vq_loss(self, sqerr: Tensor, commitment_cost: float, numel: int) -> Tensor:
+        loss = torch.empty((), dtype=torch.float32, device=sqerr.device)
+        self._check(self.lib.vq3d_vq_loss(self._p(sqerr), float(commitment_cost), numel, self._p(loss), self.stream()))
+        return loss
+
+    def vq_ema_update(self, counts, dw, decay, alpha, cluster_size, embed_avg, embed) -> None:
+        K, D = embed.shape
+        for t in (cluster_size, embed_avg, embed):
+            assert t.is_contiguous()
+        self._check(self.lib.vq3d_vq_ema_update(self._p(self._t(counts)), self._p(self._t(dw)), K, D, float(decay), float(alpha),
+                                                self._p(self._t(cluster_size)), self._p(self._t(embed_avg)), self._p(self._t(embed)),
+                                                self.stream()))
+
+    def vq_init_stats(self, x: Tensor) -> Tensor:
+        x = self._t(x.detach())
+        B, D = x.shape[0], x.shape[1]
+        S = x[0, 0].numel()
+        scratch = torch.empty(2 * D, dtype=torch.float64, device=x.device)
+        meanstd = torch.empty((2, D), dtype=torch.float32, device=x.device)
+        self._check(self.lib.vq3d_vq_init_stats(self._p(x), B, D, S, self._p(scratch), self._p(meanstd), self.stream()))
+        return meanstd
+
+    def vq_init_apply(self, meanstd, total_vectors, embed, embed_avg, cluster_size, first_pass) -> None:
+        K, D = embed.shape
+        self._check(self.lib.vq3d_vq_init_apply(self._p(self._t(meanstd)), K, D, float(total_vectors), self._p(self._t(embed)),
+                                                self._p(self._t(embed_avg)), self._p(self._t(cluster_size)),
+                                                self._p(self._t(first_pass, torch.int64)), self.stream()))
+
+    def embed_code(self, idx: Tensor, embed: Tensor) -> Tensor:
+        idx = self._t(idx, torch.int64)
+        embed = self._t(embed)
+        K, D = embed.shape
+        out = torch.empty(tuple(idx.shape) + (D,), dtype=torch.float32, device=embed.device)
+        self._check(self.lib.vq3d_vq_embed_code(self._p(idx), self._p(embed), idx.numel(), D, K, self._p(out), self.stream()))
+        return out
+
+    def vq_backward(self, grad_quant, grad_loss, x, quant, commitment_cost) -> Tensor:
+        x, quant = self._t(x), self._t(quant)
+        gx = torch.empty_like(x)
+        self._check(self.lib.vq3d_vq_backward(self._p(self._t(grad_quant)), self._p(self._t(grad_loss)), self._p(x), self._p(quant),
+                                              x.numel(), float(commitment_cost), self._p(gx), self.stream()))
+        return gx
+
+    # -- convolution ------------------------------------------------------------------
+    def conv3d(self, x1: Tensor, w: Tensor, *, x2: Optional[Tensor] = None, bias: Optional[Tensor] = None, stride: int = 1,
+               pad: int = 0, circular: bool = False, pre_act: bool = False, pre_a: Optional[Tensor] = None,
+               pre_b: Optional[Tensor] = None, post_scale: Optional[Tensor] = None, post_b: Optional[Tensor] = None,
+               residual: Optional[Tensor] = None, post_act: bool = False) -> Tensor:
+        x1, x2, w = self._t(x1), self._t(x2), self._t(w)
+        B, C1, H, W, Z = x1.shape
+        C2 = 0 if x2 is None else x2.shape[1]
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        if Cin != C1 + C2:
+            raise RuntimeError(f"conv3d: weight expects {Cin} input channels, got {C1}+{C2}")
+        if x2 is not None and tuple(x2.shape[2:]) != (H, W, Z):
+            raise RuntimeError("conv3d: x1/x2 spatial mismatch")
+        out_sp = tuple((n + 2 * pad - k) // stride + 1 for n in (H, W, Z))
+        y = torch.empty((B, Cout) + out_sp, dtype=torch.float32, device=x1.device)
+        residual = self._t(residual)
+        if residual is not None and residual.shape != y.shape:
+            raise RuntimeError("conv3d: residual shape mismatch")
+        d = _cabi.ConvDesc(B=B, H=H, W=W, Z=Z, C1=C1, C2=C2, Cout=Cout, k=k, stride=stride, pad=pad,
+                           pad_circular=int(circular), pre_act=int(pre_act), post_act=int(post_act),
+                           x1=self._p(x1), x2=self._p(x2), w=self._p(w), bias=self._p(self._t(bias)),
+                           pre_a=self._p(self._t(pre_a)), pre_b=self._p(self._t(pre_b)),
+                           post_scale=self._p(self._t(post_scale)), post_b=self._p(self._t(post_b)),
+                           residual=self._p(residual), y=self._p(y))
+        self._check(self.lib.vq3d_conv3d(C.byref(d), self.stream()))
+        return y
+
+    def upsample2x(self, x: Tensor, *, pre_act: bool = False, pre_a: Optional[Tensor] = None,
+                   pre_b: Optional[Tensor] = None) -> Tensor:
+        x = self._t(x)
+        B, Cc, H, W, Z = x.shape
+        y = torch.empty((B, Cc, 2 * H, 2 * W, 2 * Z), dtype=torch.float32, device=x.device)
+        self._check(self.lib.vq3d_upsample2x(self._p(x), B, Cc, H, W, Z, int(pre_act), self._p(self._t(pre_a)),
+                                             self._p(self._t(pre_b)), self._p(y), self.stream()))
+        return y
+
+    def preact_desc(self, x: Tensor, y: Optional[Tensor], blk, mode: int) -> "_cabi.PreactDesc":
+        B, Cin, H, W, Z = x.shape
+        w1, w2, w3 = blk.branch_conv1.weight, blk.branch_conv2.weight, blk.branch_conv3.weight
+        skip = blk.skip_conv.weight if blk.skip_conv is not None else None
+        g = lambda n: self._p(self._t(getattr(blk, n).data)) if hasattr(blk, n) else None
+        return _cabi.PreactDesc(B=B, H=H, W=W, Z=Z, Cin=Cin, Cb=w1.shape[0], Cout=w3.shape[0], mode=mode,
+                                x=self._p(x), w1=self._p(self._t(w1.data)), w2=self._p(self._t(w2.data)),
+                                w3=self._p(self._t(w3.data)), wskip=None if skip is None else self._p(self._t(skip.data)),
+                                b1a=g("bias1a"), b1b=g("bias1b"), b2a=g("bias2a"), b2b=g("bias2b"), b3a=g("bias3a"),
+                                b3b=g("bias3b"), b4=g("bias4"), scale=g("scale"), b1c=g("bias1c"), b1d=g("bias1d"),
+                                y=None if y is None else self._p(y))
+
+    def preact_block(self, x: Tensor, blk, mode: int) -> Optional[Tensor]:
+        """Whole PreActFixupResBlock in one launch; None if no fused kernel covers the shape."""
+        x = self._t(x)
+        B, Cin, H, W, Z = x.shape
+        Cout = blk.branch_conv3.weight.shape[0]
+        sp = {0: (H, W, Z), 1: (H // 2, W // 2, Z // 2), 2: (2 * H, 2 * W, 2 * Z)}[mode]
+        y = torch.empty((B, Cout) + sp, dtype=torch.float32, device=x.device)
+        d = self.preact_desc(x, y, blk, mode)
+        ok = self._check(self.lib.vq3d_preact_block(C.byref(d), self.stream()), allow_unsupported=True)
+        return y if ok else None
+
+    def preact_stack(self, x: Tensor, blocks) -> Optional[Tensor]:
+        """n consecutive equal-shape 'same' blocks; None if unsupported."""
+        x = self._t(x)
+        n = len(blocks)
+        y, tmp = torch.empty_like(x), torch.empty_like(x)
+        arr = (_cabi.PreactDesc * n)()
+        for i, blk in enumerate(blocks):
+            arr[i] = self.preact_desc(x, y, blk, 0)
+        ok = self._check(self.lib.vq3d_preact_stack(arr, n, self._p(tmp), self.stream()), allow_unsupported=True)
+        return y if ok else None
+
+    def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
+        decoded, x = self._t(decoded), self._t(x)
+        B, _, H, W, Z = x.shape
+        acc = torch.zeros(2, dtype=torch.float64, device=x.device)
+        self._check(self.lib.vq3d_huber_elu_mask(self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)),
+                                                 self._p(self._t(mask_hw, torch.uint8)), B, H, W, Z,
+                                                 acc[0:1].data_ptr(), acc[1:2].data_ptr(), self.stream()))
+        return acc
+
+
+_DEFAULT: Optional[Ops] = None
+
+
+def default() -> Ops:
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = Ops()
+    return _DEFAULT

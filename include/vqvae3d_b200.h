@@ -1,0 +1,179 @@
+/*
+ * vqvae3d_b200.h -- C ABI of libvqvae3d_b200.so: sm_100a kernels for the 3D VQ-VAE-2
+ * encode -> quantize -> decode hot path of sara-nl/3D-VQ-VAE-2.
+ *
+ * The reference has no FFI layer: its boundary is the Python nn.Module API of
+ * vqvae/layers.py / vqvae/evonorm.py.  Each entry point below states which
+ * reference function (file:line under the reference repo) it replaces.  The Python mirror
+ * of those modules (3d-vq-vae-2_b200/vqvae/) binds this library with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory;
+ *  - activations are fp32, contiguous, in the reference's layout (B, C, H, W, Z) with the
+ *    CT depth axis Z innermost; S = H*W*Z;
+ *  - convolution weights are the reference's (C_out, C_in, k, k, k) fp32 tensors, unpacked;
+ *  - the Fixup scalars (bias1a ... bias4, scale: nn.Parameter of shape (1,)) are passed as
+ *    device pointers to one float; NULL means "absent" (0 for biases, 1 for scale);
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream); calls only enqueue work;
+ *  - return value 0 = success; non-zero = error, message in vq3d_last_error() (thread-local).
+ *    No global state, re-entrant per stream.
+ */
+#ifndef VQVAE3D_B200_H
+#define VQVAE3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQ3D_ABI_VERSION 1
+
+int vq3d_abi_version(void);
+const char *vq3d_last_error(void);
+/* 1 if the library was built from the CUDA sources for sm_100a (always, for the product). */
+int vq3d_is_cuda_build(void);
+
+/* ------------------------------------------------------------------------------------
+ * Quantizer (vqvae/layers.py:602-728)
+ * ------------------------------------------------------------------------------------ */
+
+/*
+ * Fused Quantizer.forward body, layers.py:687-720 (+ the one-hot sums of _update_ema,
+ * :638-643, when counts/dw are given):
+ *   idx[b,s]   = first k minimising sqrt(sum_d (x[b,d,s]-embed[k,d])^2), fp32, in the
+ *                summation order of torch.cdist(compute_mode='donot_use_mm_for_euclid_dist')
+ *   quant[b,d,s] = x + (embed[idx[b,s], d] - x) (straight-through value, layers.py:720, same two
+ *                roundings; the codebook BEFORE this step's EMA update)
+ *   *sqerr    += sum (embed[idx] - x)^2             (double accumulator; caller zeroes it)
+ *   counts[k] += #{idx == k};  dw[k,d] += sum_{idx==k} x[.,d,.]   (fp32; caller zeroes)
+ * x, quant: [B, D, S]; idx: [B, S] int64; embed: [K, D]; counts/dw may both be NULL (eval).
+ */
+int vq3d_vq_assign(const float *x, const float *embed, int64_t B, int D, int64_t S, int K,
+                   float *quant, int64_t *idx, double *sqerr, float *counts, float *dw,
+                   void *stream);
+
+/* loss = commitment_cost * sqerr / numel  (F.mse_loss * commitment_cost, layers.py:716-717) */
+int vq3d_vq_loss(const double *sqerr, double commitment_cost, int64_t numel, float *loss, void *stream);
+
+/*
+ * Tail of Quantizer._update_ema, layers.py:649-663, in place on the three buffers:
+ *   cluster_size = decay*cluster_size + (1-decay)*counts
+ *   embed_avg    = decay*embed_avg    + (1-decay)*dw
+ *   n = sum(cluster_size); smoothed = n*(cluster_size+alpha)/(n+K*alpha); embed = embed_avg/smoothed
+ * counts/dw are the (already all-reduced) outputs of vq3d_vq_assign.
+ */
+int vq3d_vq_ema_update(const float *counts, const float *dw, int K, int D, double decay, double laplace_alpha,
+                       float *cluster_size, float *embed_avg, float *embed, void *stream);
+
+/*
+ * First half of Quantizer._init_ema, layers.py:666-667: mean[d], unbiased std[d] of the
+ * B*S latent vectors.  meanstd: [2, D] fp32 out (row 0 mean, row 1 std); scratch: [2*D]
+ * doubles, zeroed by the call.  The caller all-reduces/averages meanstd across ranks
+ * (layers.py:670-674) before vq3d_vq_init_apply.
+ */
+int vq3d_vq_init_stats(const float *x, int64_t B, int D, int64_t S, double *scratch, float *meanstd, void *stream);
+
+/*
+ * Second half of _init_ema, layers.py:678-683: embed = embed*std + mean; embed_avg = embed;
+ * cluster_size += total_vectors / K; *first_pass = 0 (int64 scalar buffer).
+ */
+int vq3d_vq_init_apply(const float *meanstd, int K, int D, double total_vectors, float *embed, float *embed_avg,
+                       float *cluster_size, int64_t *first_pass, void *stream);
+
+/* Quantizer.embed_code, layers.py:633-634 (F.embedding): out[n, :] = embed[idx[n], :]. */
+int vq3d_vq_embed_code(const int64_t *idx, const float *embed, int64_t n, int D, int K, float *out, void *stream);
+
+/*
+ * Backward of the straight-through estimator + commitment loss, layers.py:716-720:
+ *   grad_x = grad_quant + grad_loss * 2*commitment_cost/numel * (x - quant)
+ * grad_quant may be NULL (treated as 0); grad_loss is a device scalar.
+ */
+int vq3d_vq_backward(const float *grad_quant, const float *grad_loss, const float *x, const float *quant,
+                     int64_t numel, double commitment_cost, float *grad_x, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Convolution building blocks (every nn.Conv3d / ResizeConv3D call site of layers.py)
+ * ------------------------------------------------------------------------------------ */
+
+typedef struct vq3d_conv_desc {
+    /* geometry */
+    int32_t B, H, W, Z;          /* input spatial size */
+    int32_t C1, C2;              /* channels of x1 and x2; C_in = C1 + C2 (implicit torch.cat, layers.py:385,512) */
+    int32_t Cout;
+    int32_t k, stride, pad;      /* cubic kernel; out = (in + 2*pad - k)/stride + 1 */
+    int32_t pad_circular;        /* 1: padding_mode='circular' (layers.py:109), 0: zeros */
+    /* input transform, applied to every input element before padding:
+     *   pre_act ? ELU(x + *pre_a) + *pre_b : x + *pre_b                          (layers.py:178-185) */
+    int32_t pre_act;
+    /* output transform: y = conv * (*post_scale) + *post_b + bias[co] + residual; then ELU if post_act */
+    int32_t post_act;
+    const float *x1, *x2;        /* [B, C1, S], [B, C2, S]; x2 may be NULL when C2 == 0 */
+    const float *w;              /* [Cout, C1+C2, k, k, k] */
+    const float *bias;           /* [Cout] or NULL */
+    const float *pre_a, *pre_b;  /* device scalars or NULL */
+    const float *post_scale, *post_b;
+    const float *residual;       /* [B, Cout, S_out] or NULL */
+    float *y;                    /* [B, Cout, S_out] */
+} vq3d_conv_desc;
+
+/* Direct convolution for any shape on the path (fallback for layers without a fused kernel). */
+int vq3d_conv3d(const vq3d_conv_desc *desc, void *stream);
+
+/*
+ * nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False) of ResizeConv3D
+ * (layers.py:591-597) with the same optional input transform as vq3d_conv_desc:
+ * y[B, C, 2H, 2W, 2Z] = upsample(pre_act ? ELU(x + *pre_a) + *pre_b : x + *pre_b).
+ */
+int vq3d_upsample2x(const float *x, int64_t B, int C, int H, int W, int Z, int pre_act,
+                    const float *pre_a, const float *pre_b, float *y, void *stream);
+
+/*
+ * One whole PreActFixupResBlock.forward (layers.py:176-195) in ONE launch:
+ *   o = conv1x1(ELU(x+b1a)+b1b); o = conv_k(ELU(o+b2a)+b2b) [circular; after a trilinear x2
+ *   upsample when mode==up]; o = conv1x1(ELU(o+b3a)+b3b); o = o*scale + b4;
+ *   y = o + (skip(x+b1c)+b1d | x)
+ * mode: 0 same/out (k3 s1), 1 down (k4 s2, skip k2 s2), 2 up (ResizeConv3D k3, skip ResizeConv3D k1).
+ * Returns VQ3D_ERR_UNSUPPORTED (2) when no fused instantiation covers the channel counts;
+ * the caller then composes the block from vq3d_conv3d / vq3d_upsample2x.
+ */
+typedef struct vq3d_preact_desc {
+    int32_t B, H, W, Z;          /* input spatial size */
+    int32_t Cin, Cb, Cout;
+    int32_t mode;
+    const float *x;              /* [B, Cin, S] */
+    const float *w1, *w2, *w3;   /* branch_conv1/2/3.weight */
+    const float *wskip;          /* skip_conv.weight or NULL */
+    const float *b1a, *b1b, *b2a, *b2b, *b3a, *b3b, *b4, *scale, *b1c, *b1d;
+    float *y;                    /* [B, Cout, S_out] */
+} vq3d_preact_desc;
+
+#define VQ3D_OK 0
+#define VQ3D_ERR_INVALID 1
+#define VQ3D_ERR_UNSUPPORTED 2
+#define VQ3D_ERR_CUDA 3
+
+int vq3d_preact_block(const vq3d_preact_desc *desc, void *stream);
+
+/*
+ * A run of n consecutive 'same' PreActFixupResBlocks with equal channel counts (the
+ * nn.Sequential stacks of layers.py:492-494,566-569) in as few launches as possible.
+ * blocks[i] describes block i; blocks[i].x / .y are ignored except blocks[0].x (input) and
+ * blocks[n-1].y (output); tmp is a scratch activation buffer of the same size (ping-pong).
+ */
+int vq3d_preact_stack(const vq3d_preact_desc *blocks, int n, float *tmp, void *stream);
+
+/*
+ * Loss epilogue of VQVAE.loc_metric, model.py:120-152, fused: loc = ELU(decoded), zero where
+ * z >= num_valid[b], optional centre-cylinder mask over (H, W) (utils/load_nrrd_dataset.py:288-300,
+ * mask: [H*W] uint8 or NULL), smooth-L1 (beta 1) against x, summed into *sum (double, caller
+ * zeroes) with the element count into *count.
+ */
+int vq3d_huber_elu_mask(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                        int64_t B, int H, int W, int Z, double *sum, double *count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQVAE3D_B200_H */
