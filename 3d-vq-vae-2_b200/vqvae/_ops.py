@@ -21,6 +21,8 @@ class Ops:
 
     def __init__(self, lib: Optional[C.CDLL] = None):
         self._lib = lib
+        self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
+        self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
 
     # -- plumbing ---------------------------------------------------------------------
     @property
@@ -46,6 +48,20 @@ class Ops:
     def _p(t: Optional[Tensor]) -> Optional[int]:
         return None if t is None else t.data_ptr()
 
+    def _call(self, name, cfunc, args, kernels=1, nbytes=0, flops=0, tag="", allow_unsupported=False) -> bool:
+        """One C-ABI call.  With `profile` set, brackets it with CUDA events on the launching stream."""
+        prof = self.profile
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ok = self._check(cfunc(*args), allow_unsupported)
+        if ok:
+            self.launches += kernels
+            if prof is not None:
+                e1.record()
+                prof.append((name, tag, nbytes, flops, e0, e1))
+        return ok
+
     def _check(self, rc: int, allow_unsupported: bool = False) -> bool:
         if rc == _cabi.OK:
             return True
@@ -69,22 +85,24 @@ class Ops:
         if want_stats:
             stats = torch.zeros(K * (D + 1), dtype=torch.float32, device=x.device)   # one flat all-reduce buffer
             counts, dw = stats[:K], stats[K:]
-        self._check(self.lib.vq3d_vq_assign(self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx),
-                                            self._p(sqerr), self._p(counts), self._p(dw), self.stream()))
+        self._call("vq_assign", self.lib.vq3d_vq_assign,
+                   (self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx), self._p(sqerr), self._p(counts),
+                    self._p(dw), self.stream()),
+                   nbytes=B * S * (8 * D + 8), flops=2 * B * S * K * D, tag=f"N{B * S}xD{D}xK{K}")
         return quant, idx, sqerr, stats
 
     def vq_loss(self, sqerr: Tensor, commitment_cost: float, numel: int) -> Tensor:
         loss = torch.empty((), dtype=torch.float32, device=sqerr.device)
-        self._check(self.lib.vq3d_vq_loss(self._p(sqerr), float(commitment_cost), numel, self._p(loss), self.stream()))
+        self._call("vq_loss", self.lib.vq3d_vq_loss, (self._p(sqerr), float(commitment_cost), numel, self._p(loss), self.stream()))
         return loss
 
     def vq_ema_update(self, counts, dw, decay, alpha, cluster_size, embed_avg, embed) -> None:
         K, D = embed.shape
         for t in (cluster_size, embed_avg, embed):
             assert t.is_contiguous()
-        self._check(self.lib.vq3d_vq_ema_update(self._p(self._t(counts)), self._p(self._t(dw)), K, D, float(decay), float(alpha),
-                                                self._p(self._t(cluster_size)), self._p(self._t(embed_avg)), self._p(self._t(embed)),
-                                                self.stream()))
+        self._call("vq_ema_update", self.lib.vq3d_vq_ema_update,
+                   (self._p(self._t(counts)), self._p(self._t(dw)), K, D, float(decay), float(alpha),
+                    self._p(self._t(cluster_size)), self._p(self._t(embed_avg)), self._p(self._t(embed)), self.stream()))
 
     def vq_init_stats(self, x: Tensor) -> Tensor:
         x = self._t(x.detach())
@@ -92,28 +110,31 @@ class Ops:
         S = x[0, 0].numel()
         scratch = torch.empty(2 * D, dtype=torch.float64, device=x.device)
         meanstd = torch.empty((2, D), dtype=torch.float32, device=x.device)
-        self._check(self.lib.vq3d_vq_init_stats(self._p(x), B, D, S, self._p(scratch), self._p(meanstd), self.stream()))
+        self._call("vq_init_stats", self.lib.vq3d_vq_init_stats,
+                   (self._p(x), B, D, S, self._p(scratch), self._p(meanstd), self.stream()), kernels=2)
         return meanstd
 
     def vq_init_apply(self, meanstd, total_vectors, embed, embed_avg, cluster_size, first_pass) -> None:
         K, D = embed.shape
-        self._check(self.lib.vq3d_vq_init_apply(self._p(self._t(meanstd)), K, D, float(total_vectors), self._p(self._t(embed)),
-                                                self._p(self._t(embed_avg)), self._p(self._t(cluster_size)),
-                                                self._p(self._t(first_pass, torch.int64)), self.stream()))
+        self._call("vq_init_apply", self.lib.vq3d_vq_init_apply,
+                   (self._p(self._t(meanstd)), K, D, float(total_vectors), self._p(self._t(embed)), self._p(self._t(embed_avg)),
+                    self._p(self._t(cluster_size)), self._p(self._t(first_pass, torch.int64)), self.stream()))
 
     def embed_code(self, idx: Tensor, embed: Tensor) -> Tensor:
         idx = self._t(idx, torch.int64)
         embed = self._t(embed)
         K, D = embed.shape
         out = torch.empty(tuple(idx.shape) + (D,), dtype=torch.float32, device=embed.device)
-        self._check(self.lib.vq3d_vq_embed_code(self._p(idx), self._p(embed), idx.numel(), D, K, self._p(out), self.stream()))
+        self._call("vq_embed_code", self.lib.vq3d_vq_embed_code,
+                   (self._p(idx), self._p(embed), idx.numel(), D, K, self._p(out), self.stream()), nbytes=idx.numel() * (8 + 4 * D))
         return out
 
     def vq_backward(self, grad_quant, grad_loss, x, quant, commitment_cost) -> Tensor:
         x, quant = self._t(x), self._t(quant)
         gx = torch.empty_like(x)
-        self._check(self.lib.vq3d_vq_backward(self._p(self._t(grad_quant)), self._p(self._t(grad_loss)), self._p(x), self._p(quant),
-                                              x.numel(), float(commitment_cost), self._p(gx), self.stream()))
+        self._call("vq_backward", self.lib.vq3d_vq_backward,
+                   (self._p(self._t(grad_quant)), self._p(self._t(grad_loss)), self._p(x), self._p(quant), x.numel(),
+                    float(commitment_cost), self._p(gx), self.stream()), nbytes=16 * x.numel())
         return gx
 
     # -- convolution ------------------------------------------------------------------
@@ -140,7 +161,10 @@ class Ops:
                            pre_a=self._p(self._t(pre_a)), pre_b=self._p(self._t(pre_b)),
                            post_scale=self._p(self._t(post_scale)), post_b=self._p(self._t(post_b)),
                            residual=self._p(residual), y=self._p(y))
-        self._check(self.lib.vq3d_conv3d(C.byref(d), self.stream()))
+        so = y[0, 0].numel()
+        self._call("conv3d", self.lib.vq3d_conv3d, (C.byref(d), self.stream()),
+                   nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
+                   flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
         return y
 
     def upsample2x(self, x: Tensor, *, pre_act: bool = False, pre_a: Optional[Tensor] = None,
@@ -148,8 +172,9 @@ class Ops:
         x = self._t(x)
         B, Cc, H, W, Z = x.shape
         y = torch.empty((B, Cc, 2 * H, 2 * W, 2 * Z), dtype=torch.float32, device=x.device)
-        self._check(self.lib.vq3d_upsample2x(self._p(x), B, Cc, H, W, Z, int(pre_act), self._p(self._t(pre_a)),
-                                             self._p(self._t(pre_b)), self._p(y), self.stream()))
+        self._call("upsample2x", self.lib.vq3d_upsample2x,
+                   (self._p(x), B, Cc, H, W, Z, int(pre_act), self._p(self._t(pre_a)), self._p(self._t(pre_b)), self._p(y),
+                    self.stream()), nbytes=4 * B * Cc * H * W * Z * 9, tag=f"{Cc}ch @{H}x{W}x{Z}")
         return y
 
     def preact_desc(self, x: Tensor, y: Optional[Tensor], blk, mode: int) -> "_cabi.PreactDesc":
@@ -172,7 +197,13 @@ class Ops:
         sp = {0: (H, W, Z), 1: (H // 2, W // 2, Z // 2), 2: (2 * H, 2 * W, 2 * Z)}[mode]
         y = torch.empty((B, Cout) + sp, dtype=torch.float32, device=x.device)
         d = self.preact_desc(x, y, blk, mode)
-        ok = self._check(self.lib.vq3d_preact_block(C.byref(d), self.stream()), allow_unsupported=True)
+        si, so = H * W * Z, sp[0] * sp[1] * sp[2]
+        Cb = blk.branch_conv1.weight.shape[0]
+        k3 = blk.branch_conv2.weight.shape[2] ** 3
+        ok = self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()), allow_unsupported=True,
+                        nbytes=4 * B * (Cin * si + Cout * so),
+                        flops=2 * B * (Cin * Cb * si + Cb * Cb * k3 * so + Cb * Cout * so + (Cin * Cout * so * (8 if mode == 1 else 1) if blk.skip_conv is not None else 0)),
+                        tag=f"{('same', 'down', 'up')[mode]} {Cin}->{Cb}->{Cout} @{H}x{W}x{Z}")
         return y if ok else None
 
     def preact_stack(self, x: Tensor, blocks) -> Optional[Tensor]:
@@ -183,16 +214,20 @@ class Ops:
         arr = (_cabi.PreactDesc * n)()
         for i, blk in enumerate(blocks):
             arr[i] = self.preact_desc(x, y, blk, 0)
-        ok = self._check(self.lib.vq3d_preact_stack(arr, n, self._p(tmp), self.stream()), allow_unsupported=True)
+        B, Cc, H, W, Z = x.shape
+        Cb = blocks[0].branch_conv1.weight.shape[0]
+        ok = self._call("preact_stack", self.lib.vq3d_preact_stack, (arr, n, self._p(tmp), self.stream()), allow_unsupported=True,
+                        kernels=n, nbytes=n * 8 * x.numel(), flops=n * 2 * B * H * W * Z * (2 * Cc * Cb + 27 * Cb * Cb),
+                        tag=f"stack{n} {Cc}->{Cb}->{Cc} @{H}x{W}x{Z}")
         return y if ok else None
 
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
         decoded, x = self._t(decoded), self._t(x)
         B, _, H, W, Z = x.shape
         acc = torch.zeros(2, dtype=torch.float64, device=x.device)
-        self._check(self.lib.vq3d_huber_elu_mask(self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)),
-                                                 self._p(self._t(mask_hw, torch.uint8)), B, H, W, Z,
-                                                 acc[0:1].data_ptr(), acc[1:2].data_ptr(), self.stream()))
+        self._call("huber_elu_mask", self.lib.vq3d_huber_elu_mask,
+                   (self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)), self._p(self._t(mask_hw, torch.uint8)),
+                    B, H, W, Z, acc[0:1].data_ptr(), acc[1:2].data_ptr(), self.stream()), nbytes=8 * x.numel())
         return acc
 
 

