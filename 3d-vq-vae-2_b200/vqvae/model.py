@@ -79,8 +79,8 @@ class VQVAE(_Base):
         return self._forward_eager(data)
 
     def _forward_eager(self, data):
-        commitment_loss, quantizations, encoding_idx = zip(*self.encode(data))
-        decoded = self.decode(quantizations)
+        commitment_loss, quantizations, encoding_idx = zip(*self.encoder(data))
+        decoded = self.decoder(quantizations)
         return decoded, (commitment_loss, quantizations, encoding_idx)
 
     # ---- CUDA graphs: the eval-mode forward is ~1.5k launches of small kernels; replaying a

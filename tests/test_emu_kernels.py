@@ -136,3 +136,43 @@ def test_emu_model(name):
         # teacher-forced decoder: the reference's own quantised latents -> reference decoded volume
         dec_tf = m.decoder([torch.from_numpy(g[f"eval_quantized_{i}"]) for i in range(n)])
         assert close(dec_tf.numpy(), g["eval_decoded"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,mode,shape", [
+    (4, 4, "same", (1, 4, 20, 12, 40)),      # several tiles per axis, ragged in H and Z
+    (18, 18, "same", (1, 18, 9, 5, 3)),      # odd extents smaller than a tile
+    (18, 2, "same", (2, 18, 10, 9, 33)),
+    (4, 8, "down", (1, 4, 20, 18, 68)),
+    (8, 16, "down", (2, 8, 6, 4, 2)),
+    (8, 4, "up", (1, 8, 10, 5, 17)),         # hi-res 20 x 10 x 34: ragged tiles + wrap on every axis
+    (18, 8, "up", (1, 18, 3, 1, 2)),
+    (4, 2, "up", (2, 4, 2, 6, 20)),
+])
+def test_emu_fused_equals_composed_multitile(cin, cout, mode, shape):
+    torch.manual_seed(cin * 100 + cout)
+    with use_emulator() as o, torch.no_grad():
+        m = L.PreActFixupResBlock(cin, cout, mode).eval()
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        m.scale.fill_(0.9)
+        x = torch.randn(shape)
+        n0 = o.launches
+        y = m(x)
+        assert o.launches - n0 == 1, "expected the single fused launch"
+        ref = m.forward_composed(x)
+        assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())
+
+
+def test_emu_stack_ping_pong():
+    torch.manual_seed(5)
+    with use_emulator() as o, torch.no_grad():
+        for n in (1, 2, 3):
+            seq = L.BlockSequence(*(L.PreActFixupResBlock(4, 4, "same") for _ in range(n))).eval()
+            for p in seq.parameters():
+                p.copy_(torch.randn(p.shape) * 0.3)
+            x = torch.randn(1, 4, 6, 5, 9)
+            ref = x
+            for blk in seq:
+                ref = blk.forward_composed(ref)
+            y = seq(x)
+            assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
