@@ -1,0 +1,277 @@
+// tc_kernels.cu -- implicit-GEMM 3-D convolution on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Used for the GEMM-shaped layers of the path: C_in*k^3 >= 64 reduction length with >= 16
+// output channels (the 72/64/128/256-channel blocks of the Full model, vqvae/layers.py:134-171
+// at the sizes of SURVEY.md 8a).  D[voxel, co] = sum_k A[voxel, k] * W[co, k], k = (ci, kh, kw, kz):
+//
+//   A  (M = 128 output voxels per CTA, K-major bf16): gathered on the fly by the CTA's warps from
+//      the fp32 activation (wrapped coordinates = circular padding, zero padding = zero fill),
+//      with the Fixup input transform ELU(x+a)+b applied, packed to bf16 and stored in the UMMA
+//      canonical no-swizzle K-major layout (core matrix = 8 rows x 16 B, LBO = K-direction stride,
+//      SBO = 8-row-group stride).  These activations are <= a few MB and L2 resident; the gather
+//      is coordinate arithmetic, which TMA's zero-fill out-of-bounds mode cannot express for wrap.
+//   B  (N = C_out padded to 16, K-major bf16): the reference's (C_out, C_in, k, k, k) fp32 weight
+//      is already K-major; rows are converted to bf16 while being staged.
+//   D  fp32 accumulators in TMEM (N columns x 128 lanes); one elected thread issues
+//      tcgen05.mma.cta_group::1.kind::f16 (M128 x N x K16), tcgen05.commit signals an mbarrier per
+//      smem stage so the gather of chunk i+1 overlaps the MMAs of chunk i.
+//   epilogue: tcgen05.ld 32x32b (lane = voxel) -> *scale + b + bias[co] + residual (+ELU) -> fp32
+//      planar store, coalesced because consecutive lanes are consecutive voxels.
+//
+// Operands are rounded to bf16 (fp32 accumulate): results match the fp32 path to ~1e-2 relative
+// (north_star tolerance for BF16 paths); the quantizer stays fp32 and index-exact on its inputs.
+#include "vq3d_rt.h"
+
+#ifndef VQ3D_EMU
+#include <cuda_bf16.h>
+
+namespace vq3d {
+
+constexpr int kTcBK = 64;            // K elements per smem stage
+constexpr int kTcStages = 2;
+constexpr int kTcM = 128;
+
+struct TcParams {
+    int B, H, W, Z, C1, C2, Cout, k, stride, pad, circ, pre_act, post_act;
+    int Ho, Wo, Zo, Npad, Ktot, G;
+    const float *x1, *x2, *w, *bias, *pre_a, *pre_b, *post_scale, *post_b, *residual;
+    float *y;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();   // never hang the GPU: a lost arrival becomes a launch error instead
+}
+
+// K-major, no swizzle: bits [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// threads = 128 * G: thread (row r = tid % 128, group g = tid / 128); a stage holds K = 64 = 8 chunks
+// of 8 elements (16 B); group g packs chunks g, g+G, ...
+__global__ void __launch_bounds__(512)
+conv3d_tc_kernel(TcParams p) {
+    VQ3D_DYN_SMEM(unsigned char, smem_raw);
+    __shared__ __align__(8) uint64_t mma_done[kTcStages];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid & (kTcM - 1), g = tid >> 7, G = p.G;
+    const int Npad = p.Npad, Ktot = p.Ktot;
+    const int k = p.k, kk = k * k, k3 = kk * k;
+    const int Cin = p.C1 + p.C2;
+    // stage layout: A [8 k-chunks][16 row-groups][128 B] = 16 KB, then B [8][Npad/8][128 B]
+    const uint32_t a_bytes = kTcM * kTcBK * 2, b_bytes = (uint32_t)Npad * kTcBK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t a_lbo = (kTcM / 8) * 128, b_lbo = (uint32_t)(Npad / 8) * 128, sbo = 128;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    unsigned char *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)Npad) tmem_cols <<= 1;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&mma_done[0], 1);
+        mbar_init(&mma_done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    // this thread's output voxel
+    const int64_t S = (int64_t)p.H * p.W * p.Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
+    const int64_t total = (int64_t)p.B * So;
+    const int64_t v = (int64_t)blockIdx.x * kTcM + r;
+    const bool row_ok = v < total;
+    int b = 0, oh = 0, ow = 0, oz = 0;
+    if (row_ok) {
+        b = (int)(v / So);
+        int rem = (int)(v - (int64_t)b * So);
+        oh = rem / (p.Wo * p.Zo);
+        rem -= oh * p.Wo * p.Zo;
+        ow = rem / p.Zo;
+        oz = rem - ow * p.Zo;
+    }
+    const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad, iz0 = oz * p.stride - p.pad;
+    const float pa = ld_scalar(p.pre_a, 0.f), pb = ld_scalar(p.pre_b, 0.f);
+    // instruction descriptor: D fp32 (1<<4), A/B bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+    const int nchunks = (Ktot + kTcBK - 1) / kTcBK;
+    for (int it = 0; it < nchunks; ++it) {
+        const int s = it & 1;
+        if (it >= kTcStages) mbar_wait(&mma_done[s], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs that read this stage are done
+        unsigned char *sa = smem + (size_t)s * stage_bytes;
+        unsigned char *sb = sa + a_bytes;
+        const int kbase = it * kTcBK;
+        // ---- A: gather + transform + bf16 pack, one 16-byte chunk (8 k's) at a time ----------
+        for (int c = g; c < 8; c += G) {
+            int kidx = kbase + c * 8;
+            int ci = kidx / k3, t = kidx - ci * k3;
+            int kh = t / kk; t -= kh * kk;
+            int kw = t / k, kz = t - kw * k;
+            float vals[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float xv = 0.0f;
+                if (row_ok && ci < Cin) {
+                    int ih = ih0 + kh, iw = iw0 + kw, iz = iz0 + kz;
+                    bool ok = true;
+                    if (p.circ) { ih = wrap(ih, p.H); iw = wrap(iw, p.W); iz = wrap(iz, p.Z); }
+                    else ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;
+                    if (ok) {
+                        const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+                        xv = __ldg(src + ((size_t)ih * p.W + iw) * p.Z + iz);
+                        xv = p.pre_act ? elu1(xv + pa) + pb : xv + pb;
+                    }
+                }
+                vals[e] = xv;
+                if (++kz == k) { kz = 0; if (++kw == k) { kw = 0; if (++kh == k) { kh = 0; ++ci; } } }
+            }
+            uint4 pk;
+            pk.x = pack_bf16(vals[0], vals[1]); pk.y = pack_bf16(vals[2], vals[3]);
+            pk.z = pack_bf16(vals[4], vals[5]); pk.w = pack_bf16(vals[6], vals[7]);
+            *reinterpret_cast<uint4 *>(sa + (size_t)c * a_lbo + (size_t)(r >> 3) * sbo + (size_t)(r & 7) * 16) = pk;
+        }
+        // ---- B: weight rows, fp32 -> bf16 -------------------------------------------------------
+        for (int i = tid; i < Npad * 8; i += blockDim.x) {
+            const int n = i >> 3, c = i & 7;
+            const int k0 = kbase + c * 8;
+            float wv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) wv[e] = (n < p.Cout && k0 + e < Ktot) ? __ldg(p.w + (size_t)n * Ktot + k0 + e) : 0.0f;
+            uint4 pk;
+            pk.x = pack_bf16(wv[0], wv[1]); pk.y = pack_bf16(wv[2], wv[3]);
+            pk.z = pack_bf16(wv[4], wv[5]); pk.w = pack_bf16(wv[6], wv[7]);
+            *reinterpret_cast<uint4 *>(sb + (size_t)c * b_lbo + (size_t)(n >> 3) * sbo + (size_t)(n & 7) * 16) = pk;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (tensor core)
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes, b_addr = a_addr + a_bytes;
+#pragma unroll
+            for (int j = 0; j < kTcBK / 16; ++j) {
+                const uint64_t adesc = make_desc(a_addr + (uint32_t)(2 * j) * a_lbo, a_lbo, sbo);
+                const uint64_t bdesc = make_desc(b_addr + (uint32_t)(2 * j) * b_lbo, b_lbo, sbo);
+                umma_bf16(tmem_d, adesc, bdesc, idesc, (it > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(&mma_done[s]);       // arrives when every MMA issued so far has completed
+        }
+    }
+    // all MMAs complete in order: waiting for the last commit covers everything
+    {
+        const int last = nchunks - 1;
+        mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns split across the G warp groups ----
+    {
+        const int q = warp & 3, wg = warp >> 2;
+        const int row = q * 32 + lane;
+        const int64_t vr = (int64_t)blockIdx.x * kTcM + row;
+        const bool ok = vr < total;
+        int bb = 0; int64_t rem = 0;
+        if (ok) { bb = (int)(vr / So); rem = vr - (int64_t)bb * So; }
+        const float sc = ld_scalar(p.post_scale, 1.f), sbias = ld_scalar(p.post_b, 0.f);
+        for (int c0 = wg * 8; c0 < Npad; c0 += G * 8) {
+            uint32_t acc[8];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ok) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int co = c0 + e;
+                    if (co < p.Cout) {
+                        const size_t o = ((size_t)bb * p.Cout + co) * So + rem;
+                        float yv = __fmaf_rn(__uint_as_float(acc[e]), sc, sbias);
+                        if (p.bias) yv += __ldg(p.bias + co);
+                        if (p.residual) yv += __ldg(p.residual + o);
+                        if (p.post_act) yv = elu1(yv);
+                        p.y[o] = yv;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    }
+}
+
+}  // namespace vq3d
+#endif  // !VQ3D_EMU
+
+using namespace vq3d;
+
+extern "C" int vq3d_conv3d_tc(const vq3d_conv_desc *d, void *stream) {
+#ifdef VQ3D_EMU
+    (void)d; (void)stream;
+    return fail(VQ3D_ERR_UNSUPPORTED, "conv3d_tc: tensor-core kernels cannot run in the host emulator");
+#else
+    if (!d) return fail(VQ3D_ERR_INVALID, "conv3d_tc: null descriptor");
+    if (!d->x1 || !d->w || !d->y) return fail(VQ3D_ERR_INVALID, "conv3d_tc: null x1/w/y");
+    if (d->C2 > 0 && !d->x2) return fail(VQ3D_ERR_INVALID, "conv3d_tc: C2 > 0 but x2 is NULL");
+    if (d->B < 1 || d->H < 1 || d->W < 1 || d->Z < 1 || d->C1 < 1 || d->C2 < 0 || d->Cout < 1) return fail(VQ3D_ERR_INVALID, "conv3d_tc: bad sizes");
+    if (d->k < 1 || d->k > 4 || (d->stride != 1 && d->stride != 2) || d->pad < 0 || d->pad >= d->k) return fail(VQ3D_ERR_INVALID, "conv3d_tc: unsupported geometry");
+    if (d->pad_circular && (d->pad > d->H || d->pad > d->W || d->pad > d->Z)) return fail(VQ3D_ERR_INVALID, "conv3d_tc: circular padding larger than the input");
+    const int Cin = d->C1 + d->C2;
+    const int64_t Ktot = (int64_t)Cin * d->k * d->k * d->k;
+    if (d->Cout > 256) return fail(VQ3D_ERR_UNSUPPORTED, "conv3d_tc: Cout > 256");
+    if (Ktot < 32 || d->Cout < 8) return fail(VQ3D_ERR_UNSUPPORTED, "conv3d_tc: not GEMM-shaped (K=%lld, N=%d)", (long long)Ktot, d->Cout);
+    TcParams p;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z; p.C1 = d->C1; p.C2 = d->C2; p.Cout = d->Cout;
+    p.k = d->k; p.stride = d->stride; p.pad = d->pad; p.circ = d->pad_circular; p.pre_act = d->pre_act; p.post_act = d->post_act;
+    p.Ho = (d->H + 2 * d->pad - d->k) / d->stride + 1;
+    p.Wo = (d->W + 2 * d->pad - d->k) / d->stride + 1;
+    p.Zo = (d->Z + 2 * d->pad - d->k) / d->stride + 1;
+    if (p.Ho < 1 || p.Wo < 1 || p.Zo < 1) return fail(VQ3D_ERR_INVALID, "conv3d_tc: empty output");
+    p.Npad = (d->Cout + 15) & ~15;
+    p.Ktot = (int)Ktot;
+    p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.bias = d->bias; p.pre_a = d->pre_a; p.pre_b = d->pre_b;
+    p.post_scale = d->post_scale; p.post_b = d->post_b; p.residual = d->residual; p.y = d->y;
+    const int64_t total = (int64_t)p.B * p.Ho * p.Wo * p.Zo;
+    const int64_t tiles = ceil_div(total, kTcM);
+    p.G = tiles >= 2 * kNumSMs ? 2 : 4;      // few tiles: put more gather threads on each
+    const size_t smem = (size_t)kTcStages * ((size_t)kTcM * kTcBK * 2 + (size_t)p.Npad * kTcBK * 2) + 256;
+    return launch("conv3d_tc", conv3d_tc_kernel, dim3((unsigned)tiles), dim3((unsigned)(kTcM * p.G)), smem, stream, p);
+#endif
+}

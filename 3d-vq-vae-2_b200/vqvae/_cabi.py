@@ -44,6 +44,7 @@ SIGNATURES = {
     "vq3d_vq_embed_code": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp]),
     "vq3d_vq_backward": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_double, _fp, _fp]),
     "vq3d_conv3d": (C.c_int, [C.POINTER(ConvDesc), _fp]),
+    "vq3d_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), _fp]),
     "vq3d_upsample2x": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_preact_block": (C.c_int, [C.POINTER(PreactDesc), _fp]),
     "vq3d_preact_stack": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),

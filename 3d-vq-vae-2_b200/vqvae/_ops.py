@@ -21,6 +21,9 @@ class Ops:
 
     def __init__(self, lib: Optional[C.CDLL] = None):
         self._lib = lib
+        # "bf16": GEMM-shaped convolutions (C_in*k^3 >= 64, C_out >= 16) run on the tcgen05 tensor cores
+        # with bf16 operands / fp32 accumulation; "fp32": every convolution on the exact fp32 SIMT kernels
+        self.precision = "bf16"
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
 
@@ -162,9 +165,12 @@ class Ops:
                            post_scale=self._p(self._t(post_scale)), post_b=self._p(self._t(post_b)),
                            residual=self._p(residual), y=self._p(y))
         so = y[0, 0].numel()
-        self._call("conv3d", self.lib.vq3d_conv3d, (C.byref(d), self.stream()),
-                   nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
-                   flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
+        meta = dict(nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
+                    flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
+        if self.precision == "bf16" and Cout >= 16 and Cin * k ** 3 >= 64:
+            if self._call("conv3d_tc", self.lib.vq3d_conv3d_tc, (C.byref(d), self.stream()), allow_unsupported=True, **meta):
+                return y
+        self._call("conv3d", self.lib.vq3d_conv3d, (C.byref(d), self.stream()), **meta)
         return y
 
     def upsample2x(self, x: Tensor, *, pre_act: bool = False, pre_a: Optional[Tensor] = None,

@@ -269,6 +269,12 @@ def run_b200(args):
                          "GBps": round(g[2] / max(g[1], 1e-9) / 1e6, 1), "TFLOPs": round(g[3] / max(g[1], 1e-9) / 1e9, 2)}
                         for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:12]],
         }
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                f.write("op\ttag\tlaunches\tms\tshare\tGB/s(algorithmic)\tTFLOP/s\n")
+                for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+                    f.write(f"{k[0]}\t{k[1]}\t{g[0]}\t{g[1]:.3f}\t{g[1] / prof_total:.4f}\t{g[2] / max(g[1], 1e-9) / 1e6:.1f}\t{g[3] / max(g[1], 1e-9) / 1e9:.2f}\n")
+                f.write(f"TOTAL\t\t{sum(g[0] for g in groups.values())}\t{prof_total:.3f}\n")
         if not args.no_cpu_baseline and world == 1:
             frac = (shape[2] * shape[3] * shape[4]) / (CPU_SAMPLE_SHAPE[2] * CPU_SAMPLE_SHAPE[3] * CPU_SAMPLE_SHAPE[4])
             times, cores = cpu_arm(kind, 3, 1)
@@ -290,6 +296,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="full_512x512x128", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-op CUDA-event table of one eager step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -122,6 +122,14 @@ typedef struct vq3d_conv_desc {
 int vq3d_conv3d(const vq3d_conv_desc *desc, void *stream);
 
 /*
+ * Same contract as vq3d_conv3d, computed as an implicit GEMM on the tcgen05 tensor cores
+ * (bf16 operands, fp32 accumulation in TMEM).  For GEMM-shaped layers only: returns
+ * VQ3D_ERR_UNSUPPORTED when C_in*k^3 < 32, C_out < 8 or C_out > 256 (callers fall back to
+ * vq3d_conv3d).  Results agree with the fp32 kernel to bf16 operand rounding (~1e-2 relative).
+ */
+int vq3d_conv3d_tc(const vq3d_conv_desc *desc, void *stream);
+
+/*
  * nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False) of ResizeConv3D
  * (layers.py:591-597) with the same optional input transform as vq3d_conv_desc:
  * y[B, C, 2H, 2W, 2Z] = upsample(pre_act ? ELU(x + *pre_a) + *pre_b : x + *pre_b).

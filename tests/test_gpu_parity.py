@@ -291,3 +291,51 @@ def test_huber_epilogue_vs_oracle():
         acc = _ops.default().huber_elu_mask(dec.to(DEV), x.to(DEV), torch.tensor(nv, dtype=torch.int32, device=DEV), mask)
         got = float(acc[0] / acc[1])
         assert abs(got - float(ref_recon)) < 1e-6 * max(1.0, abs(float(ref_recon))), (got, float(ref_recon))
+
+
+# ---- tcgen05 implicit-GEMM convolution vs the fp32 SIMT kernel ---------------------------------
+@pytest.mark.parametrize("C1,C2,Cout,k,stride,circ,shape,pre_act,res", [
+    (36, 0, 36, 3, 1, True, (1, 32, 32, 8), True, False),      # conv2 of the Full model's 72-channel stack
+    (72, 0, 36, 1, 1, False, (1, 32, 32, 8), True, False),     # its conv1
+    (36, 0, 72, 1, 1, False, (1, 32, 32, 8), True, True),      # its conv3 (+scale, bias4, residual)
+    (64, 8, 72, 1, 1, False, (1, 32, 32, 8), False, False),    # cat + proj (two sources, conv bias)
+    (64, 0, 64, 3, 1, True, (1, 16, 16, 4), True, False),
+    (128, 0, 128, 3, 1, True, (1, 8, 8, 2), True, False),      # one 128-row tile, wrap on a size-2 axis
+    (128, 0, 128, 4, 2, True, (1, 16, 16, 4), True, False),    # down block conv2
+    (64, 0, 128, 2, 2, False, (1, 16, 16, 4), False, False),   # down block skip (k2 s2, no padding)
+    (9, 0, 9, 3, 1, True, (2, 12, 10, 6), True, False),        # ragged: N padded 9 -> 16, K 243 -> 256, batch 2
+    (16, 0, 24, 3, 1, False, (1, 5, 7, 9), True, True),        # zero padding, odd extents, partial M tile
+])
+def test_tensor_core_conv_matches_fp32(C1, C2, Cout, k, stride, circ, shape, pre_act, res):
+    from vqvae import _ops
+    o = _ops.default()
+    rs = np.random.RandomState(C1 * 31 + Cout + k)
+    B, H, W, Z = shape
+    x1 = torch.from_numpy(rs.standard_normal((B, C1, H, W, Z)).astype(np.float32)).to(DEV)
+    x2 = torch.from_numpy(rs.standard_normal((B, C2, H, W, Z)).astype(np.float32)).to(DEV) if C2 else None
+    w = torch.from_numpy((rs.standard_normal((Cout, C1 + C2, k, k, k)) / np.sqrt((C1 + C2) * k ** 3)).astype(np.float32)).to(DEV)
+    bias = torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).to(DEV) if C2 else None
+    sc = lambda v: torch.tensor([v], dtype=torch.float32, device=DEV)
+    pad = 1 if k >= 3 else 0
+    kw = dict(x2=x2, bias=bias, stride=stride, pad=pad, circular=circ, pre_act=pre_act, pre_a=sc(0.1) if pre_act else None,
+              pre_b=sc(-0.05), post_scale=sc(0.9), post_b=sc(0.02))
+    prev = o.precision
+    try:
+        o.precision = "fp32"
+        ref = o.conv3d(x1, w, **kw)
+        r = torch.randn_like(ref) if res else None
+        ref = o.conv3d(x1, w, residual=r, **kw)
+        o.precision = "bf16"
+        n0 = len(o.profile) if o.profile is not None else None
+        o.profile = []
+        got = o.conv3d(x1, w, residual=r, **kw)
+        torch.cuda.synchronize()
+        assert [e[0] for e in o.profile] == ["conv3d_tc"], "tensor-core path was not taken"
+    finally:
+        o.precision = prev
+        o.profile = None
+    conv_only = ref - (r if res else 0)
+    err = float((got - ref).abs().max())
+    scale = float(conv_only.abs().max())
+    assert err <= 2e-2 * scale, (err, scale)
+    assert float((got - ref).abs().mean()) <= 4e-3 * float(conv_only.abs().mean() + 1e-6)
