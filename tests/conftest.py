@@ -12,6 +12,7 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "g
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "bf16: run the test in the bf16 tensor-core precision mode")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -38,6 +38,17 @@ def close(a, b, rtol=2e-5, atol=2e-6):
     return np.allclose(a.astype(np.float64), b.astype(np.float64), rtol=rtol, atol=atol)
 
 
+@pytest.fixture(autouse=True)
+def _precision(request):
+    """fp32 (exact SIMT kernels everywhere) unless a test asks for the bf16 tensor-core mode."""
+    from vqvae import _ops
+    o = _ops.default()
+    prev = o.precision
+    o.precision = "bf16" if "bf16" in request.keywords else "fp32"
+    yield
+    o.precision = prev
+
+
 def test_native_library_is_loaded():
     from vqvae import _cabi
     lib = _cabi.lib()
@@ -339,3 +350,47 @@ def test_tensor_core_conv_matches_fp32(C1, C2, Cout, k, stride, circ, shape, pre
     scale = float(conv_only.abs().max())
     assert err <= 2e-2 * scale, (err, scale)
     assert float((got - ref).abs().mean()) <= 4e-3 * float(conv_only.abs().mean() + 1e-6)
+
+
+@pytest.mark.bf16
+@pytest.mark.parametrize("name", ["tiny2_preact", "tiny3_preact"])
+def test_model_golden_bf16_tensor_core_mode(name):
+    """Default product mode: GEMM-shaped convs on tcgen05 with bf16 operands.  Tolerance of the
+    north star for BF16 paths: max-abs 1e-2 relative (to the volume's dynamic range), on the
+    teacher-forced decoder; code indices stay bit-exact on identical latents (quantizer is fp32)."""
+    g = load(name)
+    c, m = _golden_model(name)
+    n = c["cfg"]["n_bottleneck_blocks"]
+    sub = (lambda t: t) if c["decoded_full"] else (lambda t: t[..., ::4, ::4, ::4])
+    with torch.no_grad():
+        dec_tf = m.decoder([torch.from_numpy(g[f"eval_quantized_{i}"]).to(DEV) for i in range(n)])
+        ref = g["eval_decoded"]
+        err = np.abs(sub(dec_tf).cpu().numpy() - ref).max()
+        assert err <= 1e-2 * np.abs(ref).max(), (err, np.abs(ref).max())
+        for i, qz in enumerate(m.encoder.quantize):
+            _, _, got = qz(torch.from_numpy(g[f"eval_latent_{i}"]).to(DEV))
+            assert np.array_equal(got.cpu().numpy(), g[f"eval_idx_{i}"])
+        x = portable_volume(c["shape"], c["seed"] + 11).to(DEV)
+        dec, (_, _, idxs) = m(x)
+        mism = [float((idxs[i].cpu().numpy() != g[f"eval_idx_{i}"]).mean()) for i in range(n)]
+        assert max(mism) <= 0.1, mism
+
+
+@pytest.mark.bf16
+def test_full_model_512_bf16_close_to_fp32():
+    """Full model, 512x512x128: the bf16 tensor-core mode against the fp32 mode of the same
+    kernels (teacher-forced through the decoder so a flipped code cannot dominate)."""
+    from vqvae import _ops
+    o = _ops.default()
+    m = _perturbed(full_config_args()).to(DEV)
+    x = O.synthetic_volume((1, 1, 512, 512, 128)).to(DEV)
+    with torch.no_grad():
+        o.precision = "fp32"
+        dec32, (_, q32, idx32) = m(x)
+        o.precision = "bf16"
+        dec16 = m.decoder(q32)
+        _, (_, _, idx16) = m(x)
+    scale = float(dec32.abs().max())
+    assert float((dec16 - dec32).abs().max()) <= 2e-2 * scale
+    assert float((dec16 - dec32).abs().mean()) <= 2e-3 * scale
+    assert float((idx16[0] != idx32[0]).float().mean()) < 0.05
