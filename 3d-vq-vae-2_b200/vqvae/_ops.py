@@ -26,6 +26,7 @@ class Ops:
         self.precision = "bf16"
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
+        self._sync_ws = None         # device scratch for the grid barrier of the persistent stack kernels
 
     # -- plumbing ---------------------------------------------------------------------
     @property
@@ -212,19 +213,37 @@ class Ops:
                         tag=f"{('same', 'down', 'up')[mode]} {Cin}->{Cb}->{Cout} @{H}x{W}x{Z}")
         return y if ok else None
 
+    # (C, Cb) pairs whose 'same' blocks run on the tensor-core stack kernel in bf16 mode
+    TC_STACK_SHAPES = {(8, 4), (16, 8), (18, 9), (32, 16), (64, 32), (72, 36)}
+    TC_STACK_MAX_BLOCKS = 24     # blocks per launch (kTcsMaxBlocks)
+
     def preact_stack(self, x: Tensor, blocks) -> Optional[Tensor]:
-        """n consecutive equal-shape 'same' blocks; None if unsupported."""
+        """n >= 1 consecutive equal-shape 'same' blocks; None if unsupported."""
         x = self._t(x)
         n = len(blocks)
-        y, tmp = torch.empty_like(x), torch.empty_like(x)
+        y = torch.empty_like(x)
+        tmp = torch.empty_like(x) if n > 1 else None
         arr = (_cabi.PreactDesc * n)()
         for i, blk in enumerate(blocks):
             arr[i] = self.preact_desc(x, y, blk, 0)
         B, Cc, H, W, Z = x.shape
         Cb = blocks[0].branch_conv1.weight.shape[0]
+        meta = dict(nbytes=n * 8 * x.numel(), flops=n * 2 * B * H * W * Z * (2 * Cc * Cb + 27 * Cb * Cb),
+                    tag=f"stack{n} {Cc}->{Cb}->{Cc} @{H}x{W}x{Z}")
+        if self.precision == "bf16" and (Cc, Cb) in self.TC_STACK_SHAPES:
+            if self._sync_ws is None or self._sync_ws.device != x.device:
+                self._sync_ws = torch.zeros(16, dtype=torch.int32, device=x.device)
+            launches = -(-n // self.TC_STACK_MAX_BLOCKS)
+            if self._call("preact_stack_tc", self.lib.vq3d_preact_stack_tc,
+                          (arr, n, self._p(tmp), self._p(self._sync_ws), self.stream()), allow_unsupported=True,
+                          kernels=launches, **meta):
+                return y
+        if n == 1:
+            d = arr[0]
+            return y if self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()),
+                                   allow_unsupported=True, **meta) else None
         ok = self._call("preact_stack", self.lib.vq3d_preact_stack, (arr, n, self._p(tmp), self.stream()), allow_unsupported=True,
-                        kernels=n, nbytes=n * 8 * x.numel(), flops=n * 2 * B * H * W * Z * (2 * Cc * Cb + 27 * Cb * Cb),
-                        tag=f"stack{n} {Cc}->{Cb}->{Cc} @{H}x{W}x{Z}")
+                        kernels=n, **meta)
         return y if ok else None
 
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):

@@ -231,7 +231,7 @@ class BlockSequence(nn.Sequential):
             if _stackable(m):
                 while j + 1 < len(mods) and _stackable(mods[j + 1]) and _same_shape(m, mods[j + 1]):
                     j += 1
-            if j > i:
+            if j > i or _stackable(m):
                 _no_conv_backward(*chain.from_iterable(b.parameters() for b in mods[i:j + 1]))
                 y = ops().preact_stack(x, mods[i:j + 1])
                 if y is not None:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 1
+#define VQ3D_ABI_VERSION 2
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -171,6 +171,16 @@ int vq3d_preact_block(const vq3d_preact_desc *desc, void *stream);
  * blocks[n-1].y (output); tmp is a scratch activation buffer of the same size (ping-pong).
  */
 int vq3d_preact_stack(const vq3d_preact_desc *blocks, int n, float *tmp, void *stream);
+
+/*
+ * Same contract as vq3d_preact_stack with the k3 convolution on the tcgen05 tensor cores (bf16
+ * operands, fp32 accumulation in TMEM) and up to 24 blocks per launch: persistent CTAs pass a grid
+ * barrier between consecutive blocks (cooperative launch).  sync_ws: 4 bytes of device scratch for
+ * that barrier (the call zeroes it in-stream).  tmp may be NULL when n == 1.  Results agree with the
+ * fp32 kernels to bf16 operand rounding.  Returns VQ3D_ERR_UNSUPPORTED when no instantiation covers
+ * (Cin, Cb) -- callers fall back to vq3d_preact_stack.
+ */
+int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, float *tmp, uint32_t *sync_ws, void *stream);
 
 /*
  * Loss epilogue of VQVAE.loc_metric, model.py:120-152, fused: loc = ELU(decoded), zero where
