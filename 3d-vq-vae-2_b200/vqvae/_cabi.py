@@ -48,7 +48,8 @@ SIGNATURES = {
     "vq3d_upsample2x": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_preact_block": (C.c_int, [C.POINTER(PreactDesc), _fp]),
     "vq3d_preact_stack": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),
-    "vq3d_preact_stack_tc": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp, _fp]),
+    "vq3d_preact_stack_tc_workspace": (C.c_size_t, [C.POINTER(PreactDesc)]),
+    "vq3d_preact_stack_tc": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, C.c_size_t, _fp]),
     "vq3d_huber_elu_mask": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
 }
 

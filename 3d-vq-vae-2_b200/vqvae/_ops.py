@@ -26,7 +26,7 @@ class Ops:
         self.precision = "bf16"
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
-        self._sync_ws = None         # device scratch for the grid barrier of the persistent stack kernels
+        self._ws = {}                # device -> uint8 workspace of the persistent stack kernels (grown on demand)
 
     # -- plumbing ---------------------------------------------------------------------
     @property
@@ -65,6 +65,15 @@ class Ops:
                 e1.record()
                 prof.append((name, tag, nbytes, flops, e0, e1))
         return ok
+
+    def _workspace(self, nbytes: int, device) -> Tensor:
+        """Scratch for kernels that need one; work on a stream is ordered, so one buffer per device is
+        enough (its contents never outlive a call)."""
+        ws = self._ws.get(device)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+            self._ws[device] = ws
+        return ws
 
     def _check(self, rc: int, allow_unsupported: bool = False) -> bool:
         if rc == _cabi.OK:
@@ -231,13 +240,13 @@ class Ops:
         meta = dict(nbytes=n * 8 * x.numel(), flops=n * 2 * B * H * W * Z * (2 * Cc * Cb + 27 * Cb * Cb),
                     tag=f"stack{n} {Cc}->{Cb}->{Cc} @{H}x{W}x{Z}")
         if self.precision == "bf16" and (Cc, Cb) in self.TC_STACK_SHAPES:
-            if self._sync_ws is None or self._sync_ws.device != x.device:
-                self._sync_ws = torch.zeros(16, dtype=torch.int32, device=x.device)
-            launches = -(-n // self.TC_STACK_MAX_BLOCKS)
-            if self._call("preact_stack_tc", self.lib.vq3d_preact_stack_tc,
-                          (arr, n, self._p(tmp), self._p(self._sync_ws), self.stream()), allow_unsupported=True,
-                          kernels=launches, **meta):
-                return y
+            need = self.lib.vq3d_preact_stack_tc_workspace(C.byref(arr[0]))
+            if need:
+                ws = self._workspace(need, x.device)
+                launches = -(-n // self.TC_STACK_MAX_BLOCKS)
+                if self._call("preact_stack_tc", self.lib.vq3d_preact_stack_tc,
+                              (arr, n, self._p(ws), ws.numel(), self.stream()), allow_unsupported=True, kernels=launches, **meta):
+                    return y
         if n == 1:
             d = arr[0]
             return y if self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()),

@@ -22,6 +22,7 @@
 #ifndef VQVAE3D_B200_H
 #define VQVAE3D_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -173,14 +174,18 @@ int vq3d_preact_block(const vq3d_preact_desc *desc, void *stream);
 int vq3d_preact_stack(const vq3d_preact_desc *blocks, int n, float *tmp, void *stream);
 
 /*
- * Same contract as vq3d_preact_stack with the k3 convolution on the tcgen05 tensor cores (bf16
- * operands, fp32 accumulation in TMEM) and up to 24 blocks per launch: persistent CTAs pass a grid
- * barrier between consecutive blocks (cooperative launch).  sync_ws: 4 bytes of device scratch for
- * that barrier (the call zeroes it in-stream).  tmp may be NULL when n == 1.  Results agree with the
+ * Same contract as vq3d_preact_stack (n >= 1 equal-shape 'same' blocks, layers.py:492-494,566-569) with
+ * the k3 convolution on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM) and up to
+ * 24 blocks per launch: persistent warp-specialised CTAs pass a grid barrier between consecutive
+ * blocks (cooperative launch).  blocks[0].x is the input, blocks[n-1].y the output (updated in place by
+ * blocks 1..n-1; it must not alias the input).  ws: device workspace of at least
+ * vq3d_preact_stack_tc_workspace(&blocks[0]) bytes, 256-byte aligned (bf16 intermediate of the next
+ * block + the barrier counter); contents need not be preserved between calls.  Results agree with the
  * fp32 kernels to bf16 operand rounding.  Returns VQ3D_ERR_UNSUPPORTED when no instantiation covers
- * (Cin, Cb) -- callers fall back to vq3d_preact_stack.
+ * (Cin, Cb) -- callers fall back to vq3d_preact_stack; the workspace query then returns 0.
  */
-int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, float *tmp, uint32_t *sync_ws, void *stream);
+size_t vq3d_preact_stack_tc_workspace(const vq3d_preact_desc *first_block);
+int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_bytes, void *stream);
 
 /*
  * Loss epilogue of VQVAE.loc_metric, model.py:120-152, fused: loc = ELU(decoded), zero where
