@@ -14,18 +14,24 @@
 // cp.async.bulk (UBLKCP) straight into the UMMA canonical K-major no-swizzle layout
 // ([chunk][box voxel L][16 B], L = (h*IW + w)*IZ + z).
 //
-//   producer warp   waits for a free A buffer, issues the row copies of the next tile (mbarrier tx)
-//   3 MMA lanes     the 27 taps of conv2 = 27 accumulating tcgen05.mma (M128 x N=CBP x K16 per 16
+//   warp 0 (1 lane) the 27 taps of conv2 = 27 accumulating tcgen05.mma (M128 x N=CBP x K16 per 16
 //                   branch channels) per M-block of 128 CONSECUTIVE box indices: the A operand of tap
 //                   (kh,kw,kz) is the same smem array shifted by ((kh-1)*IW + (kw-1))*IZ + (kz-1)
 //                   rows -- a descriptor start-address change, no im2col.  Rows that fall on halo
 //                   positions compute garbage that is never stored.  fp32 accumulators in TMEM.
-//   consumer warps  tcgen05.ld (lane = voxel) -> ELU -> conv3 -> *scale + b4 + x -> store y (fp32,
-//                   the reference's planar layout, in place) -> ELU -> conv1 of the next block -> ELU ->
-//                   bf16 -> t1 workspace.
-// A buffers and TMEM accumulators are double buffered, so copies, MMAs and the SIMT epilogue of
-// neighbouring tiles overlap inside the single resident CTA (kernels that use tcgen05 get one CTA
-// per SM from this driver).  Between blocks every CTA passes a grid barrier (cooperative launch).
+//   warps 1..3      producers: wait for a free A buffer, issue the row copies of the next tile
+//   consumer warps  in groups of 4 (one per TMEM lane quarter), one M-block at a time per group:
+//                   tcgen05.ld D2 (lane = voxel) -> ELU -> bf16 -> smem -> tcgen05.mma with W3 (conv3)
+//                   -> tcgen05.ld -> *scale + b4 + x -> store y (fp32, the reference's planar layout,
+//                   in place) -> ELU -> bf16 -> smem -> tcgen05.mma with the NEXT block's W1 (conv1)
+//                   -> tcgen05.ld -> ELU -> bf16 -> t1 workspace.  The two pointwise MMAs are issued
+//                   by the group's own leader lane; SIMT only does ELU / convert / the residual add.
+// Weights are converted once per call by a small prep kernel into bf16 B-operand images; a block's
+// images (conv2, conv3, next conv1) are one contiguous bulk copy into shared memory.
+// A buffers and TMEM accumulators are double buffered where they fit, so copies, MMAs and the
+// epilogue of neighbouring tiles overlap inside the single resident CTA (kernels that use tcgen05
+// get one CTA per SM from this driver).  Between blocks every CTA passes a grid barrier
+// (cooperative launch).
 #include "vq3d_rt.h"
 
 #ifndef VQ3D_EMU
@@ -35,8 +41,9 @@
 namespace vq3d {
 
 constexpr int kTcsMaxBlocks = 24;          // blocks per launch (kernel parameter space)
-constexpr int kTcsAuxWarps = 4;            // warp 0 producer, warps 1..3 MMA issuers
-constexpr int kTcsMmaWarps = 3;
+constexpr int kTcsAuxWarps = 4;            // warp 0 MMA issuer, warps 1..3 producers
+constexpr int kTcsProdWarps = 3;
+constexpr int kTcsMaxMB = 16;              // M-blocks per tile
 
 struct TcsBlock {
     const float *w1, *w2, *w3;
@@ -55,6 +62,7 @@ struct TcsParams {
     const float *x;                        // input of block 0 (may alias y)
     float *y;                              // output of every block (updated in place from block 1 on)
     uint4 *t1[2];                          // bf16 t1 ping-pong: [B][NCH][H][W][Z+2] 16-byte units
+    const unsigned char *wimg;             // per block [W1 | W2 | W3] bf16 B-operand images (+ one trailing W1 slot)
     TcsBlock blk[kTcsMaxBlocks];
 };
 
@@ -66,6 +74,7 @@ __device__ __forceinline__ void mbarrier_init(uint64_t *bar, uint32_t count) {
 
 __device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = s_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -73,6 +82,13 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
         if (ok) return;
     }
     __trap();   // a lost arrival becomes a launch error, never a hung GPU
+}
+
+__device__ __forceinline__ bool mbarrier_test(uint64_t *bar, uint32_t parity) {     // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 __device__ __forceinline__ void mbarrier_arrive(uint64_t *bar) {
@@ -103,6 +119,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 
 __device__ __forceinline__ void umma_commit_to(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+
+// one lane of a converged warp (the compiler keeps operands in uniform registers inside the branch)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
+
+// ELU(alpha = 1) without predicates: max(v, 2^(min(v,0)*log2 e) - 1)   (e^v - 1 >= v for v <= 0)
+__device__ __forceinline__ float elu_bl(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.0f) * 1.4426950408889634f));
+    return fmaxf(v, e - 1.0f);
 }
 
 __device__ __forceinline__ uint32_t bf16x2(float lo, float hi) {
@@ -148,88 +178,113 @@ __device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int tar
 
 constexpr int rup(int v, int m) { return (v + m - 1) / m * m; }
 
-// debug timeline (VQ3D_TC_TRACE=1): CTA 0 stamps %globaltimer for blocks 1 and 2 into 9 slots each
+// debug timeline (VQ3D_TC_TRACE=1): CTA 0 stamps %globaltimer of block 1 into 16 slots
 __device__ __forceinline__ void tc_trace(unsigned long long *tr, int blk, int ev) {
-    if (tr != nullptr && blockIdx.x == 0 && (blk == 1 || blk == 2)) {
+    if (tr != nullptr && blockIdx.x == 0 && blk == 1) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        tr[(blk - 1) * 9 + ev] = t;
+        tr[ev] = t;
     }
 }
 
 template <int C, int CB>
 struct TcsCfg {
-    static constexpr int CBP = rup(CB, 16);            // MMA N and K extent
-    static constexpr int NK = CBP / 16;
-    static constexpr int NCH = CBP / 8;                // 8-channel (16 B) chunks per voxel
-    static constexpr int CB4 = rup(CB, 4), C4 = rup(C, 4);
-    static constexpr int OC = C <= 32 ? C : 24;        // conv3 output channels per register pass
+    static constexpr int CBP = rup(CB, 16);            // branch channels padded: N and K of conv2, K of conv3, N of conv1
+    static constexpr int CP = rup(C, 16);              // block channels padded: N of conv3, K of conv1
+    static constexpr int NK2 = CBP / 16, NK1 = CP / 16;
+    static constexpr int NCH = CBP / 8, CPCH = CP / 8; // 8-channel (16 B) chunks per voxel
+    static constexpr int CB4 = rup(CB, 4);
     static constexpr uint32_t W2TAP = (uint32_t)CBP * CBP * 2;   // bytes of one tap's B operand
     static constexpr uint32_t W2BYTES = 27u * W2TAP;
-    static constexpr uint32_t LBO_B = (uint32_t)CBP * 16;
-    static constexpr size_t w_floats = (size_t)C * CB4 + (size_t)CB * C4;
-    static size_t smem_bytes(int NLA) { return 128 + W2BYTES + 2 * (size_t)NCH * NLA * 16 + w_floats * 4; }
+    static constexpr uint32_t WPBYTES = (uint32_t)CP * CBP * 2;  // bytes of a pointwise (conv1 or conv3) B operand
+    static constexpr uint32_t WIMG = W2BYTES + 2 * WPBYTES;      // per block image [W1 | W2 | W3]
+    static constexpr uint32_t LBO_B2 = (uint32_t)CBP * 16;       // conv2 and conv1 images: CBP rows per k-chunk
+    static constexpr uint32_t LBO_B3 = (uint32_t)CP * 16;        // conv3 image: CP rows per k-chunk
+    static constexpr uint32_t SAP = (uint32_t)CP * 256;          // per consumer group staging: 128 rows x CP bf16 (A3 aliases A1)
+    static size_t smem_bytes(int NLA, int nbuf, int ng) {
+        return 128 + WIMG + (size_t)nbuf * NCH * NLA * 16 + (size_t)ng * SAP;
+    }
 };
 
-// pointwise first half of a block from the (fp32) values of one voxel, streamed channel by channel
+// ELU(v + a) + b for 16 accumulator columns, packed to two 16-byte bf16 chunks; columns >= nreal become 0
+__device__ __forceinline__ void elu_pack16(const float *v, float a, float b, int nreal, uint4 &lo, uint4 &hi) {
+    float t[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = j < nreal ? elu_bl(v[j] + a) + b : 0.0f;
+    lo.x = bf16x2(t[0], t[1]); lo.y = bf16x2(t[2], t[3]); lo.z = bf16x2(t[4], t[5]); lo.w = bf16x2(t[6], t[7]);
+    hi.x = bf16x2(t[8], t[9]); hi.y = bf16x2(t[10], t[11]); hi.z = bf16x2(t[12], t[13]); hi.w = bf16x2(t[14], t[15]);
+}
+
+// weights -> bf16 B-operand images (K-major, no swizzle: [k-chunk of 8][row n][16 B]), once per call
 template <int C, int CB>
-struct T1Acc {
-    static constexpr int CBP = TcsCfg<C, CB>::CBP, CB4 = TcsCfg<C, CB>::CB4, NCH = TcsCfg<C, CB>::NCH;
-    float acc[CBP];
-    __device__ __forceinline__ void clear() {
+__global__ void __launch_bounds__(256)
+tcs_prep_kernel(const __grid_constant__ TcsParams p, unsigned char *wimg) {
+    using Cfg = TcsCfg<C, CB>;
+    constexpr int CBP = Cfg::CBP, CP = Cfg::CP, NCH = Cfg::NCH, CPCH = Cfg::CPCH;
+    const int blk = blockIdx.y;                         // 0..nblocks (the last one is the zero W1 slot only)
+    unsigned char *img = wimg + (size_t)blk * Cfg::WIMG;
+    const bool real = blk < p.nblocks;
+    const TcsBlock &bp = p.blk[real ? blk : 0];
+    const int n1 = CPCH * CBP, n2 = 27 * NCH * CBP, n3 = NCH * CP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + (real ? n2 + n3 : 0); i += gridDim.x * blockDim.x) {
+        float wv[8];
+        unsigned char *dst;
+        if (i < n1) {                                   // W1: rows n = cb, K = c
+            const int n = i % CBP, kc = i / CBP;
 #pragma unroll
-        for (int c = 0; c < CBP; ++c) acc[c] = 0.0f;
-    }
-    // v = value of input channel ci (before ELU); sw1 = [C][CB4] transposed conv1 weights
-    __device__ __forceinline__ void add(int ci, float v, const float *sw1, float b1a, float b1b) {
-        const float a = elu1(v + b1a) + b1b;
-        const float4 *wr = reinterpret_cast<const float4 *>(sw1 + ci * CB4);
+            for (int e = 0; e < 8; ++e) {
+                const int c = kc * 8 + e;
+                wv[e] = (real && n < CB && c < C) ? __ldg(bp.w1 + n * C + c) : 0.0f;
+            }
+            dst = img + (size_t)kc * Cfg::LBO_B2 + (size_t)n * 16;
+        } else if (i < n1 + n2) {                       // W2: per tap, rows n = co, K = ci
+            const int j = i - n1;
+            const int n = j % CBP, kc = (j / CBP) % NCH, t = j / (CBP * NCH);
 #pragma unroll
-        for (int j = 0; j < CB4 / 4; ++j) {
-            const float4 w = wr[j];
-            acc[4 * j + 0] = __fmaf_rn(w.x, a, acc[4 * j + 0]);
-            if (4 * j + 1 < CB) acc[4 * j + 1] = __fmaf_rn(w.y, a, acc[4 * j + 1]);
-            if (4 * j + 2 < CB) acc[4 * j + 2] = __fmaf_rn(w.z, a, acc[4 * j + 2]);
-            if (4 * j + 3 < CB) acc[4 * j + 3] = __fmaf_rn(w.w, a, acc[4 * j + 3]);
+            for (int e = 0; e < 8; ++e) {
+                const int ci = kc * 8 + e;
+                wv[e] = (n < CB && ci < CB) ? __ldg(bp.w2 + ((size_t)n * CB + ci) * 27 + t) : 0.0f;
+            }
+            dst = img + Cfg::WPBYTES + (size_t)t * Cfg::W2TAP + (size_t)kc * Cfg::LBO_B2 + (size_t)n * 16;
+        } else {                                        // W3: rows n = c, K = cb
+            const int j = i - n1 - n2;
+            const int n = j % CP, kc = j / CP;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int cb = kc * 8 + e;
+                wv[e] = (n < C && cb < CB) ? __ldg(bp.w3 + n * CB + cb) : 0.0f;
+            }
+            dst = img + Cfg::WPBYTES + Cfg::W2BYTES + (size_t)kc * Cfg::LBO_B3 + (size_t)n * 16;
         }
+        uint4 pk;
+        pk.x = bf16x2(wv[0], wv[1]); pk.y = bf16x2(wv[2], wv[3]); pk.z = bf16x2(wv[4], wv[5]); pk.w = bf16x2(wv[6], wv[7]);
+        *reinterpret_cast<uint4 *>(dst) = pk;
     }
-    // ELU, bf16, store into the z-padded chunk-planar workspace (+ the circular depth halo copies)
-    __device__ __forceinline__ void store(uint4 *t1, int b, int oh, int ow, int oz, int H, int W, int Z, float b2a, float b2b) {
-#pragma unroll
-        for (int c = 0; c < CBP; ++c) acc[c] = c < CB ? elu1(acc[c] + b2a) + b2b : 0.0f;
-#pragma unroll
-        for (int kc = 0; kc < NCH; ++kc) {
-            uint4 pk;
-            pk.x = bf16x2(acc[8 * kc + 0], acc[8 * kc + 1]); pk.y = bf16x2(acc[8 * kc + 2], acc[8 * kc + 3]);
-            pk.z = bf16x2(acc[8 * kc + 4], acc[8 * kc + 5]); pk.w = bf16x2(acc[8 * kc + 6], acc[8 * kc + 7]);
-            uint4 *row = t1 + ((((size_t)b * NCH + kc) * H + oh) * W + ow) * (size_t)(Z + 2);
-            row[oz + 1] = pk;
-            if (oz == 0) row[Z + 1] = pk;
-            if (oz == Z - 1) row[0] = pk;
-        }
-    }
-};
+}
 
-template <int C, int CB, int NCW>
+template <int C, int CB, int NCW, int NBUF>
 __global__ void __launch_bounds__((kTcsAuxWarps + NCW) * 32, 1)
 preact_tc_kernel(const __grid_constant__ TcsParams p) {
     using Cfg = TcsCfg<C, CB>;
-    constexpr int CBP = Cfg::CBP, NK = Cfg::NK, NCH = Cfg::NCH, CB4 = Cfg::CB4, C4 = Cfg::C4, OC = Cfg::OC;
+    constexpr int CBP = Cfg::CBP, CP = Cfg::CP, NK2 = Cfg::NK2, NK1 = Cfg::NK1, NCH = Cfg::NCH, CB4 = Cfg::CB4;
     constexpr int NT = (kTcsAuxWarps + NCW) * 32;
     constexpr int NG = NCW / 4;
     static_assert(NCW % 4 == 0 && NCW >= 4, "consumer warps come in groups of 4 (TMEM lane quarters)");
+    static_assert(NBUF == 1 || NBUF == 2, "one or two A / accumulator buffers");
     VQ3D_DYN_SMEM(unsigned char, smem_raw);
-    __shared__ __align__(8) uint64_t bar_full[2], bar_sa_empty[2], bar_tm_full[2], bar_tm_empty[2];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_sa_empty[2], bar_tm_empty[2], bar_w, bar_g[NG], bar_mb[2][kTcsMaxMB];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t base = (s_u32(smem_raw) + 127u) & ~127u;
     unsigned char *smem = smem_raw + (base - s_u32(smem_raw));
-    unsigned char *sW2 = smem;                                        // 27 x [NCH][CBP rows][16 B]
+    // [W2 | W3 | W1next] (one contiguous image copy) | A buffers | per-group staging
+    const uint32_t sW2_addr = base, sW3_addr = base + Cfg::W2BYTES, sW1_addr = sW3_addr + Cfg::WPBYTES;
     const uint32_t lbo_a = (uint32_t)p.NLA * 16;
     const uint32_t sa_bytes = (uint32_t)NCH * lbo_a;                  // one A buffer: [NCH][NLA][16 B]
-    float *sw3 = reinterpret_cast<float *>(smem + Cfg::W2BYTES + 2 * (size_t)sa_bytes);   // [CB][C4]  this block
-    float *sw1n = sw3 + CB * C4;                                      // [C][CB4]  NEXT block's conv1
-    const uint32_t sW2_addr = base, sA_addr = base + Cfg::W2BYTES;
+    const uint32_t sA_addr = base + Cfg::WIMG;
+    unsigned char *sA = smem + Cfg::WIMG;
+    const uint32_t sAp_addr = sA_addr + NBUF * sa_bytes;
+    unsigned char *sAp = sA + (size_t)NBUF * sa_bytes;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -237,30 +292,35 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
     }
     if (tid == 32) {
         for (int s = 0; s < 2; ++s) {
-            mbarrier_init(&bar_full[s], 1);
-            mbarrier_init(&bar_sa_empty[s], kTcsMmaWarps);
-            mbarrier_init(&bar_tm_full[s], kTcsMmaWarps);
+            mbarrier_init(&bar_full[s], kTcsProdWarps);
+            mbarrier_init(&bar_sa_empty[s], 1);
+            for (int m = 0; m < kTcsMaxMB; ++m) mbarrier_init(&bar_mb[s][m], 1);
             mbarrier_init(&bar_tm_empty[s], NCW);
         }
+        mbarrier_init(&bar_w, 1);
+        for (int g = 0; g < NG; ++g) mbarrier_init(&bar_g[g], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_slot;
+    const uint32_t tmem_grp = tmem_d + (uint32_t)(NBUF * p.NMB * CBP);    // per group: D3 (CP columns) then D1 (CBP columns)
     // D fp32 (1<<4), A/B bf16 (1<<7, 1<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CBP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CBP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = CBP
+    const uint32_t idesc_c = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // N = CP
 
     const int H = p.H, W = p.W, Z = p.Z;
     const int64_t S = (int64_t)H * W * Z;
     const int IW = p.IW, IZ = p.IZ, IWZ = p.IW * p.IZ;
 
-    // ---- prologue: t1 of block 0 from x (pointwise, grid-stride over voxels) -----------------------
+    // ---- prologue: t1 of block 0 from x (pointwise SIMT, grid-stride over voxels; fp32 weights in the A area) ----
     {
         const TcsBlock &b0 = p.blk[0];
+        float *sw1 = reinterpret_cast<float *>(sA);          // [C][CB4]
         for (int i = tid; i < C * CB4; i += NT) {
             const int cb = i % CB4, ci = i / CB4;
-            sw1n[i] = cb < CB ? __ldg(b0.w1 + cb * C + ci) : 0.0f;
+            sw1[i] = cb < CB ? __ldg(b0.w1 + cb * C + ci) : 0.0f;
         }
         const float b1a = ld_scalar(b0.b1a, 0.f), b1b = ld_scalar(b0.b1b, 0.f), b2a = ld_scalar(b0.b2a, 0.f), b2b = ld_scalar(b0.b2b, 0.f);
         __syncthreads();
@@ -272,89 +332,80 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
             const int64_t hw = r / Z;
             const int ow = (int)(hw % W), oh = (int)(hw / W);
             const float *px = p.x + (size_t)b * C * S + r;
-            T1Acc<C, CB> t;
-            t.clear();
+            float acc[CBP];
+#pragma unroll
+            for (int c = 0; c < CBP; ++c) acc[c] = 0.0f;
 #pragma unroll(C <= 32 ? C : 8)
-            for (int ci = 0; ci < C; ++ci) t.add(ci, __ldcg(px + (size_t)ci * S), sw1n, b1a, b1b);
-            t.store(p.t1[0], b, oh, ow, oz, H, W, Z, b2a, b2b);
+            for (int ci = 0; ci < C; ++ci) {
+                const float a = elu1(__ldcg(px + (size_t)ci * S) + b1a) + b1b;
+                const float4 *wr = reinterpret_cast<const float4 *>(sw1 + ci * CB4);
+#pragma unroll
+                for (int j = 0; j < CB4 / 4; ++j) {
+                    const float4 w = wr[j];
+                    acc[4 * j + 0] = __fmaf_rn(w.x, a, acc[4 * j + 0]);
+                    acc[4 * j + 1] = __fmaf_rn(w.y, a, acc[4 * j + 1]);
+                    acc[4 * j + 2] = __fmaf_rn(w.z, a, acc[4 * j + 2]);
+                    acc[4 * j + 3] = __fmaf_rn(w.w, a, acc[4 * j + 3]);
+                }
+            }
+#pragma unroll
+            for (int ks = 0; ks < NK2; ++ks) {
+                uint4 lo, hi;
+                elu_pack16(acc + 16 * ks, b2a, b2b, CB - 16 * ks, lo, hi);
+                uint4 *r0 = p.t1[0] + ((((size_t)b * NCH + 2 * ks) * H + oh) * W + ow) * (size_t)(Z + 2);
+                uint4 *r1 = r0 + (size_t)H * W * (Z + 2);
+                r0[oz + 1] = lo; r1[oz + 1] = hi;
+                if (oz == 0) { r0[Z + 1] = lo; r1[Z + 1] = hi; }
+                if (oz == Z - 1) { r0[0] = lo; r1[0] = hi; }
+            }
         }
         grid_barrier(p.sync, gridDim.x);
     }
 
     // tiles of this CTA (the same sequence in every block and for every role)
     const int my_tiles = p.ntiles > (int)blockIdx.x ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    uint32_t kt = 0;          // tiles processed by this CTA so far: buffer = kt & 1, use count = kt >> 1
+    uint32_t kt = 0;          // tiles processed by this CTA so far: buffer = kt % NBUF, use count = kt / NBUF
+    uint32_t gph = 0;         // parity of this consumer group's pointwise-MMA barrier
 
     for (int blk = 0; blk < p.nblocks; ++blk) {
         const TcsBlock &bp = p.blk[blk];
         const bool has_next = blk + 1 < p.nblocks;
         if (tid == 0) tc_trace(p.trace, blk, 0);
-        // ---- weights of this block (conv2 as the B operand, conv3) and of the next block's conv1 -----
-        for (int i = tid; i < CB * C4; i += NT) {
-            const int c = i % C4, cb = i / C4;
-            sw3[i] = c < C ? __ldg(bp.w3 + c * CB + cb) : 0.0f;
-        }
-        if (has_next) {
-            const float *w1n = p.blk[blk + 1].w1;
-            for (int i = tid; i < C * CB4; i += NT) {
-                const int cb = i % CB4, ci = i / CB4;
-                sw1n[i] = cb < CB ? __ldg(w1n + cb * C + ci) : 0.0f;
-            }
-        }
-        for (int i = tid; i < 27 * NCH * CBP; i += NT) {
-            const int n = i % CBP, kc = (i / CBP) % NCH, t = i / (CBP * NCH);
-            float wv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int ci = kc * 8 + e;
-                wv[e] = (n < CB && ci < CB) ? __ldg(bp.w2 + ((size_t)n * CB + ci) * 27 + t) : 0.0f;
-            }
-            uint4 pk;
-            pk.x = bf16x2(wv[0], wv[1]); pk.y = bf16x2(wv[2], wv[3]); pk.z = bf16x2(wv[4], wv[5]); pk.w = bf16x2(wv[6], wv[7]);
-            *reinterpret_cast<uint4 *>(sW2 + (size_t)t * Cfg::W2TAP + (size_t)kc * Cfg::LBO_B + (size_t)n * 16) = pk;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // sW2 written by the generic proxy, read by the tensor core
-        __syncthreads();
-        if (tid == 0) tc_trace(p.trace, blk, 1);
-
         const uint4 *t1src = p.t1[blk & 1];
         uint4 *t1dst = p.t1[(blk + 1) & 1];
         const float *resid = blk == 0 ? p.x : p.y;
 
         if (warp == 0) {
-            // ================= producer: haloed box rows -> A buffer (bulk copies) =======================
-            const int nrows = p.IH * IW;
-            asm volatile("fence.proxy.async;" ::: "memory");     // t1 was written with generic-proxy stores (other CTAs, before the barrier)
-            for (int i = 0; i < my_tiles; ++i) {
-                const uint32_t k = kt + (uint32_t)i, s = k & 1u, u = k >> 1;
-                int t = (int)blockIdx.x + i * (int)gridDim.x;
-                const int twi = t % p.ntw; t /= p.ntw;
-                const int thi = t % p.nth; t /= p.nth;
-                const int b = t, oh0 = thi * p.th, ow0 = twi * p.tw;
-                mbarrier_wait(&bar_sa_empty[s], (u & 1u) ^ 1u);
-                if (lane == 0) mbarrier_arrive_expect_tx(&bar_full[s], (uint32_t)p.NL * NCH * 16u);
-                __syncwarp();
-                const uint32_t row_bytes = (uint32_t)IZ * 16u;
-                for (int r = lane; r < nrows * NCH; r += 32) {
-                    const int kc = r / nrows, rr = r - kc * nrows;
-                    const int lh = rr / IW, lw = rr - lh * IW;
-                    const int gh = pmodi(oh0 - 1 + lh, H), gw = pmodi(ow0 - 1 + lw, W);
-                    const uint4 *src = t1src + ((((size_t)b * NCH + kc) * H + gh) * W + gw) * (size_t)(Z + 2);
-                    bulk_g2s(sA_addr + s * sa_bytes + (uint32_t)kc * lbo_a + (uint32_t)rr * row_bytes, src, row_bytes, &bar_full[s]);
+            // ================= weights (one image copy) + MMA issue for conv2 (warp 0, one elected lane) ==========
+            if (elect_one()) {
+                const unsigned char *src = p.wimg + (size_t)blk * Cfg::WIMG + Cfg::WPBYTES;    // [W2 | W3 | W1 of blk+1]
+                mbarrier_arrive_expect_tx(&bar_w, Cfg::WIMG);
+                for (uint32_t o = 0; o < Cfg::WIMG; o += 32768u) {
+                    const uint32_t n = Cfg::WIMG - o < 32768u ? Cfg::WIMG - o : 32768u;
+                    bulk_g2s(sW2_addr + o, src + o, n, &bar_w);
                 }
-                if (i == 0 && lane == 0) tc_trace(p.trace, blk, 2);
             }
-        } else if (warp < kTcsAuxWarps) {
-            // ================= MMA issuers: lane 0 of warps 1..3, M-blocks round-robin ====================
-            if (lane == 0) {
-                for (int i = 0; i < my_tiles; ++i) {
-                    const uint32_t k = kt + (uint32_t)i, s = k & 1u, u = k >> 1;
-                    mbarrier_wait(&bar_full[s], u & 1u);
-                    mbarrier_wait(&bar_tm_empty[s], (u & 1u) ^ 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (i == 0 && warp == 1) tc_trace(p.trace, blk, 3);
-                    const uint32_t a_base = sA_addr + s * sa_bytes;
-                    for (int mb = warp - 1; mb < p.NMB; mb += kTcsMmaWarps) {
+            __syncwarp();
+            mbarrier_wait(&bar_w, (uint32_t)blk & 1u);
+            if (lane == 0) tc_trace(p.trace, blk, 1);
+            // conv2: one batch of 27*NK2 MMAs per M-block, each committed to its own barrier so the consumers
+            // can start on M-block 0 while the rest of the tile is still in the pipe.  The tensor pipe
+            // executes in issue order and the consumer groups issue their pointwise MMAs themselves, so
+            // the queue is kept short: a batch is only issued once the batch two before it has completed.
+            uint64_t *pace_bar[2] = {nullptr, nullptr};      // barriers of the two most recently issued batches
+            uint32_t pace_par[2] = {0, 0};
+            for (int i = 0; i < my_tiles; ++i) {
+                const uint32_t k = kt + (uint32_t)i, s = k % NBUF, u = k / NBUF;
+                mbarrier_wait(&bar_full[s], u & 1u);
+                mbarrier_wait(&bar_tm_empty[s], (u & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (i == 0 && lane == 0) tc_trace(p.trace, blk, 3);
+                const uint32_t a_base = sA_addr + s * sa_bytes;
+                for (int mb = 0; mb < p.NMB; ++mb) {
+                    if (pace_bar[0] != nullptr) mbarrier_wait(pace_bar[0], pace_par[0]);     // at most two batches queued in the pipe
+                    pace_bar[0] = pace_bar[1]; pace_par[0] = pace_par[1];
+                    pace_bar[1] = &bar_mb[s][mb]; pace_par[1] = u & 1u;
+                    if (elect_one()) {
                         const uint32_t row0 = (uint32_t)(p.L0 + mb * 128);
                         const uint32_t d_addr = tmem_d + (uint32_t)((s * p.NMB + mb) * CBP);
 #pragma unroll
@@ -362,96 +413,188 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                             const int kh = tp / 9, kw = (tp / 3) % 3, kz = tp % 3;
                             const uint32_t arow = row0 + (uint32_t)((kh - 1) * IWZ + (kw - 1) * IZ + (kz - 1));
 #pragma unroll
-                            for (int ks = 0; ks < NK; ++ks) {
+                            for (int ks = 0; ks < NK2; ++ks) {
                                 const uint64_t adesc = umma_desc(a_base + arow * 16u + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-                                const uint64_t bdesc = umma_desc(sW2_addr + (uint32_t)tp * Cfg::W2TAP + (uint32_t)(2 * ks) * Cfg::LBO_B, Cfg::LBO_B, 128);
-                                umma_f16(d_addr, adesc, bdesc, idesc, (tp > 0 || ks > 0) ? 1u : 0u);
+                                const uint64_t bdesc = umma_desc(sW2_addr + (uint32_t)tp * Cfg::W2TAP + (uint32_t)(2 * ks) * Cfg::LBO_B2, Cfg::LBO_B2, 128);
+                                umma_f16(d_addr, adesc, bdesc, idesc_b, (tp > 0 || ks > 0) ? 1u : 0u);
                             }
                         }
+                        umma_commit_to(&bar_mb[s][mb]);                      // this M-block's accumulator is complete
+                        if (mb + 1 == p.NMB) umma_commit_to(&bar_sa_empty[s]);  // ... and the A buffer has been read
                     }
-                    umma_commit_to(&bar_tm_full[s]);       // accumulators of this thread's M-blocks are complete
-                    umma_commit_to(&bar_sa_empty[s]);      // ... and its reads of the A buffer are done
-                    if (i == 0 && warp == 1) tc_trace(p.trace, blk, 4);
+                    __syncwarp();
                 }
+                if (i == 0 && lane == 0) tc_trace(p.trace, blk, 4);
+            }
+        } else if (warp < kTcsAuxWarps) {
+            // ================= producers: haloed box rows -> A buffer (bulk copies), rows split over 3 warps ===
+            const int nrows = p.IH * IW;
+            const uint32_t row_bytes = (uint32_t)IZ * 16u;
+            const int pw = warp - 1;
+            const int ncopies = nrows * NCH;
+            const int mine = ncopies > pw * 32 + lane ? (ncopies - 1 - (pw * 32 + lane)) / (kTcsProdWarps * 32) + 1 : 0;
+            uint32_t wbytes = (uint32_t)mine * row_bytes;       // bytes this warp will deliver
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wbytes += __shfl_xor_sync(0xffffffffu, wbytes, o);
+            for (int i = 0; i < my_tiles; ++i) {
+                const uint32_t k = kt + (uint32_t)i, s = k % NBUF, u = k / NBUF;
+                int t = (int)blockIdx.x + i * (int)gridDim.x;
+                const int twi = t % p.ntw; t /= p.ntw;
+                const int thi = t % p.nth; t /= p.nth;
+                const int b = t, oh0 = thi * p.th, ow0 = twi * p.tw;
+                mbarrier_wait(&bar_sa_empty[s], (u & 1u) ^ 1u);
+                if (lane == 0) mbarrier_arrive_expect_tx(&bar_full[s], wbytes);
+                __syncwarp();
+                for (int r = pw * 32 + lane; r < ncopies; r += kTcsProdWarps * 32) {
+                    const int kc = r / nrows, rr = r - kc * nrows;
+                    const int lh = rr / IW, lw = rr - lh * IW;
+                    const int gh = pmodi(oh0 - 1 + lh, H), gw = pmodi(ow0 - 1 + lw, W);
+                    const uint4 *src = t1src + ((((size_t)b * NCH + kc) * H + gh) * W + gw) * (size_t)(Z + 2);
+                    bulk_g2s(sA_addr + s * sa_bytes + (uint32_t)kc * lbo_a + (uint32_t)rr * row_bytes, src, row_bytes, &bar_full[s]);
+                }
+                if (i == 0 && tid == 32) tc_trace(p.trace, blk, 2);
             }
         } else {
-            // ================= consumers: TMEM -> conv3 + residual -> y, conv1 of the next block -> t1 =======
+            // ================= consumers ==============================================================
             const int cw = warp - kTcsAuxWarps, g = cw >> 2, q = warp & 3;
+            const int row = q * 32 + lane;
             const float b3a = ld_scalar(bp.b3a, 0.f), b3b = ld_scalar(bp.b3b, 0.f), b4 = ld_scalar(bp.b4, 0.f), sc = ld_scalar(bp.scale, 1.f);
             float n1a = 0.f, n1b = 0.f, n2a = 0.f, n2b = 0.f;
             if (has_next) {
                 const TcsBlock &nb = p.blk[blk + 1];
                 n1a = ld_scalar(nb.b1a, 0.f); n1b = ld_scalar(nb.b1b, 0.f); n2a = ld_scalar(nb.b2a, 0.f); n2b = ld_scalar(nb.b2b, 0.f);
             }
+            unsigned char *my_ap = sAp + (size_t)g * Cfg::SAP + (size_t)row * 16;      // this row in the group's staging tile
+            const uint32_t ap_addr = sAp_addr + (uint32_t)g * Cfg::SAP;
+            const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+            const uint32_t d3_addr = tmem_grp + (uint32_t)(g * (CP + CBP)), d1_addr = d3_addr + CP;
+            const int last_mb = p.NMB > g ? g + ((p.NMB - 1 - g) / NG) * NG : -1;
+            mbarrier_wait(&bar_w, (uint32_t)blk & 1u);          // the group leaders issue MMAs that read W3 / W1
             for (int i = 0; i < my_tiles; ++i) {
-                const uint32_t k = kt + (uint32_t)i, s = k & 1u, u = k >> 1;
+                const uint32_t k = kt + (uint32_t)i, s = k % NBUF, u = k / NBUF;
                 int t = (int)blockIdx.x + i * (int)gridDim.x;
                 const int twi = t % p.ntw; t /= p.ntw;
                 const int thi = t % p.nth; t /= p.nth;
                 const int b = t, oh0 = thi * p.th, ow0 = twi * p.tw;
-                bool waited = false;
                 for (int mb = g; mb < p.NMB; mb += NG) {
-                    const int L = p.L0 + mb * 128 + q * 32 + lane;
+                    const int L = p.L0 + mb * 128 + row;
                     const int lz = L % IZ, r = L / IZ;
                     const int lw = r % IW, lh = r / IW;
                     const int oh = oh0 + lh - 1, ow = ow0 + lw - 1, oz = lz - 1;
                     const bool valid = lh >= 1 && lh <= p.th && lw >= 1 && lw <= p.tw && lz >= 1 && lz <= Z && oh < H && ow < W;
-                    const size_t off = valid ? ((size_t)oh * W + ow) * Z + oz : 0;
-                    const float *px = resid + (size_t)b * C * S + off;
-                    float xr[OC];
+                    const size_t off = valid ? (size_t)b * C * S + ((size_t)oh * W + ow) * Z + oz : 0;
+                    const float *px = resid + off;
+                    float xr[C <= 32 ? C : 16];
                     if (C <= 32 && valid) {       // residual loads in flight while the MMAs finish
+                        const float *pc = px;
 #pragma unroll
-                        for (int j = 0; j < OC; ++j) xr[j] = __ldcg(px + (size_t)j * S);
+                        for (int j = 0; j < (C <= 32 ? C : 16); ++j) { xr[j] = __ldcg(pc); pc += S; }
                     }
-                    if (!waited) {
-                        mbarrier_wait(&bar_tm_full[s], u & 1u);
+                    mbarrier_wait(&bar_mb[s][mb], u & 1u);
+                    if (i == 0 && mb == 0 && tid == kTcsAuxWarps * 32) tc_trace(p.trace, blk, 5);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // ---- phase 1: t2 = ELU(D2 + b3a) + b3b -> bf16 A operand of conv3 -------------------------
+                    float v[16];
+#pragma unroll
+                    for (int ks = 0; ks < NK2; ++ks) {
+                        tmem_ld16(tmem_d + lane_sel + (uint32_t)((s * p.NMB + mb) * CBP + ks * 16), v);
+                        uint4 lo, hi;
+                        elu_pack16(v, b3a, b3b, CB - 16 * ks, lo, hi);
+                        *reinterpret_cast<uint4 *>(my_ap + (size_t)(2 * ks) * 2048) = lo;
+                        *reinterpret_cast<uint4 *>(my_ap + (size_t)(2 * ks + 1) * 2048) = hi;
+                    }
+                    if (mb == last_mb) {          // this warp has read its last accumulator rows of the tile
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbarrier_arrive(&bar_tm_empty[s]);
+                    }
+                    const bool tr0 = i == 0 && mb == 0 && tid == kTcsAuxWarps * 32;
+                    if (tr0) tc_trace(p.trace, blk, 9);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                    if (q == 0 && elect_one()) {
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        waited = true;
-                        if (i == 0 && tid == kTcsAuxWarps * 32) tc_trace(p.trace, blk, 5);
+#pragma unroll
+                        for (int ks = 0; ks < NK2; ++ks)
+                            umma_f16(d3_addr, umma_desc(ap_addr + (uint32_t)(2 * ks) * 2048u, 2048, 128),
+                                     umma_desc(sW3_addr + (uint32_t)(2 * ks) * Cfg::LBO_B3, Cfg::LBO_B3, 128), idesc_c, ks > 0 ? 1u : 0u);
+                        umma_commit_to(&bar_g[g]);
                     }
-                    float t2[CBP];
+                    mbarrier_wait(&bar_g[g], gph); gph ^= 1u;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (tr0) tc_trace(p.trace, blk, 10);
+                    // ---- phase 2: y = D3*scale + b4 + x -> global; ELU(y + b1a') + b1b' -> bf16 A operand of conv1' ----
+                    float *py = p.y + off;
 #pragma unroll
-                    for (int ks = 0; ks < NK; ++ks)
-                        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((s * p.NMB + mb) * CBP + ks * 16), t2 + ks * 16);
-                    if (valid) {
+                    for (int kc2 = 0; kc2 < NK1; ++kc2) {
+                        constexpr int XB = C <= 32 ? 0 : 1;      // C > 32: residual loaded chunk by chunk
+                        if (XB && valid) {
+                            const float *pc = px + (size_t)(16 * kc2) * S;
 #pragma unroll
-                        for (int cb = 0; cb < CB; ++cb) t2[cb] = elu1(t2[cb] + b3a) + b3b;
-                        float *py = p.y + (size_t)b * C * S + off;
-                        T1Acc<C, CB> tn;
-                        tn.clear();
+                            for (int j = 0; j < 16; ++j)
+                                if (16 * kc2 + j < C) { xr[j] = __ldcg(pc); pc += S; }
+                        }
+                        tmem_ld16(d3_addr + lane_sel + (uint32_t)(kc2 * 16), v);
 #pragma unroll
-                        for (int c0 = 0; c0 < C; c0 += OC) {
-                            float out[OC];
-                            if (C > 32) {
+                        for (int j = 0; j < 16; ++j)
+                            if (16 * kc2 + j < C) v[j] = __fmaf_rn(v[j], sc, b4);
+                        if (valid) {
+                            float *pc = py + (size_t)(16 * kc2) * S;
 #pragma unroll
-                                for (int j = 0; j < OC; ++j)
-                                    if (c0 + j < C) xr[j] = __ldcg(px + (size_t)(c0 + j) * S);
-                            }
-#pragma unroll
-                            for (int j = 0; j < OC; ++j) out[j] = 0.0f;
-#pragma unroll
-                            for (int cb = 0; cb < CB; ++cb) {
-                                const float *wr = sw3 + cb * C4 + c0;
-#pragma unroll
-                                for (int j = 0; j < OC; ++j)
-                                    if (c0 + j < C) out[j] = __fmaf_rn(wr[j], t2[cb], out[j]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < OC; ++j) {
-                                if (c0 + j < C) {
-                                    const float yv = __fmaf_rn(out[j], sc, b4) + xr[j];
-                                    py[(size_t)(c0 + j) * S] = yv;
-                                    if (has_next) tn.add(c0 + j, yv, sw1n, n1a, n1b);
+                            for (int j = 0; j < 16; ++j) {
+                                if (16 * kc2 + j < C) {
+                                    v[j] += xr[XB ? j : 16 * kc2 + j];
+                                    *pc = v[j];
+                                    pc += S;
                                 }
                             }
                         }
-                        if (has_next) tn.store(t1dst, b, oh, ow, oz, H, W, Z, n2a, n2b);
+                        if (has_next) {
+                            uint4 lo, hi;
+                            elu_pack16(v, n1a, n1b, C - 16 * kc2, lo, hi);
+                            *reinterpret_cast<uint4 *>(my_ap + (size_t)(2 * kc2) * 2048) = lo;
+                            *reinterpret_cast<uint4 *>(my_ap + (size_t)(2 * kc2 + 1) * 2048) = hi;
+                        }
+                    }
+                    if (tr0) tc_trace(p.trace, blk, 11);
+                    if (has_next) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                        if (q == 0 && elect_one()) {
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                            for (int ks = 0; ks < NK1; ++ks)
+                                umma_f16(d1_addr, umma_desc(ap_addr + (uint32_t)(2 * ks) * 2048u, 2048, 128),
+                                         umma_desc(sW1_addr + (uint32_t)(2 * ks) * Cfg::LBO_B2, Cfg::LBO_B2, 128), idesc_b, ks > 0 ? 1u : 0u);
+                            umma_commit_to(&bar_g[g]);
+                        }
+                        mbarrier_wait(&bar_g[g], gph); gph ^= 1u;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (tr0) tc_trace(p.trace, blk, 12);
+                        // ---- phase 3: t1' = ELU(D1 + b2a') + b2b' -> bf16 -> workspace (with the circular depth halo) ----
+#pragma unroll
+                        for (int ks = 0; ks < NK2; ++ks) {
+                            tmem_ld16(d1_addr + lane_sel + (uint32_t)(ks * 16), v);
+                            uint4 lo, hi;
+                            elu_pack16(v, n2a, n2b, CB - 16 * ks, lo, hi);
+                            if (valid) {
+                                uint4 *r0 = t1dst + ((((size_t)b * NCH + 2 * ks) * H + oh) * W + ow) * (size_t)(Z + 2);
+                                uint4 *r1 = r0 + (size_t)H * W * (Z + 2);
+                                r0[oz + 1] = lo; r1[oz + 1] = hi;
+                                if (oz == 0) { r0[Z + 1] = lo; r1[Z + 1] = hi; }
+                                if (oz == Z - 1) { r0[0] = lo; r1[0] = hi; }
+                            }
+                        }
+                        if (tr0) tc_trace(p.trace, blk, 13);
                     }
                 }
-                if (!waited) mbarrier_wait(&bar_tm_full[s], u & 1u);    // keep the phase bookkeeping in step
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbarrier_arrive(&bar_tm_empty[s]);
+                if (last_mb < 0) {                  // a group without M-blocks in this tile still keeps the phases in step
+                    mbarrier_wait(&bar_mb[s][p.NMB - 1], u & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbarrier_arrive(&bar_tm_empty[s]);
+                }
                 if (i == 0 && tid == kTcsAuxWarps * 32) tc_trace(p.trace, blk, 6);
             }
         }
@@ -484,9 +627,10 @@ static int sm_count() {
     return n;
 }
 
-template <int C, int CB>
+template <int C, int CB, int NCW, int NBUF>
 static bool plan_tile(const vq3d_preact_desc *d, TcsPlan &best) {
     using Cfg = TcsCfg<C, CB>;
+    constexpr int NG = NCW / 4;
     const int cand[] = {1, 2, 4, 8, 16, 32, 64};
     int forced[2] = {0, 0};
     if (const char *e = getenv("VQ3D_TC_TILE")) sscanf(e, "%d,%d", &forced[0], &forced[1]);
@@ -505,24 +649,29 @@ static bool plan_tile(const vq3d_preact_desc *d, TcsPlan &best) {
         pl.L0 = (pl.IW + 1) * pl.IZ + 1;
         const int Lend = (th * pl.IW + tw) * pl.IZ + d->Z;
         pl.NMB = (Lend - pl.L0 + 1 + 127) / 128;
-        bool ok = 2 * pl.NMB * Cfg::CBP <= 512;
+        if (pl.NMB > kTcsMaxMB) { if (forced[0] > 0) return false; continue; }
+        const int cols_needed = NBUF * pl.NMB * Cfg::CBP + NG * (Cfg::CP + Cfg::CBP);
+        bool ok = cols_needed <= 512;
         pl.NLA = (pl.L0 + pl.NMB * 128 + pl.L0 + 7) & ~7;
         if (pl.NLA < pl.NL) pl.NLA = (pl.NL + 7) & ~7;
         ok = ok && (size_t)pl.NLA * 16 <= 0x3fffu * 16;                   // LBO field
-        pl.smem = Cfg::smem_bytes(pl.NLA);
+        pl.smem = Cfg::smem_bytes(pl.NLA, NBUF, NG);
+        if (pl.smem < 128 + (size_t)Cfg::WIMG + (size_t)C * Cfg::CB4 * 4) ok = false;   // prologue scratch lives in the A area
         ok = ok && pl.smem <= smem_cap;
         if (ok) {
             uint32_t cols = 32;
-            while (cols < (uint32_t)(2 * pl.NMB * Cfg::CBP)) cols <<= 1;
+            while (cols < (uint32_t)cols_needed) cols <<= 1;
             pl.tmem_cols = cols;
             pl.ntiles = d->B * (int)ceil_div(d->H, th) * (int)ceil_div(d->W, tw);
-            // cycles per tile on one SM: SIMT epilogue (128 lanes/cycle), MMA issue, L2 -> smem copies; they overlap
-            const double simt = ((double)pl.NMB * 128 * 40 + (double)th * tw * d->Z * (2.0 * C * CB + 14.0 * C + 16.0 * CB + 80.0)) / 128.0;
-            const double mma = (double)pl.NMB * 27 * Cfg::NK * (Cfg::CBP / 2 > 24 ? Cfg::CBP / 2 : 24) / kTcsMmaWarps;
-            const double load = (double)pl.NL * Cfg::NCH * 16 / 48.0 + (double)pl.IH * pl.IW * Cfg::NCH * 4.0;
+            // cycles per tile on one SM; epilogue (SIMT), tensor pipe (smem operand fetch bound) and copies overlap
+            const double rows = (double)pl.NMB * 128;
+            const double simt = rows * (14.0 * (C + 2 * CB) + 6.0 * C + 150.0) / 128.0 * (12.0 / NCW) + (double)ceil_div(pl.NMB, NG) * 1500.0;
+            const double mma = rows * 27 * Cfg::NK2 * (32.0 + Cfg::CBP * 2.0) / 128.0 + rows * (Cfg::NK2 + Cfg::NK1) * 48.0 / 128.0;
+            const double load = (double)pl.NL * Cfg::NCH * 16 / 64.0 + (double)pl.IH * pl.IW * Cfg::NCH * 60.0 / kTcsProdWarps;
             double tile = simt > mma ? simt : mma;
             if (load > tile) tile = load;
-            pl.cost = (double)ceil_div(pl.ntiles, nsm) * (tile + 400.0) + 2500.0 + load + mma;
+            if (NBUF == 1) tile = simt + mma + load;
+            pl.cost = (double)ceil_div(pl.ntiles, nsm) * (tile + 300.0) + (NBUF == 1 ? 0.0 : load + mma + 3000.0);
             if (!found || pl.cost < best.cost) { best = pl; found = true; }
         }
         if (forced[0] > 0) return found;
@@ -535,33 +684,31 @@ static size_t t1_units(const vq3d_preact_desc *d) {       // 16-byte units of ON
     return (size_t)d->B * TcsCfg<C, CB>::NCH * d->H * d->W * (size_t)(d->Z + 2);
 }
 
+// [256 B: barrier counter, trace] [t1 x 2] [weight images of up to kTcsMaxBlocks blocks + one W1 slot]
 template <int C, int CB>
-static size_t ws_bytes(const vq3d_preact_desc *d) { return 256 + 2 * t1_units<C, CB>(d) * 16; }
+static size_t ws_bytes(const vq3d_preact_desc *d) {
+    return 256 + 2 * t1_units<C, CB>(d) * 16 + (size_t)(kTcsMaxBlocks + 1) * TcsCfg<C, CB>::WIMG;
+}
 
-template <int C, int CB, int NCW>
+template <int C, int CB, int NCW, int NBUF>
 static int launch_tcs(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_size, void *stream) {
+    using Cfg = TcsCfg<C, CB>;
     constexpr int NT = (kTcsAuxWarps + NCW) * 32;
     const vq3d_preact_desc *d = &blocks[0];
     if (ws_size < ws_bytes<C, CB>(d)) return fail(VQ3D_ERR_INVALID, "preact_stack_tc: workspace too small (%zu < %zu bytes)", ws_size, ws_bytes<C, CB>(d));
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(VQ3D_ERR_INVALID, "preact_stack_tc: workspace must be 256-byte aligned");
     TcsPlan pl;
-    if (!plan_tile<C, CB>(d, pl)) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack_tc: no tile fits shared memory / TMEM");
-    auto kernel = preact_tc_kernel<C, CB, NCW>;
-    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (!plan_tile<C, CB, NCW, NBUF>(d, pl)) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack_tc: no tile fits shared memory / TMEM");
+    auto kernel = preact_tc_kernel<C, CB, NCW, NBUF>;
+    size_t smem = pl.smem < 120 * 1024 ? 120 * 1024 : pl.smem;     // > half an SM: never two resident CTAs (they would fight over TMEM)
+    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(attr)");
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, pl.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, smem);
     if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(occupancy)");
     if (occ < 1) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack_tc: kernel does not fit on an SM");
-    // one CTA per SM: the kernel may hold the SM's whole TMEM, a second resident CTA could spin in tcgen05.alloc forever
     int grid = sm_count();
     if (grid > pl.ntiles) grid = pl.ntiles;
-    size_t smem = pl.smem;
-    if (occ > 1 && smem < 120 * 1024) {
-        smem = 120 * 1024;
-        e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(attr)");
-    }
     if (getenv("VQ3D_TC_DEBUG"))
         fprintf(stderr, "preact_stack_tc<%d,%d>: %dx%dx%d n=%d tile %dx%dx%d NL=%d NMB=%d ntiles=%d occ=%d grid=%d smem=%zu tmem=%u\n", C, CB,
                 d->H, d->W, d->Z, n, pl.th, pl.tw, d->Z, pl.NL, pl.NMB, pl.ntiles, occ, grid, smem, pl.tmem_cols);
@@ -573,12 +720,16 @@ static int launch_tcs(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws
     p.nth = (int)ceil_div(d->H, pl.th); p.ntw = (int)ceil_div(d->W, pl.tw);
     p.IH = pl.IH; p.IW = pl.IW; p.IZ = pl.IZ; p.NL = pl.NL; p.L0 = pl.L0; p.NMB = pl.NMB; p.NLA = pl.NLA;
     p.ntiles = pl.ntiles; p.tmem_cols = pl.tmem_cols;
-    p.sync = reinterpret_cast<unsigned int *>(ws);
+    unsigned char *wsb = static_cast<unsigned char *>(ws);
+    p.sync = reinterpret_cast<unsigned int *>(wsb);
     const bool trace = getenv("VQ3D_TC_TRACE") != nullptr;
-    p.trace = trace ? reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + 64) : nullptr;
-    p.t1[0] = reinterpret_cast<uint4 *>(static_cast<unsigned char *>(ws) + 256);
+    p.trace = trace ? reinterpret_cast<unsigned long long *>(wsb + 64) : nullptr;
+    p.t1[0] = reinterpret_cast<uint4 *>(wsb + 256);
     p.t1[1] = p.t1[0] + t1_units<C, CB>(d);
+    unsigned char *wimg = reinterpret_cast<unsigned char *>(p.t1[1] + t1_units<C, CB>(d));
+    p.wimg = wimg;
     p.y = blocks[n - 1].y;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int i0 = 0; i0 < n; i0 += kTcsMaxBlocks) {
         const int nb = n - i0 < kTcsMaxBlocks ? n - i0 : kTcsMaxBlocks;
         p.nblocks = nb;
@@ -589,20 +740,25 @@ static int launch_tcs(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws
             t.w1 = s.w1; t.w2 = s.w2; t.w3 = s.w3;
             t.b1a = s.b1a; t.b1b = s.b1b; t.b2a = s.b2a; t.b2b = s.b2b; t.b3a = s.b3a; t.b3b = s.b3b; t.b4 = s.b4; t.scale = s.scale;
         }
-        e = cudaMemsetAsync(p.sync, 0, sizeof(unsigned int), static_cast<cudaStream_t>(stream));
+        e = cudaMemsetAsync(p.sync, 0, sizeof(unsigned int), st);
         if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(memset)");
+        const int items = Cfg::CPCH * Cfg::CBP + 27 * Cfg::NCH * Cfg::CBP + Cfg::NCH * Cfg::CP;
+        tcs_prep_kernel<C, CB><<<dim3((unsigned)ceil_div(items, 256), (unsigned)(nb + 1)), 256, 0, st>>>(p, wimg);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(prep)");
         void *args[] = {&p};
-        e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kernel), dim3((unsigned)grid), dim3(NT), args, smem, static_cast<cudaStream_t>(stream));
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kernel), dim3((unsigned)grid), dim3(NT), args, smem, st);
         if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(cooperative launch)");
         if (trace) {
-            unsigned long long h[18];
-            cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+            unsigned long long h[16];
+            cudaStreamSynchronize(st);
             cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
-            const char *names[9] = {"block start", "weights staged", "copies issued", "A full (MMA)", "MMAs committed", "TMEM full (consumer)",
-                                    "tile 0 drained", "all tiles drained", "grid barrier passed"};
-            for (int b = 0; b < 2; ++b)
-                for (int ev = 0; ev < 9; ++ev)
-                    fprintf(stderr, "  trace blk %d %-22s +%6.2f us\n", b + 1, names[ev], (double)(long long)(h[b * 9 + ev] - h[b * 9]) * 1e-3);
+            const char *names[14] = {"block start", "weights landed", "first copies issued", "A full (MMA)", "MMAs committed", "TMEM full (consumer)",
+                                     "tile 0 drained", "all tiles drained", "grid barrier passed", "  mb0 phase 1 staged", "  mb0 conv3 MMA done",
+                                     "  mb0 phase 2 staged", "  mb0 conv1 MMA done", "  mb0 phase 3 stored"};
+            const int order[14] = {0, 1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 6, 7, 8};
+            for (int k = 0; k < 14; ++k)
+                fprintf(stderr, "  trace %-24s +%6.2f us\n", names[order[k]], (double)(long long)(h[order[k]] - h[0]) * 1e-3);
         }
     }
     return VQ3D_OK;
@@ -614,9 +770,9 @@ struct TcsEntry {
     size_t (*ws)(const vq3d_preact_desc *);
 };
 
-#define VQ3D_TCS(C, CB, NCW) {C, CB, launch_tcs<C, CB, NCW>, ws_bytes<C, CB>}
+#define VQ3D_TCS(C, CB, NCW, NBUF) {C, CB, launch_tcs<C, CB, NCW, NBUF>, ws_bytes<C, CB>}
 static const TcsEntry kTcs[] = {
-    VQ3D_TCS(8, 4, 12), VQ3D_TCS(16, 8, 12), VQ3D_TCS(18, 9, 12), VQ3D_TCS(32, 16, 12), VQ3D_TCS(64, 32, 8), VQ3D_TCS(72, 36, 8),
+    VQ3D_TCS(8, 4, 16, 2), VQ3D_TCS(16, 8, 24, 2), VQ3D_TCS(18, 9, 24, 2), VQ3D_TCS(32, 16, 16, 2), VQ3D_TCS(64, 32, 8, 2), VQ3D_TCS(72, 36, 8, 1),
 };
 
 static const TcsEntry *find_tcs(const vq3d_preact_desc *d) {
