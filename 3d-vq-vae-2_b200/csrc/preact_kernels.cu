@@ -24,6 +24,8 @@
 
 namespace vq3d {
 
+int preact_row_dispatch(const vq3d_preact_desc *d, void *stream, bool *handled);    // preact_row_kernels.cu
+
 struct PreactParams {
     int B, H, W, Z;            // input spatial
     int Ho, Wo, Zo;            // output spatial
@@ -390,7 +392,8 @@ static const FusedEntry *find_fused(const vq3d_preact_desc *d) {
 
 static int validate(const vq3d_preact_desc *d) {
     if (!d) return fail(VQ3D_ERR_INVALID, "preact_block: null descriptor");
-    if (!d->x || !d->y || !d->w1 || !d->w2 || !d->w3) return fail(VQ3D_ERR_INVALID, "preact_block: null x/y/weights");
+    if (!d->x || !d->w1 || !d->w2 || !d->w3) return fail(VQ3D_ERR_INVALID, "preact_block: null x/weights");
+    if (d->out_w ? !d->out_y : !d->y) return fail(VQ3D_ERR_INVALID, "preact_block: null output");
     if (d->B < 1 || d->H < 1 || d->W < 1 || d->Z < 1 || d->Cin < 1 || d->Cb < 1 || d->Cout < 1 || d->mode < 0 || d->mode > 2)
         return fail(VQ3D_ERR_INVALID, "preact_block: bad sizes");
     if (d->mode != 0 && !d->wskip) return fail(VQ3D_ERR_INVALID, "preact_block: mode down/up needs a skip conv");
@@ -405,6 +408,10 @@ using namespace vq3d;
 extern "C" int vq3d_preact_block(const vq3d_preact_desc *d, void *stream) {
     int rc = validate(d);
     if (rc) return rc;
+    bool handled = false;
+    rc = preact_row_dispatch(d, stream, &handled);
+    if (rc || handled) return rc;
+    if (d->out_w) return fail(VQ3D_ERR_UNSUPPORTED, "preact_block: no kernel fuses the trailing 1x1 convolution for this shape");
     const FusedEntry *e = find_fused(d);
     if (!e) return fail(VQ3D_ERR_UNSUPPORTED, "preact_block: no fused instantiation for Cin=%d Cb=%d Cout=%d mode=%d", d->Cin, d->Cb, d->Cout, d->mode);
     return e->fn(d, stream);
@@ -418,17 +425,25 @@ extern "C" int vq3d_preact_stack(const vq3d_preact_desc *blocks, int n, float *t
         if (blocks[i].mode != 0 || blocks[i].wskip || blocks[i].Cin != blocks[0].Cin || blocks[i].Cb != blocks[0].Cb)
             return fail(VQ3D_ERR_INVALID, "preact_stack: blocks must be equal-shape 'same' blocks without skip");
     }
+    for (int i = 0; i + 1 < n; ++i)
+        if (blocks[i].out_w) return fail(VQ3D_ERR_INVALID, "preact_stack: only the last block may carry a trailing 1x1 convolution");
     const FusedEntry *e = find_fused(&blocks[0]);
-    if (!e) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack: no fused instantiation for C=%d", blocks[0].Cin);
-    // ping-pong between tmp and y so that block n-1 lands in blocks[n-1].y
+    // ping-pong between tmp and y so that block n-1 lands in blocks[n-1].y (or .out_y through the fused 1x1)
     const float *src = blocks[0].x;
     float *out = blocks[n - 1].y;
     for (int i = 0; i < n; ++i) {
         vq3d_preact_desc d = blocks[i];
         d.x = src;
         d.y = ((n - 1 - i) % 2 == 0) ? out : tmp;
-        int rc = e->fn(&d, stream);
+        bool handled = false;
+        int rc = preact_row_dispatch(&d, stream, &handled);
         if (rc) return rc;
+        if (!handled) {
+            if (d.out_w) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack: no kernel fuses the trailing 1x1 convolution for this shape");
+            if (!e) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack: no fused instantiation for C=%d", blocks[0].Cin);
+            rc = e->fn(&d, stream);
+            if (rc) return rc;
+        }
         src = d.y;
     }
     return VQ3D_OK;

@@ -1,0 +1,222 @@
+// preact_row_kernels.cu -- 'same' PreActFixupResBlocks (vqvae/layers.py:102-216) with very few channels
+// (4 -> 2 -> 4 at 512x512x128, 8 -> 4 -> 8 at 256x256x64, 2 -> 1 -> 2): the layers whose tensors are
+// hundreds of MB and whose arithmetic is far too thin for the tensor cores (K = 2..4 of a K16 MMA).
+//
+// They are bound by HBM traffic and, in practice, by how many instructions the SIMT pipes spend per
+// voxel, so this kernel is built around the contiguous depth axis: a thread owns 4 consecutive z
+// (float4 loads/stores, one LDS.128 per conv2 row window), a tile is (th, tw) FULL depth rows, so the
+// circular wrap along z needs no halo traffic at all (two extra shared-memory entries per row), and no
+// per-voxel integer division is left anywhere.
+//
+//   stage A  t1 = ELU(conv1(ELU(x+b1a)+b1b)+b2a)+b2b for the (th+2)(tw+2) haloed rows -> shared memory
+//   stage B  3x3x3 circular conv from shared memory, 4 z per thread in registers
+//   stage C  ELU, conv3, *scale + b4 + x  [+ the decoder's final 1x1 `out` convolution (layers.py:508,516)
+//            when asked to: the last block then writes 1 channel instead of 4]
+#include "vq3d_rt.h"
+
+namespace vq3d {
+
+constexpr int kRowThreads = 256;
+
+struct RowParams {
+    int B, H, W, Z;
+    int th, tw, nth, ntw;
+    const float *x, *w1, *w2, *w3;
+    const float *b1a, *b1b, *b2a, *b2b, *b3a, *b3b, *b4, *scale;
+    const float *out_w, *out_b;       // fused trailing 1x1 conv (C -> 1) or NULL
+    float *y;                         // [B, C, S], or [B, 1, S] when out_w is given
+};
+
+__host__ __device__ __forceinline__ int rmod(int i, int n) {
+    int r = i % n;
+    return r < 0 ? r + n : r;
+}
+
+template <int C, int CB>
+struct RowSmem {
+    static constexpr int w1 = 0;                        // [C][CB]
+    static constexpr int w2 = w1 + C * CB;              // [CB ci][9 (kh,kw)][3 kz][CB co]
+    static constexpr int w3 = w2 + CB * 27 * CB;        // [CB][C]
+    static constexpr int wo = w3 + CB * C;              // [C] + bias
+    static constexpr int tile = (wo + C + 1 + 3) & ~3;  // [CB][(th+2)(tw+2)][Z+8], 16-byte aligned rows
+    static size_t floats(int th, int tw, int Z) { return tile + (size_t)CB * (th + 2) * (tw + 2) * (Z + 8); }
+};
+
+template <int C, int CB, bool OUTC>
+__global__ void __launch_bounds__(kRowThreads)
+preact_row_kernel(RowParams p) {
+    using SM = RowSmem<C, CB>;
+    VQ3D_DYN_SMEM(float, smem);
+    float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_wo = smem + SM::wo, *s_t1 = smem + SM::tile;
+    const int tid = threadIdx.x;
+    const int Z = p.Z, ZQ = Z >> 2, ZP = Z + 8;
+    const int IW = p.tw + 2, nrows_in = (p.th + 2) * IW, nrows_out = p.th * p.tw;
+    const int zq = tid % ZQ, slot = tid / ZQ, nslots = kRowThreads / ZQ;
+    const int64_t S = (int64_t)p.H * p.W * Z;
+
+    int bid = blockIdx.x;
+    const int twi = bid % p.ntw; bid /= p.ntw;
+    const int thi = bid % p.nth; bid /= p.nth;
+    const int b = bid, oh0 = thi * p.th, ow0 = twi * p.tw;
+    const float *xb = p.x + (size_t)b * C * S;
+
+    for (int i = tid; i < C * CB; i += kRowThreads) s_w1[i] = p.w1[(i % CB) * C + i / CB];
+    for (int i = tid; i < CB * 27 * CB; i += kRowThreads) {
+        const int co = i % CB, t = (i / CB) % 27, ci = i / (CB * 27);
+        s_w2[i] = p.w2[((size_t)co * CB + ci) * 27 + t];
+    }
+    for (int i = tid; i < CB * C; i += kRowThreads) s_w3[i] = p.w3[(i % C) * CB + i / C];
+    if (OUTC) {
+        if (tid < C) s_wo[tid] = p.out_w[tid];
+        if (tid == C) s_wo[C] = p.out_b ? p.out_b[0] : 0.0f;
+    }
+    const float b1a = ld_scalar(p.b1a, 0.f), b1b = ld_scalar(p.b1b, 0.f), b2a = ld_scalar(p.b2a, 0.f), b2b = ld_scalar(p.b2b, 0.f);
+    __syncthreads();
+
+    // ---- stage A ----------------------------------------------------------------------------------
+    for (int rs = slot; rs < nrows_in; rs += nslots) {
+        const int lh = rs / IW, lw = rs - lh * IW;
+        const int gh = rmod(oh0 - 1 + lh, p.H), gw = rmod(ow0 - 1 + lw, p.W);
+        const float *px = xb + ((size_t)gh * p.W + gw) * Z + 4 * zq;
+        float t[CB][4];
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[cb][k] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
+            const float a0 = elu1(v.x + b1a) + b1b, a1 = elu1(v.y + b1a) + b1b, a2 = elu1(v.z + b1a) + b1b, a3 = elu1(v.w + b1a) + b1b;
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const float w = s_w1[c * CB + cb];
+                t[cb][0] = __fmaf_rn(w, a0, t[cb][0]); t[cb][1] = __fmaf_rn(w, a1, t[cb][1]);
+                t[cb][2] = __fmaf_rn(w, a2, t[cb][2]); t[cb][3] = __fmaf_rn(w, a3, t[cb][3]);
+            }
+        }
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+            float4 o;
+            o.x = elu1(t[cb][0] + b2a) + b2b; o.y = elu1(t[cb][1] + b2a) + b2b;
+            o.z = elu1(t[cb][2] + b2a) + b2b; o.w = elu1(t[cb][3] + b2a) + b2b;
+            float *row = s_t1 + ((size_t)cb * nrows_in + rs) * ZP;
+            *reinterpret_cast<float4 *>(row + 4 + 4 * zq) = o;
+            if (zq == 0) row[Z + 4] = o.x;              // circular halo: z = Z  -> z = 0
+            if (zq == ZQ - 1) row[3] = o.w;             //                z = -1 -> z = Z-1
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B + C ------------------------------------------------------------------------------
+    const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
+    for (int ro = slot; ro < nrows_out; ro += nslots) {
+        const int lh = ro / p.tw, lw = ro - lh * p.tw;
+        const int oh = oh0 + lh, ow = ow0 + lw;
+        if (oh >= p.H || ow >= p.W) continue;
+        float acc[CB][4];
+#pragma unroll
+        for (int co = 0; co < CB; ++co)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[co][k] = 0.0f;
+#pragma unroll
+        for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float *row = s_t1 + ((size_t)ci * nrows_in + (lh + kh) * IW + lw + kw) * ZP + 4 * zq;
+                    const float4 m = *reinterpret_cast<const float4 *>(row + 4);
+                    const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                    const float *wt = s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB;
+#pragma unroll
+                    for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                        for (int co = 0; co < CB; ++co) {
+                            const float w = wt[kz * CB + co];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[co][k] = __fmaf_rn(w, r[k + kz], acc[co][k]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < CB; ++co)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
+        const size_t off = ((size_t)oh * p.W + ow) * Z + 4 * zq;
+        float o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const float w = s_w3[cb * C + c];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+            }
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off));
+            float4 yv;
+            yv.x = __fmaf_rn(out[0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[1], sc, b4) + xv.y;
+            yv.z = __fmaf_rn(out[2], sc, b4) + xv.z; yv.w = __fmaf_rn(out[3], sc, b4) + xv.w;
+            if (OUTC) {
+                const float w = s_wo[c];
+                o4[0] = __fmaf_rn(w, yv.x, o4[0]); o4[1] = __fmaf_rn(w, yv.y, o4[1]);
+                o4[2] = __fmaf_rn(w, yv.z, o4[2]); o4[3] = __fmaf_rn(w, yv.w, o4[3]);
+            } else {
+                *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off) = yv;
+            }
+        }
+        if (OUTC) {
+            const float bo = s_wo[C];
+            float4 ov;
+            ov.x = o4[0] + bo; ov.y = o4[1] + bo; ov.z = o4[2] + bo; ov.w = o4[3] + bo;
+            *reinterpret_cast<float4 *>(p.y + (size_t)b * S + off) = ov;
+        }
+    }
+}
+
+template <int C, int CB, bool OUTC>
+static int launch_row(const vq3d_preact_desc *d, void *stream) {
+    using SM = RowSmem<C, CB>;
+    RowParams p;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z;
+    // tile: as large as shared memory allows (halo recompute), but keep >= 2 CTAs per SM in flight
+    const size_t cap = 110 * 1024;
+    int th = d->H < 8 ? d->H : 8, tw = d->W < 8 ? d->W : 8;
+    auto ntiles = [&]() { return (int64_t)d->B * ceil_div(d->H, th) * ceil_div(d->W, tw); };
+    while (SM::floats(th, tw, d->Z) * 4 > cap || (ntiles() < 2 * kNumSMs && th * tw > 4)) {
+        if (th >= tw && th > 1) th = (th + 1) / 2;
+        else if (tw > 1) tw = (tw + 1) / 2;
+        else return fail(VQ3D_ERR_UNSUPPORTED, "preact_block(row): tile does not fit shared memory");
+    }
+    p.th = th; p.tw = tw; p.nth = (int)ceil_div(d->H, th); p.ntw = (int)ceil_div(d->W, tw);
+    p.x = d->x; p.w1 = d->w1; p.w2 = d->w2; p.w3 = d->w3;
+    p.b1a = d->b1a; p.b1b = d->b1b; p.b2a = d->b2a; p.b2b = d->b2b; p.b3a = d->b3a; p.b3b = d->b3b; p.b4 = d->b4; p.scale = d->scale;
+    p.out_w = d->out_w; p.out_b = d->out_b;
+    p.y = OUTC ? d->out_y : d->y;
+    const int64_t grid = ntiles();
+    if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(row): grid too large");
+    return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(kRowThreads), SM::floats(th, tw, d->Z) * 4, stream, p);
+}
+
+// Z must be a multiple of 4 with Z/4 a power of two <= 32 (a row of Z/4 float4 lanes divides the CTA)
+static bool row_shape_ok(const vq3d_preact_desc *d) {
+    const int zq = d->Z / 4;
+    return d->Z % 4 == 0 && zq >= 1 && zq <= 32 && (zq & (zq - 1)) == 0 &&
+           (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out_w ? d->out_y : d->y) & 15) == 0;
+}
+
+int preact_row_dispatch(const vq3d_preact_desc *d, void *stream, bool *handled) {
+    *handled = false;
+    if (d->mode != 0 || d->wskip || d->Cin != d->Cout || !row_shape_ok(d)) return VQ3D_OK;
+    const bool outc = d->out_w != nullptr;
+    int (*fn)(const vq3d_preact_desc *, void *) = nullptr;
+    if (d->Cin == 2 && d->Cb == 1) fn = outc ? launch_row<2, 1, true> : launch_row<2, 1, false>;
+    else if (d->Cin == 4 && d->Cb == 2) fn = outc ? launch_row<4, 2, true> : launch_row<4, 2, false>;
+    else if (d->Cin == 8 && d->Cb == 4) fn = outc ? launch_row<8, 4, true> : launch_row<8, 4, false>;
+    if (!fn) return VQ3D_OK;
+    *handled = true;
+    return fn(d, stream);
+}
+
+}  // namespace vq3d

@@ -193,7 +193,7 @@ class Ops:
                     self.stream()), nbytes=4 * B * Cc * H * W * Z * 9, tag=f"{Cc}ch @{H}x{W}x{Z}")
         return y
 
-    def preact_desc(self, x: Tensor, y: Optional[Tensor], blk, mode: int) -> "_cabi.PreactDesc":
+    def preact_desc(self, x: Tensor, y: Optional[Tensor], blk, mode: int, tail=None, out_y: Optional[Tensor] = None) -> "_cabi.PreactDesc":
         B, Cin, H, W, Z = x.shape
         w1, w2, w3 = blk.branch_conv1.weight, blk.branch_conv2.weight, blk.branch_conv3.weight
         skip = blk.skip_conv.weight if blk.skip_conv is not None else None
@@ -203,7 +203,10 @@ class Ops:
                                 w3=self._p(self._t(w3.data)), wskip=None if skip is None else self._p(self._t(skip.data)),
                                 b1a=g("bias1a"), b1b=g("bias1b"), b2a=g("bias2a"), b2b=g("bias2b"), b3a=g("bias3a"),
                                 b3b=g("bias3b"), b4=g("bias4"), scale=g("scale"), b1c=g("bias1c"), b1d=g("bias1d"),
-                                y=None if y is None else self._p(y))
+                                y=None if y is None else self._p(y),
+                                out_w=None if tail is None else self._p(self._t(tail.weight.data)),
+                                out_b=None if tail is None or tail.bias is None else self._p(self._t(tail.bias.data)),
+                                out_y=None if out_y is None else self._p(out_y))
 
     def preact_block(self, x: Tensor, blk, mode: int) -> Optional[Tensor]:
         """Whole PreActFixupResBlock in one launch; None if no fused kernel covers the shape."""
@@ -226,20 +229,28 @@ class Ops:
     TC_STACK_SHAPES = {(8, 4), (16, 8), (18, 9), (32, 16), (64, 32), (72, 36)}
     TC_STACK_MAX_BLOCKS = 24     # blocks per launch (kTcsMaxBlocks)
 
-    def preact_stack(self, x: Tensor, blocks) -> Optional[Tensor]:
-        """n >= 1 consecutive equal-shape 'same' blocks; None if unsupported."""
+    def preact_stack(self, x: Tensor, blocks, tail=None) -> Optional[Tensor]:
+        """n >= 1 consecutive equal-shape 'same' blocks; None if unsupported.  tail: a 1x1 Conv3d (C -> 1)
+        to fuse into the last block's epilogue (the decoder's `out` conv); the result is then its output."""
         x = self._t(x)
         n = len(blocks)
         y = torch.empty_like(x)
         tmp = torch.empty_like(x) if n > 1 else None
+        B, Cc, H, W, Z = x.shape
+        out_y = torch.empty((B, 1, H, W, Z), dtype=torch.float32, device=x.device) if tail is not None else None
         arr = (_cabi.PreactDesc * n)()
         for i, blk in enumerate(blocks):
-            arr[i] = self.preact_desc(x, y, blk, 0)
-        B, Cc, H, W, Z = x.shape
+            last = i == n - 1
+            arr[i] = self.preact_desc(x, y, blk, 0, tail if last else None, out_y if last else None)
         Cb = blocks[0].branch_conv1.weight.shape[0]
-        meta = dict(nbytes=n * 8 * x.numel(), flops=n * 2 * B * H * W * Z * (2 * Cc * Cb + 27 * Cb * Cb),
-                    tag=f"stack{n} {Cc}->{Cb}->{Cc} @{H}x{W}x{Z}")
-        if self.precision == "bf16" and (Cc, Cb) in self.TC_STACK_SHAPES:
+        meta = dict(nbytes=n * 8 * x.numel() - (3 * x.numel() if tail is not None else 0),
+                    flops=n * 2 * B * H * W * Z * (2 * Cc * Cb + 27 * Cb * Cb),
+                    tag=f"stack{n}{'+out' if tail is not None else ''} {Cc}->{Cb}->{Cc} @{H}x{W}x{Z}")
+        res = out_y if tail is not None else y
+        # Cb <= 4 pads the MMA K extent 4x: the tensor pipe's smem operand fetch then costs more than the SIMT
+        # kernel on big tensors; keep the tensor-core path for them only where latency (small tensors) dominates
+        tc_ok = tail is None and (Cc, Cb) in self.TC_STACK_SHAPES and (Cb > 4 or H * W * Z <= 65536)
+        if self.precision == "bf16" and tc_ok:
             need = self.lib.vq3d_preact_stack_tc_workspace(C.byref(arr[0]))
             if need:
                 ws = self._workspace(need, x.device)
@@ -249,11 +260,11 @@ class Ops:
                     return y
         if n == 1:
             d = arr[0]
-            return y if self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()),
-                                   allow_unsupported=True, **meta) else None
+            return res if self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()),
+                                     allow_unsupported=True, **meta) else None
         ok = self._call("preact_stack", self.lib.vq3d_preact_stack, (arr, n, self._p(tmp), self.stream()), allow_unsupported=True,
                         kernels=n, **meta)
-        return y if ok else None
+        return res if ok else None
 
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
         decoded, x = self._t(decoded), self._t(x)

@@ -222,25 +222,33 @@ class BlockSequence(nn.Sequential):
     equal-shape 'same' PreAct blocks to one vq3d_preact_stack call (the 50/150-deep stacks of
     layers.py:492-494,566-569 are launch-latency bound when run block by block)."""
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+    def forward(self, x: torch.Tensor, tail: Optional[nn.Module] = None) -> torch.Tensor:  # type: ignore[override]
+        """tail: a 1x1 convolution applied after the last block (the decoder's `out`, layers.py:516); it is
+        fused into the last block's kernel where one covers the shape, otherwise run after it."""
         mods = list(self)
         i = 0
+        done_tail = tail is None
         while i < len(mods):
             m = mods[i]
             j = i
             if _stackable(m):
                 while j + 1 < len(mods) and _stackable(mods[j + 1]) and _same_shape(m, mods[j + 1]):
                     j += 1
-            if j > i or _stackable(m):
                 _no_conv_backward(*chain.from_iterable(b.parameters() for b in mods[i:j + 1]))
+                if tail is not None and j == len(mods) - 1:
+                    y = ops().preact_stack(x, mods[i:j + 1], tail=tail)
+                    if y is not None:
+                        return y
                 y = ops().preact_stack(x, mods[i:j + 1])
                 if y is not None:
                     x = y
                     i = j + 1
                     continue
+            if tail is not None and i == len(mods) - 1 and isinstance(m, UpBlock):
+                return m(x, tail=tail)
             x = m(x)
             i += 1
-        return x
+        return x if done_tail else tail(x)
 
 
 def _stackable(m) -> bool:
@@ -279,8 +287,8 @@ class UpBlock(nn.Module):
                for _ in range(n_post_upscale_blocks)))
             for i in range(n_up - 1, -1, -1)))
 
-    def forward(self, data):
-        return self.layers(data)
+    def forward(self, data, tail=None):
+        return self.layers(data, tail=tail)
 
 
 class PreQuantizationConditioning(nn.Module):
@@ -330,8 +338,9 @@ class Decoder(nn.Module):
         out = None
         for i, (q, up) in enumerate(reversed(list(zip(quantizations, self.up)))):
             out = q if i == 0 else self.proj[-i](q, out)      # cat([q, out]) folded into the 1x1
-            out = up(out)
-        return self.out(out)
+            last = i == len(self.up) - 1
+            out = up(out, tail=self.out) if last else up(out)  # the final 1x1 `out` conv rides on the last block
+        return out
 
 
 class Encoder2(nn.Module):

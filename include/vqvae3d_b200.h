@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 2
+#define VQ3D_ABI_VERSION 3
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -156,6 +156,13 @@ typedef struct vq3d_preact_desc {
     const float *wskip;          /* skip_conv.weight or NULL */
     const float *b1a, *b1b, *b2a, *b2b, *b3a, *b3b, *b4, *scale, *b1c, *b1d;
     float *y;                    /* [B, Cout, S_out] */
+    /* optional trailing 1x1 convolution fused into the block's epilogue (the decoder's `out` conv,
+     * layers.py:508,516: Cout -> 1 channel with bias): when out_w != NULL the block writes
+     * out_y[B, 1, S_out] = sum_c out_w[c] * y[c] + *out_b instead of y.  Honoured by vq3d_preact_block /
+     * the last block of vq3d_preact_stack for 'same' blocks the row kernel covers; otherwise
+     * VQ3D_ERR_UNSUPPORTED (run the block and the convolution separately). */
+    const float *out_w, *out_b;
+    float *out_y;
 } vq3d_preact_desc;
 
 #define VQ3D_OK 0

@@ -176,3 +176,31 @@ def test_emu_stack_ping_pong():
                 ref = blk.forward_composed(ref)
             y = seq(x)
             assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("c,shape,n,tail", [
+    (4, (1, 4, 10, 12, 16), 1, False),     # row kernel: 4 z per thread, full-depth tiles, ragged in H
+    (8, (2, 8, 5, 6, 8), 2, False),        # batch 2, two blocks (ping-pong)
+    (2, (1, 2, 9, 7, 32), 3, False),
+    (4, (1, 4, 6, 9, 4), 2, True),         # Z = 4: one thread per row holds both circular halos; fused `out` conv
+    (4, (1, 4, 9, 10, 16), 1, True),
+])
+def test_emu_row_kernel(c, shape, n, tail):
+    """preact_row_kernels.cu (the 512x512x128 / 256x256x64 layers) against the composed generic path."""
+    torch.manual_seed(c * 7 + n)
+    with use_emulator() as o, torch.no_grad():
+        seq = L.BlockSequence(*(L.PreActFixupResBlock(c, c, "same") for _ in range(n))).eval()
+        for p in seq.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        out = L.Conv3d(c, 1, kernel_size=1)
+        x = torch.randn(shape)
+        ref = x
+        for blk in seq:
+            ref = blk.forward_composed(ref)
+        if tail:
+            ref = out(ref)
+        n0 = o.launches
+        y = seq(x, tail=out) if tail else seq(x)
+        assert o.launches - n0 == n, "expected one fused launch per block (trailing conv included)"
+        assert y.shape == ref.shape
+        assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())
