@@ -113,6 +113,74 @@ conv3d_generic_kernel(ConvParams p) {
     }
 }
 
+// 1x1x1 convolutions on big tensors (parse_input 1 -> 4 at 512^3, the cat + proj 18 -> 18 at 128x128x32,
+// layers.py:535,385,512): pure streaming.  A thread owns 4 consecutive voxels (float4 along the contiguous
+// depth axis) x CO_T output channels; weights of the chunk sit in shared memory ([ci][CO_T], broadcast reads).
+constexpr int kPwThreads = 256;
+constexpr int kPwMaxCin = 160;
+
+template <int CO_T>
+__global__ void __launch_bounds__(kPwThreads)
+pointwise_kernel(ConvParams p) {
+    __shared__ __align__(16) float s_w[kPwMaxCin * CO_T];
+    const int Cin = p.C1 + p.C2;
+    const int64_t S = (int64_t)p.H * p.W * p.Z, S4 = S >> 2;
+    const int co0 = blockIdx.y * CO_T;
+    for (int i = threadIdx.x; i < Cin * CO_T; i += kPwThreads) {
+        const int j = i % CO_T, ci = i / CO_T;
+        s_w[i] = co0 + j < p.Cout ? p.w[(size_t)(co0 + j) * Cin + ci] : 0.0f;
+    }
+    const float pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    const float sc = ld_scalar(p.post_scale, 1.0f), sb = ld_scalar(p.post_b, 0.0f);
+    __syncthreads();
+    const int64_t total = (int64_t)p.B * S4;
+    for (int64_t v = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; v < total; v += (int64_t)gridDim.x * kPwThreads) {
+        const int b = (int)(v / S4);
+        const int64_t r4 = v - (int64_t)b * S4;
+        float acc[CO_T][4];
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+            float4 xv = __ldg(reinterpret_cast<const float4 *>(src) + r4);
+            if (p.pre_act) { xv.x = elu1(xv.x + pa) + pb; xv.y = elu1(xv.y + pa) + pb; xv.z = elu1(xv.z + pa) + pb; xv.w = elu1(xv.w + pa) + pb; }
+            else { xv.x += pb; xv.y += pb; xv.z += pb; xv.w += pb; }
+            const float *wt = s_w + ci * CO_T;
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) {
+                const float w = wt[j];
+                acc[j][0] = __fmaf_rn(w, xv.x, acc[j][0]); acc[j][1] = __fmaf_rn(w, xv.y, acc[j][1]);
+                acc[j][2] = __fmaf_rn(w, xv.z, acc[j][2]); acc[j][3] = __fmaf_rn(w, xv.w, acc[j][3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+            const int co = co0 + j;
+            if (co < p.Cout) {
+                const float bias = p.bias ? __ldg(p.bias + co) : 0.0f;
+                const size_t o4 = (((size_t)b * p.Cout + co) * S >> 2) + r4;
+                float4 yv;
+                yv.x = __fmaf_rn(acc[j][0], sc, sb) + bias; yv.y = __fmaf_rn(acc[j][1], sc, sb) + bias;
+                yv.z = __fmaf_rn(acc[j][2], sc, sb) + bias; yv.w = __fmaf_rn(acc[j][3], sc, sb) + bias;
+                if (p.residual) {
+                    const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.residual) + o4);
+                    yv.x += rv.x; yv.y += rv.y; yv.z += rv.z; yv.w += rv.w;
+                }
+                if (p.post_act) { yv.x = elu1(yv.x); yv.y = elu1(yv.y); yv.z = elu1(yv.z); yv.w = elu1(yv.w); }
+                reinterpret_cast<float4 *>(p.y)[o4] = yv;
+            }
+        }
+    }
+}
+
+template <int CO_T>
+static int launch_pointwise(const ConvParams &p, void *stream) {
+    const int64_t total4 = (int64_t)p.B * p.H * p.W * p.Z / 4;
+    int64_t gx = ceil_div(total4, kPwThreads);
+    if (gx > (int64_t)kNumSMs * 16) gx = (int64_t)kNumSMs * 16;
+    return launch("pointwise", pointwise_kernel<CO_T>, dim3((unsigned)gx, (unsigned)ceil_div(p.Cout, CO_T)), dim3(kPwThreads), 0, stream, p);
+}
+
 // nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False): src = o/2 - 0.25 clamped at 0
 __device__ __forceinline__ void up_taps(int o, int n, int &i0, int &i1, float &l1) {
     float src = 0.5f * (float)o - 0.25f;
@@ -225,6 +293,14 @@ extern "C" int vq3d_conv3d(const vq3d_conv_desc *d, void *stream) {
     p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.bias = d->bias; p.pre_a = d->pre_a; p.pre_b = d->pre_b;
     p.post_scale = d->post_scale; p.post_b = d->post_b; p.residual = d->residual; p.y = d->y;
     const int64_t total = (int64_t)p.B * p.Ho * p.Wo * p.Zo;
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (d->k == 1 && d->stride == 1 && d->pad == 0 && ((int64_t)d->H * d->W * d->Z) % 4 == 0 && d->C1 + d->C2 <= kPwMaxCin &&
+        total >= 65536 && al16(d->x1) && al16(d->x2) && al16(d->y) && al16(d->residual)) {
+        if (p.Cout % 9 == 0) return launch_pointwise<9>(p, stream);
+        if (p.Cout <= 4) return launch_pointwise<4>(p, stream);
+        if (p.Cout <= 8) return launch_pointwise<8>(p, stream);
+        return launch_pointwise<16>(p, stream);
+    }
     const unsigned gx = (unsigned)ceil_div(total, kConvThreads);
     if (p.Cout >= 8) return launch("conv3d<8>", conv3d_generic_kernel<8>, dim3(gx, (unsigned)ceil_div(p.Cout, 8)), dim3(kConvThreads), 0, stream, p);
     if (p.Cout >= 3) return launch("conv3d<4>", conv3d_generic_kernel<4>, dim3(gx, (unsigned)ceil_div(p.Cout, 4)), dim3(kConvThreads), 0, stream, p);

@@ -99,9 +99,13 @@ class PreActFixupResBlock(nn.Module):
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         _no_conv_backward(*self._params())
         o = ops()
-        y = o.preact_block(input, self, _MODE_ID[self.mode])      # one fused launch when covered
-        if y is not None:
-            return y
+        # wide down blocks: the fused SIMT kernel keeps all branch channels of the (2t+2)^3 input window in
+        # shared memory, which leaves it a sliver of a tile at 16 channels; the composed tensor-core path wins
+        wide_down = self.mode == "down" and self.branch_conv1.weight.shape[0] >= 16 and o.precision == "bf16"
+        if not wide_down:
+            y = o.preact_block(input, self, _MODE_ID[self.mode])      # one fused launch when covered
+            if y is not None:
+                return y
         return self.forward_composed(input)
 
     def forward_composed(self, x: torch.Tensor) -> torch.Tensor:

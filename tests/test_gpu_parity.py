@@ -455,3 +455,38 @@ def test_tensor_core_stack_shift_equivariance():
         y = seq(x)
         ys = seq(torch.roll(x, shifts=(32, 64), dims=(2, 3)))
     assert torch.equal(ys, torch.roll(y, shifts=(32, 64), dims=(2, 3)))
+
+
+@pytest.mark.parametrize("C1,C2,Cout,shape,pre_act,res", [
+    (1, 0, 4, (1, 64, 64, 32), False, False),      # parse_input at a reduced size
+    (16, 2, 18, (1, 32, 32, 64), False, False),    # cat + proj (two sources, bias), 9-channel chunks
+    (5, 0, 7, (2, 16, 32, 128), True, True),       # Fixup transforms, residual, ragged channel chunk, batch 2
+    (12, 0, 20, (1, 32, 64, 32), True, False),
+])
+def test_pointwise_kernel_vs_torch(C1, C2, Cout, shape, pre_act, res):
+    """Vectorised 1x1 kernel (conv_kernels.cu::pointwise_kernel) against an fp64 torch reference."""
+    import torch.nn.functional as F
+    from vqvae import _ops
+    o = _ops.default()
+    rs = np.random.RandomState(C1 + 10 * Cout)
+    B, H, W, Z = shape
+    x1 = torch.from_numpy(rs.standard_normal((B, C1, H, W, Z)).astype(np.float32)).to(DEV)
+    x2 = torch.from_numpy(rs.standard_normal((B, C2, H, W, Z)).astype(np.float32)).to(DEV) if C2 else None
+    w = torch.from_numpy((rs.standard_normal((Cout, C1 + C2, 1, 1, 1)) / np.sqrt(C1 + C2)).astype(np.float32)).to(DEV)
+    bias = torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).to(DEV)
+    sc = lambda v: torch.tensor([v], dtype=torch.float32, device=DEV)
+    r = torch.from_numpy(rs.standard_normal((B, Cout, H, W, Z)).astype(np.float32)).to(DEV) if res else None
+    o.profile = []
+    try:
+        got = o.conv3d(x1, w, x2=x2, bias=bias, pre_act=pre_act, pre_a=sc(0.1) if pre_act else None, pre_b=sc(-0.05),
+                       post_scale=sc(0.9), post_b=sc(0.02), residual=r)
+        torch.cuda.synchronize()
+        assert [e[0] for e in o.profile] == ["conv3d"]
+    finally:
+        o.profile = None
+    xin = x1 if x2 is None else torch.cat([x1, x2], 1)
+    xin = F.elu(xin + 0.1) - 0.05 if pre_act else xin - 0.05
+    # fp64 reference (cuDNN's fp32 conv3d may use TF32)
+    ref = torch.einsum("oc,bchwz->bohwz", w.double().flatten(1), xin.double()) * 0.9 + 0.02 + bias.double().view(1, -1, 1, 1, 1)
+    ref = (ref + (r.double() if res else 0)).float()
+    assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5), float((got - ref).abs().max())
