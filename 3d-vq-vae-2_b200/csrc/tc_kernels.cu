@@ -34,6 +34,9 @@ constexpr int kTcM = 128;
 struct TcParams {
     int B, H, W, Z, C1, C2, Cout, k, stride, pad, circ, pre_act, post_act;
     int Ho, Wo, Zo, Npad, Ktot, G;
+    int nsplit, cps;                 // split-K: grid.y splits of cps K-chunks each (1 = no split)
+    float *ws;                       // split-K partial sums [tiles * 128][Npad] fp32 (zeroed by the host per call)
+    unsigned int *ws_cnt;            // split-K arrival counters [tiles]
     const float *x1, *x2, *w, *bias, *pre_a, *pre_b, *post_scale, *post_b, *residual;
     float *y;
 };
@@ -129,13 +132,15 @@ conv3d_tc_kernel(TcParams p) {
     // instruction descriptor: D fp32 (1<<4), A/B bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
 
-    const int nchunks = (Ktot + kTcBK - 1) / kTcBK;
+    const int nchunks_all = (Ktot + kTcBK - 1) / kTcBK;
+    const int chunk0 = (int)blockIdx.y * p.cps;
+    const int nchunks = min(p.cps, nchunks_all - chunk0);          // this CTA's share of the K loop (>= 1)
     for (int it = 0; it < nchunks; ++it) {
         const int s = it & 1;
         if (it >= kTcStages) mbar_wait(&mma_done[s], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs that read this stage are done
         unsigned char *sa = smem + (size_t)s * stage_bytes;
         unsigned char *sb = sa + a_bytes;
-        const int kbase = it * kTcBK;
+        const int kbase = (chunk0 + it) * kTcBK;
         // ---- A: gather + transform + bf16 pack, one 16-byte chunk (8 k's) at a time ----------
         for (int c = g; c < 8; c += G) {
             int kidx = kbase + c * 8;
@@ -215,12 +220,43 @@ conv3d_tc_kernel(TcParams p) {
                          : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (ok) {
+                if (p.nsplit > 1) {        // partial sums of this K slice -> workspace
+                    float *wrow = p.ws + (size_t)vr * Npad + c0;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int co = c0 + e;
-                    if (co < p.Cout) {
-                        const size_t o = ((size_t)bb * p.Cout + co) * So + rem;
-                        float yv = __fmaf_rn(__uint_as_float(acc[e]), sc, sbias);
+                    for (int e = 0; e < 8; ++e)
+                        if (c0 + e < p.Cout) atomicAdd(wrow + e, __uint_as_float(acc[e]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int co = c0 + e;
+                        if (co < p.Cout) {
+                            const size_t o = ((size_t)bb * p.Cout + co) * So + rem;
+                            float yv = __fmaf_rn(__uint_as_float(acc[e]), sc, sbias);
+                            if (p.bias) yv += __ldg(p.bias + co);
+                            if (p.residual) yv += __ldg(p.residual + o);
+                            if (p.post_act) yv = elu1(yv);
+                            p.y[o] = yv;
+                        }
+                    }
+                }
+            }
+        }
+        if (p.nsplit > 1) {
+            // the CTA that arrives last for this M tile owns the output transform
+            __shared__ unsigned int s_ticket;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_ticket = atomicAdd(p.ws_cnt + blockIdx.x, 1u);
+            __syncthreads();
+            if (s_ticket == (unsigned int)p.nsplit - 1) {
+                __threadfence();
+                const int64_t v2 = (int64_t)blockIdx.x * kTcM + r;
+                if (v2 < total) {
+                    const int b2 = (int)(v2 / So);
+                    const int64_t rem2 = v2 - (int64_t)b2 * So;
+                    for (int co = g; co < p.Cout; co += G) {
+                        const size_t o = ((size_t)b2 * p.Cout + co) * So + rem2;
+                        float yv = __fmaf_rn(__ldcg(p.ws + (size_t)v2 * Npad + co), sc, sbias);
                         if (p.bias) yv += __ldg(p.bias + co);
                         if (p.residual) yv += __ldg(p.residual + o);
                         if (p.post_act) yv = elu1(yv);
@@ -242,9 +278,43 @@ conv3d_tc_kernel(TcParams p) {
 
 using namespace vq3d;
 
-extern "C" int vq3d_conv3d_tc(const vq3d_conv_desc *d, void *stream) {
+#ifndef VQ3D_EMU
+// split-K plan: few M tiles (tiny spatial extent, long K = C_in*k^3) leave most SMs idle and make the K loop
+// a serial latency chain; slice K across grid.y and reduce through an fp32 workspace
+static void tc_split_plan(const vq3d_conv_desc *d, int64_t *tiles_out, int *nsplit, int *cps) {
+    const int Ho = (d->H + 2 * d->pad - d->k) / d->stride + 1, Wo = (d->W + 2 * d->pad - d->k) / d->stride + 1,
+              Zo = (d->Z + 2 * d->pad - d->k) / d->stride + 1;
+    const int64_t total = (int64_t)d->B * Ho * Wo * Zo;
+    const int64_t tiles = ceil_div(total, kTcM);
+    const int nchunks = (int)ceil_div((int64_t)(d->C1 + d->C2) * d->k * d->k * d->k, kTcBK);
+    int ns = 1;
+    if (tiles * 2 <= kNumSMs && nchunks >= 4) {
+        ns = (int)((2 * kNumSMs) / tiles);
+        if (ns > nchunks) ns = nchunks;
+    }
+    int c = (int)ceil_div(nchunks, ns);
+    ns = (int)ceil_div(nchunks, c);          // no empty slices
+    *tiles_out = tiles; *nsplit = ns; *cps = c;
+}
+#endif
+
+extern "C" size_t vq3d_conv3d_tc_workspace(const vq3d_conv_desc *d) {
 #ifdef VQ3D_EMU
-    (void)d; (void)stream;
+    (void)d;
+    return 0;
+#else
+    if (!d || d->B < 1 || d->H < 1 || d->W < 1 || d->Z < 1 || d->k < 1 || d->stride < 1 || d->Cout < 1) return 0;
+    int64_t tiles; int ns, cps;
+    tc_split_plan(d, &tiles, &ns, &cps);
+    if (ns <= 1) return 0;
+    const int Npad = (d->Cout + 15) & ~15;
+    return (size_t)tiles * kTcM * Npad * 4 + (size_t)((tiles * 4 + 255) & ~255);
+#endif
+}
+
+extern "C" int vq3d_conv3d_tc(const vq3d_conv_desc *d, void *ws, size_t ws_bytes, void *stream) {
+#ifdef VQ3D_EMU
+    (void)d; (void)ws; (void)ws_bytes; (void)stream;
     return fail(VQ3D_ERR_UNSUPPORTED, "conv3d_tc: tensor-core kernels cannot run in the host emulator");
 #else
     if (!d) return fail(VQ3D_ERR_INVALID, "conv3d_tc: null descriptor");
@@ -268,10 +338,23 @@ extern "C" int vq3d_conv3d_tc(const vq3d_conv_desc *d, void *stream) {
     p.Ktot = (int)Ktot;
     p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.bias = d->bias; p.pre_a = d->pre_a; p.pre_b = d->pre_b;
     p.post_scale = d->post_scale; p.post_b = d->post_b; p.residual = d->residual; p.y = d->y;
-    const int64_t total = (int64_t)p.B * p.Ho * p.Wo * p.Zo;
-    const int64_t tiles = ceil_div(total, kTcM);
-    p.G = tiles >= 2 * kNumSMs ? 2 : 4;      // few tiles: put more gather threads on each
+    int64_t tiles;
+    tc_split_plan(d, &tiles, &p.nsplit, &p.cps);
+    p.ws = nullptr; p.ws_cnt = nullptr;
+    if (p.nsplit > 1) {
+        const size_t need = vq3d_conv3d_tc_workspace(d);
+        if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) {       // no workspace: run unsplit
+            p.nsplit = 1;
+            p.cps = (int)ceil_div(Ktot, kTcBK);
+        } else {
+            cudaError_t e = cudaMemsetAsync(ws, 0, need, static_cast<cudaStream_t>(stream));
+            if (e != cudaSuccess) return check_cuda(e, "conv3d_tc(memset)");
+            p.ws_cnt = static_cast<unsigned int *>(ws);
+            p.ws = reinterpret_cast<float *>(static_cast<unsigned char *>(ws) + ((tiles * 4 + 255) & ~255));
+        }
+    }
+    p.G = tiles * p.nsplit >= 2 * kNumSMs ? 2 : 4;      // few CTAs: put more gather threads on each
     const size_t smem = (size_t)kTcStages * ((size_t)kTcM * kTcBK * 2 + (size_t)p.Npad * kTcBK * 2) + 256;
-    return launch("conv3d_tc", conv3d_tc_kernel, dim3((unsigned)tiles), dim3((unsigned)(kTcM * p.G)), smem, stream, p);
+    return launch("conv3d_tc", conv3d_tc_kernel, dim3((unsigned)tiles, (unsigned)p.nsplit), dim3((unsigned)(kTcM * p.G)), smem, stream, p);
 #endif
 }

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -44,7 +44,8 @@ SIGNATURES = {
     "vq3d_vq_embed_code": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp]),
     "vq3d_vq_backward": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_double, _fp, _fp]),
     "vq3d_conv3d": (C.c_int, [C.POINTER(ConvDesc), _fp]),
-    "vq3d_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), _fp]),
+    "vq3d_conv3d_tc_workspace": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "vq3d_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), _fp, C.c_size_t, _fp]),
     "vq3d_upsample2x": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_preact_block": (C.c_int, [C.POINTER(PreactDesc), _fp]),
     "vq3d_preact_stack": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),

@@ -178,7 +178,10 @@ class Ops:
         meta = dict(nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
                     flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
         if self.precision == "bf16" and Cout >= 8 and Cin * k ** 3 >= 32:
-            if self._call("conv3d_tc", self.lib.vq3d_conv3d_tc, (C.byref(d), self.stream()), allow_unsupported=True, **meta):
+            need = self.lib.vq3d_conv3d_tc_workspace(C.byref(d))       # > 0: few voxels, long K -> split-K through a workspace
+            ws = self._workspace(need, x1.device) if need else None
+            if self._call("conv3d_tc", self.lib.vq3d_conv3d_tc, (C.byref(d), self._p(ws), need, self.stream()),
+                          allow_unsupported=True, **meta):
                 return y
         self._call("conv3d", self.lib.vq3d_conv3d, (C.byref(d), self.stream()), **meta)
         return y

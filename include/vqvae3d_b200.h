@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 3
+#define VQ3D_ABI_VERSION 4
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -127,8 +127,13 @@ int vq3d_conv3d(const vq3d_conv_desc *desc, void *stream);
  * (bf16 operands, fp32 accumulation in TMEM).  For GEMM-shaped layers only: returns
  * VQ3D_ERR_UNSUPPORTED when C_in*k^3 < 32, C_out < 8 or C_out > 256 (callers fall back to
  * vq3d_conv3d).  Results agree with the fp32 kernel to bf16 operand rounding (~1e-2 relative).
+ * Layers with few output voxels and a long reduction (128 -> 128 k3 at 8x8x2 ...) are split along K
+ * across CTAs and reduced through `ws` (fp32 atomics, so their summation order varies run to run):
+ * pass a 16-byte aligned device buffer of vq3d_conv3d_tc_workspace(desc) bytes (0 = no split wanted
+ * for this shape); with ws == NULL the layer runs unsplit.  The call zeroes what it uses.
  */
-int vq3d_conv3d_tc(const vq3d_conv_desc *desc, void *stream);
+size_t vq3d_conv3d_tc_workspace(const vq3d_conv_desc *desc);
+int vq3d_conv3d_tc(const vq3d_conv_desc *desc, void *ws, size_t ws_bytes, void *stream);
 
 /*
  * nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False) of ResizeConv3D
