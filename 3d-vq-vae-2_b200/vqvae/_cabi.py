@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -37,6 +37,8 @@ SIGNATURES = {
     "vq3d_last_error": (C.c_char_p, []),
     "vq3d_is_cuda_build": (C.c_int, []),
     "vq3d_vq_assign": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int64, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "vq3d_vq_assign_tc_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "vq3d_vq_assign_tc": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int64, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "vq3d_vq_loss": (C.c_int, [_fp, C.c_double, C.c_int64, _fp, _fp]),
     "vq3d_vq_ema_update": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_double, C.c_double, _fp, _fp, _fp, _fp]),
     "vq3d_vq_init_stats": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int64, _fp, _fp, _fp]),

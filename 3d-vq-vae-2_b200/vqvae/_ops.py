@@ -26,6 +26,7 @@ class Ops:
         self.precision = "bf16"
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
+        self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # device -> uint8 workspace of the persistent stack kernels (grown on demand)
 
     # -- plumbing ---------------------------------------------------------------------
@@ -98,10 +99,18 @@ class Ops:
         if want_stats:
             stats = torch.zeros(K * (D + 1), dtype=torch.float32, device=x.device)   # one flat all-reduce buffer
             counts, dw = stats[:K], stats[K:]
+        meta = dict(nbytes=B * S * (8 * D + 8), flops=2 * B * S * K * D, tag=f"N{B * S}xD{D}xK{K}")
+        if self.vq_tensor_cores and D in (32, 64, 128) and B * S >= 32768 and K >= 64:
+            need = self.lib.vq3d_vq_assign_tc_workspace(D, K)
+            if need:       # tensor-core candidate pass + exact fp32 re-rank: same bits as the scan below
+                ws = self._workspace(need, x.device)
+                if self._call("vq_assign_tc", self.lib.vq3d_vq_assign_tc,
+                              (self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx), self._p(sqerr), self._p(counts),
+                               self._p(dw), self._p(ws), ws.numel(), self.stream()), kernels=2, allow_unsupported=True, **meta):
+                    return quant, idx, sqerr, stats
         self._call("vq_assign", self.lib.vq3d_vq_assign,
                    (self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx), self._p(sqerr), self._p(counts),
-                    self._p(dw), self.stream()),
-                   nbytes=B * S * (8 * D + 8), flops=2 * B * S * K * D, tag=f"N{B * S}xD{D}xK{K}")
+                    self._p(dw), self.stream()), **meta)
         return quant, idx, sqerr, stats
 
     def vq_loss(self, sqerr: Tensor, commitment_cost: float, numel: int) -> Tensor:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 4
+#define VQ3D_ABI_VERSION 5
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -54,6 +54,18 @@ int vq3d_is_cuda_build(void);
 int vq3d_vq_assign(const float *x, const float *embed, int64_t B, int D, int64_t S, int K,
                    float *quant, int64_t *idx, double *sqerr, float *counts, float *dw,
                    void *stream);
+
+/*
+ * Same contract and bit-identical results as vq3d_vq_assign, for the large problems of the quantizer
+ * sweep (embedding_dim 32, 64 or 128; B*S latent vectors in the tens of thousands and up): the distance
+ * matrix is a tcgen05 candidate pass (bf16 hi/lo split operands, fp32 accumulation in TMEM) and only the
+ * codes within a proven error margin of each row minimum are re-ranked with the reference's exact fp32
+ * arithmetic (rows with too many candidates fall back to the exact full scan).  ws: 256-byte aligned
+ * device buffer of vq3d_vq_assign_tc_workspace(D, K) bytes (codebook operand images); 0 = unsupported D/K.
+ */
+size_t vq3d_vq_assign_tc_workspace(int D, int K);
+int vq3d_vq_assign_tc(const float *x, const float *embed, int64_t B, int D, int64_t S, int K, float *quant, int64_t *idx,
+                      double *sqerr, float *counts, float *dw, void *ws, size_t ws_bytes, void *stream);
 
 /* loss = commitment_cost * sqerr / numel  (F.mse_loss * commitment_cost, layers.py:716-717) */
 int vq3d_vq_loss(const double *sqerr, double commitment_cost, int64_t numel, float *loss, void *stream);

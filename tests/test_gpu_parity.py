@@ -109,7 +109,9 @@ def test_quantizer_ties():
 # run-time-D fallbacks, and sweep-sized cases of BASELINE.json configs[4]
 @pytest.mark.parametrize("N,D,K", [(524288, 2, 128), (8192, 8, 256), (128, 32, 512), (1000, 2, 128), (77, 8, 256),
                                    (4099, 3, 19), (5000, 5, 64), (3001, 6, 40), (20000, 16, 300), (100000, 32, 512),
-                                   (30000, 64, 1024), (9000, 128, 512), (1, 2, 1), (1 << 20, 32, 512)])
+                                   (30000, 64, 1024), (9000, 128, 512), (1, 2, 1), (1 << 20, 32, 512),
+                                   # tensor-core candidate pass (N >= 32768, D in {32, 64, 128}): ragged N, K not a tile multiple
+                                   (65536, 64, 1024), (40000, 128, 2048), (50001, 32, 300), (33000, 128, 96), (70000, 64, 64)])
 def test_quantizer_vs_oracle_index_exact(N, D, K):
     rs = np.random.RandomState(N % 9973 + D * 7 + K)
     x = rs.standard_normal((N, D)).astype(np.float32)
@@ -132,6 +134,54 @@ def test_quantizer_vs_oracle_index_exact(N, D, K):
     _, _, idx2 = q(cw)
     d_self = np.sqrt(((e[ref_idx] - e[idx2.cpu().numpy().reshape(-1)]) ** 2).sum(1))
     assert (d_self == 0).all()
+
+
+def test_quantizer_tensor_core_path_ties_and_overflow():
+    """The tensor-core candidate pass must keep the reference's first-index tie rule: duplicated codebook
+    rows (more candidates than the kernel tracks -> exact full-scan fallback) and grid-snapped data with
+    many exactly equal distances."""
+    from vqvae import _ops
+    o = _ops.default()
+    rs = np.random.RandomState(11)
+    N, D, K = 40000, 32, 512
+    for snap in (False, True):
+        x = rs.standard_normal((N, D)).astype(np.float32)
+        e = rs.standard_normal((K, D)).astype(np.float32)
+        if snap:
+            x, e = np.round(x * 2) / 2, np.round(e * 2) / 2
+        e[100:120] = e[7]                       # 21 identical rows: lowest index must win
+        e[300] = e[299]
+        x[:500] = e[7] + 0.01 * rs.standard_normal((500, D)).astype(np.float32)
+        ref_idx, _ = O.vq_assign_c(x, e)
+        xt = torch.from_numpy(np.ascontiguousarray(x.T)).reshape(1, D, N // 64, 64, 1)
+        q = make_quantizer(K, D, torch.from_numpy(e), 0, False)
+        o.profile = []
+        try:
+            _, quant, idx = q(xt.to(DEV))
+            torch.cuda.synchronize()
+            assert [p[0] for p in o.profile][0] == "vq_assign_tc"
+        finally:
+            o.profile = None
+        got = idx.cpu().numpy().reshape(-1)
+        assert np.array_equal(got, ref_idx), int((got != ref_idx).sum())
+        assert (got[:500] == 7).all()
+        assert np.array_equal(quant.cpu().numpy().reshape(D, N).T, x + (e[ref_idx] - x))
+
+
+def test_quantizer_tensor_core_path_training_statistics():
+    N, D, K = 65536, 32, 512
+    rs = np.random.RandomState(5)
+    x = rs.standard_normal((N, D)).astype(np.float32)
+    e = rs.standard_normal((K, D)).astype(np.float32)
+    q = make_quantizer(K, D, torch.from_numpy(e), 0, True)
+    q.cluster_size.fill_(1.0)
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).reshape(1, D, N // 64, 64, 1)
+    _, _, idx = q(xt.to(DEV))
+    ref_idx, _ = O.vq_assign_c(x, e)
+    assert np.array_equal(idx.cpu().numpy().reshape(-1), ref_idx)
+    n, dw = O.vq_stats_c(x, ref_idx, K)
+    assert close(q.cluster_size, 0.99 + 0.01 * n, rtol=1e-5)
+    assert close(q.embed_avg, 0.99 * e.astype(np.float64) + 0.01 * dw, rtol=1e-4, atol=1e-5)
 
 
 def test_quantizer_ema_statistics_vs_oracle():
