@@ -16,7 +16,7 @@
 
 namespace vq3d {
 
-constexpr int kRowThreads = 256;
+template <int C> constexpr int row_threads() { return C >= 8 ? 256 : 512; }   // wide variants need the registers
 
 struct RowParams {
     int B, H, W, Z;
@@ -43,9 +43,10 @@ struct RowSmem {
 };
 
 template <int C, int CB, bool OUTC>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(row_threads<C>())
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
+    constexpr int kRowThreads = row_threads<C>();
     VQ3D_DYN_SMEM(float, smem);
     float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_wo = smem + SM::wo, *s_t1 = smem + SM::tile;
     const int tid = threadIdx.x;
@@ -73,36 +74,48 @@ preact_row_kernel(RowParams p) {
     const float b1a = ld_scalar(p.b1a, 0.f), b1b = ld_scalar(p.b1b, 0.f), b2a = ld_scalar(p.b2a, 0.f), b2b = ld_scalar(p.b2b, 0.f);
     __syncthreads();
 
-    // ---- stage A ----------------------------------------------------------------------------------
-    for (int rs = slot; rs < nrows_in; rs += nslots) {
-        const int lh = rs / IW, lw = rs - lh * IW;
-        const int gh = rmod(oh0 - 1 + lh, p.H), gw = rmod(ow0 - 1 + lw, p.W);
-        const float *px = xb + ((size_t)gh * p.W + gw) * Z + 4 * zq;
-        float t[CB][4];
+    // ---- stage A (the loads of the next row slot are issued before the arithmetic of the current one) ------
+    {
+        float4 nxt[C];
+        auto issue = [&](int rs) {
+            const int lh = rs / IW, lw = rs - lh * IW;
+            const int gh = rmod(oh0 - 1 + lh, p.H), gw = rmod(ow0 - 1 + lw, p.W);
+            const float *px = xb + ((size_t)gh * p.W + gw) * Z + 4 * zq;
 #pragma unroll
-        for (int cb = 0; cb < CB; ++cb)
+            for (int c = 0; c < C; ++c) nxt[c] = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
+        };
+        if (slot < nrows_in) issue(slot);
+        for (int rs = slot; rs < nrows_in; rs += nslots) {
+            float4 cur[C];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) t[cb][k] = 0.0f;
+            for (int c = 0; c < C; ++c) cur[c] = nxt[c];
+            if (rs + nslots < nrows_in) issue(rs + nslots);
+            float t[CB][4];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
-            const float a0 = elu1(v.x + b1a) + b1b, a1 = elu1(v.y + b1a) + b1b, a2 = elu1(v.z + b1a) + b1b, a3 = elu1(v.w + b1a) + b1b;
+            for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[cb][k] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float4 v = cur[c];
+                const float a0 = elu1(v.x + b1a) + b1b, a1 = elu1(v.y + b1a) + b1b, a2 = elu1(v.z + b1a) + b1b, a3 = elu1(v.w + b1a) + b1b;
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float w = s_w1[c * CB + cb];
+                    t[cb][0] = __fmaf_rn(w, a0, t[cb][0]); t[cb][1] = __fmaf_rn(w, a1, t[cb][1]);
+                    t[cb][2] = __fmaf_rn(w, a2, t[cb][2]); t[cb][3] = __fmaf_rn(w, a3, t[cb][3]);
+                }
+            }
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb) {
-                const float w = s_w1[c * CB + cb];
-                t[cb][0] = __fmaf_rn(w, a0, t[cb][0]); t[cb][1] = __fmaf_rn(w, a1, t[cb][1]);
-                t[cb][2] = __fmaf_rn(w, a2, t[cb][2]); t[cb][3] = __fmaf_rn(w, a3, t[cb][3]);
+                float4 o;
+                o.x = elu1(t[cb][0] + b2a) + b2b; o.y = elu1(t[cb][1] + b2a) + b2b;
+                o.z = elu1(t[cb][2] + b2a) + b2b; o.w = elu1(t[cb][3] + b2a) + b2b;
+                float *row = s_t1 + ((size_t)cb * nrows_in + rs) * ZP;
+                *reinterpret_cast<float4 *>(row + 4 + 4 * zq) = o;
+                if (zq == 0) row[Z + 4] = o.x;              // circular halo: z = Z  -> z = 0
+                if (zq == ZQ - 1) row[3] = o.w;             //                z = -1 -> z = Z-1
             }
-        }
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb) {
-            float4 o;
-            o.x = elu1(t[cb][0] + b2a) + b2b; o.y = elu1(t[cb][1] + b2a) + b2b;
-            o.z = elu1(t[cb][2] + b2a) + b2b; o.w = elu1(t[cb][3] + b2a) + b2b;
-            float *row = s_t1 + ((size_t)cb * nrows_in + rs) * ZP;
-            *reinterpret_cast<float4 *>(row + 4 + 4 * zq) = o;
-            if (zq == 0) row[Z + 4] = o.x;              // circular halo: z = Z  -> z = 0
-            if (zq == ZQ - 1) row[3] = o.w;             //                z = -1 -> z = Z-1
         }
     }
     __syncthreads();
@@ -196,7 +209,7 @@ static int launch_row(const vq3d_preact_desc *d, void *stream) {
     p.y = OUTC ? d->out_y : d->y;
     const int64_t grid = ntiles();
     if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(row): grid too large");
-    return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(kRowThreads), SM::floats(th, tw, d->Z) * 4, stream, p);
+    return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(row_threads<C>()), SM::floats(th, tw, d->Z) * 4, stream, p);
 }
 
 // Z must be a multiple of 4 with Z/4 a power of two <= 32 (a row of Z/4 float4 lanes divides the CTA)

@@ -114,6 +114,47 @@ def physical_gpu_index(local):
     return local
 
 
+def quantizer_point(dev, pk, N=1 << 20, D=32, K=512, reps=10):
+    """Quantizer.forward (eval) on N latent vectors presented as (1, D, N/4096, 64, 64): Gcodes/s and the
+    fraction of min(HBM, tensor) roofline (8D+8 bytes, 2KD flops per vector)."""
+    from vqvae.layers import Quantizer
+    g = torch.Generator().manual_seed(7)
+    q = Quantizer(K, D, 0.1)
+    q.embed.copy_(torch.randn(K, D, generator=g)); q.first_pass.fill_(0)
+    q = q.to(dev).eval()
+    x = torch.randn(1, D, N // 4096, 64, 64, generator=g).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            q(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            q(x)
+        e1.record()
+        torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / reps * 1e-3
+    gc = N / t / 1e9
+    hbm = pk["hbm_gbs"] / (8 * D + 8)
+    tens = pk.get("bf16_tflops_sustained", 1400.0) * 1e3 / (2.0 * K * D)
+    return {"value": gc, "unit": "Gcodes/s", "config": {"N": N, "D": D, "K": K, "mode": "eval", "path": "tcgen05 candidates + exact fp32 re-rank"},
+            "ms": t * 1e3, "roofline": {"bound": "hbm" if hbm < tens else "tensor", "peak": min(hbm, tens), "unit": "Gcodes/s", "frac": gc / min(hbm, tens)},
+            "sweep": "profiles/r01_quantizer_sweep_tc.tsv (tools/bench_quantizer.py)"}
+
+
+def ncu_traffic(kernel_tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    --set full capture (profiles/ncu_traffic.json, written by hand from profiles/*.summary.txt)."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+    for key, val in table.items():
+        if key in kernel_tag:
+            return val
+    return None
+
+
 # ---------------------------------------------------------------------------------------
 def cpu_arm(kind, steps, warmup):
     """The reference's CPU path (oracle port, ATen fp32, all host cores) on a bounded sample."""
@@ -285,6 +326,15 @@ def run_b200(args):
                 for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1]):
                     f.write(f"{k[0]}\t{k[1]}\t{g[0]}\t{g[1]:.3f}\t{g[1] / prof_total:.4f}\t{g[2] / max(g[1], 1e-9) / 1e6:.1f}\t{g[3] / max(g[1], 1e-9) / 1e9:.2f}\n")
                 f.write(f"TOTAL\t\t{sum(g[0] for g in groups.values())}\t{prof_total:.3f}\n")
+        # second half of BASELINE.json's metric: quantizer Gcodes/s on a sweep point (configs[4]), inputs resident in HBM
+        try:
+            line["quantizer"] = quantizer_point(dev, pk)
+        except Exception as ex:  # pragma: no cover
+            line["quantizer"] = {"error": repr(ex)}
+        traffic = ncu_traffic(f"{dom_key[0]} [{dom_key[1]}]")
+        if traffic is not None:
+            line["roofline"]["traffic"] = traffic["dram_bytes_per_launch"]
+            line["roofline"]["traffic_source"] = traffic["source"]
         if not args.no_cpu_baseline and world == 1:
             frac = (shape[2] * shape[3] * shape[4]) / (CPU_SAMPLE_SHAPE[2] * CPU_SAMPLE_SHAPE[3] * CPU_SAMPLE_SHAPE[4])
             times, cores = cpu_arm(kind, 3, 1)
