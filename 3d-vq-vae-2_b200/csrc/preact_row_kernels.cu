@@ -16,7 +16,7 @@
 
 namespace vq3d {
 
-template <int C> constexpr int row_threads() { return C >= 8 ? 256 : 512; }   // wide variants need the registers
+template <int C> struct RowThreads { static constexpr int value = C >= 8 ? 256 : 512; };   // wide variants need the registers
 
 struct RowParams {
     int B, H, W, Z;
@@ -43,10 +43,10 @@ struct RowSmem {
 };
 
 template <int C, int CB, bool OUTC>
-__global__ void __launch_bounds__(row_threads<C>())
+__global__ void __launch_bounds__(RowThreads<C>::value)
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
-    constexpr int kRowThreads = row_threads<C>();
+    constexpr int kRowThreads = RowThreads<C>::value;
     VQ3D_DYN_SMEM(float, smem);
     float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_wo = smem + SM::wo, *s_t1 = smem + SM::tile;
     const int tid = threadIdx.x;
@@ -209,7 +209,7 @@ static int launch_row(const vq3d_preact_desc *d, void *stream) {
     p.y = OUTC ? d->out_y : d->y;
     const int64_t grid = ntiles();
     if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(row): grid too large");
-    return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(row_threads<C>()), SM::floats(th, tw, d->Z) * 4, stream, p);
+    return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(RowThreads<C>::value), SM::floats(th, tw, d->Z) * 4, stream, p);
 }
 
 // Z must be a multiple of 4 with Z/4 a power of two <= 32 (a row of Z/4 float4 lanes divides the CTA)
