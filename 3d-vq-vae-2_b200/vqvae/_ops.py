@@ -278,6 +278,24 @@ class Ops:
                         kernels=n, **meta)
         return res if ok else None
 
+    def evonorm_s0(self, x: Tensor, v: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+        """EvoNorm3D-S0 forward (evonorm.py:70-76), batch 1 like the reference."""
+        x = self._t(x)
+        B, Cc = x.shape[0], x.shape[1]
+        if B != 1:
+            raise RuntimeError("EvoNorm3DS0 supports batch size 1 only (as the reference, evonorm.py:24)")
+        S = x[0, 0].numel()
+        groups = max(Cc // 8, 1)
+        scratch = torch.empty(2 * groups, dtype=torch.float64, device=x.device)
+        std = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        self._call("evonorm_s0_stats", self.lib.vq3d_evonorm_s0_stats,
+                   (self._p(x), Cc, S, groups, float(eps), self._p(scratch), self._p(std), self.stream()), kernels=2, nbytes=4 * x.numel())
+        flat = lambda t: self._p(self._t(t.detach().reshape(-1)))
+        self._call("evonorm_s0_apply", self.lib.vq3d_evonorm_s0_apply,
+                   (self._p(x), flat(v), flat(gamma), flat(beta), self._p(std), Cc, S, self._p(y), self.stream()), nbytes=8 * x.numel())
+        return y
+
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
         decoded, x = self._t(decoded), self._t(x)
         B, _, H, W, Z = x.shape

@@ -185,8 +185,8 @@ class FixupResBlock(nn.Module):
 
 
 class EvonormResBlock(nn.Module):
-    """layers.py:14-98 (`--block-type evonorm`).  Kept for constructor/state_dict
-    compatibility; its EvoNorm3D-S0 kernels are not built yet, so forward raises."""
+    """layers.py:14-98 (`--block-type evonorm`): EvoNorm3D-S0 -> conv bottleneck with biases and zero
+    padding; composed from the EvoNorm kernels and the generic / tensor-core convolutions."""
 
     def __init__(self, in_channels, out_channels, mode, bottleneck_divisor=4):
         super().__init__()
@@ -209,8 +209,23 @@ class EvonormResBlock(nn.Module):
         self.initialize_weights()
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("EvonormResBlock: the EvoNorm3D-S0 kernels are not built yet "
-                                  "(--block-type pre-activation and regular are)")
+        """layers.py:84-91: conv1(EN1(x)) -> conv2(EN2(.)) -> conv3(EN3(.)) + (skip(x) | x); zero padding, conv biases."""
+        _no_conv_backward(*self.parameters())
+        o = ops()
+        stride = 2 if self.mode == "down" else 1
+        t = o.conv3d(self.evonorm_1(input), self.branch_conv1.weight, bias=self.branch_conv1.bias)
+        t = self.evonorm_2(t)
+        if self.mode == "up":
+            t = o.conv3d(o.upsample2x(t), self.branch_conv2.weight, bias=self.branch_conv2.bias, pad=1)
+        else:
+            t = o.conv3d(t, self.branch_conv2.weight, bias=self.branch_conv2.bias, stride=stride, pad=1)
+        if self.skip_conv is None:
+            s = input
+        elif self.mode == "up":
+            s = o.conv3d(o.upsample2x(input), self.skip_conv.weight, bias=self.skip_conv.bias)
+        else:
+            s = o.conv3d(input, self.skip_conv.weight, bias=self.skip_conv.bias, stride=stride)
+        return o.conv3d(self.evonorm_3(t), self.branch_conv3.weight, bias=self.branch_conv3.bias, residual=s)
 
     @torch.no_grad()
     def initialize_weights(self):

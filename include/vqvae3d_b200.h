@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 5
+#define VQ3D_ABI_VERSION 6
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -210,6 +210,15 @@ int vq3d_preact_stack(const vq3d_preact_desc *blocks, int n, float *tmp, void *s
  */
 size_t vq3d_preact_stack_tc_workspace(const vq3d_preact_desc *first_block);
 int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * EvoNorm3D-S0 (vqvae/evonorm.py:12-26,59-76; batch 1 like the reference): per-channel std[c] =
+ * sqrt(unbiased_var(x over the channel group of c) + eps), groups = max(C // 8, 1) (scratch: 2*groups doubles),
+ * then y = x * sigmoid(v[c] * x) * gamma[c] / std[c] + beta[c].  x, y: [C, S].
+ */
+int vq3d_evonorm_s0_stats(const float *x, int C, int64_t S, int groups, double eps, double *scratch, float *std_out, void *stream);
+int vq3d_evonorm_s0_apply(const float *x, const float *v, const float *gamma, const float *beta, const float *std_in,
+                          int C, int64_t S, float *y, void *stream);
 
 /*
  * Loss epilogue of VQVAE.loc_metric, model.py:120-152, fused: loc = ELU(decoded), zero where

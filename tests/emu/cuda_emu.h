@@ -167,6 +167,7 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __expf(float a) { return expf(a); }
 inline float __fdividef(float a, float b) { return a / b; }
 template <typename T> inline T __ldg(const T *p) { return *p; }

@@ -87,7 +87,7 @@ def test_emu_embed_code():
         assert torch.equal(q.embed_code(idx), q.embed[idx])
 
 
-@pytest.mark.parametrize("name", by_kind("block", lambda c: c["cls"] != "EvonormResBlock"))
+@pytest.mark.parametrize("name", by_kind("block"))
 def test_emu_block(name):
     c, g = CASES[name], load(name)
     with use_emulator(), torch.no_grad():
@@ -116,7 +116,7 @@ def _build_model(cfg):
     return m
 
 
-@pytest.mark.parametrize("name", ["tiny2_preact", "tiny2_regular"])
+@pytest.mark.parametrize("name", ["tiny2_preact", "tiny2_regular", "tiny2_evonorm"])
 def test_emu_model(name):
     c, g = CASES[name], load(name)
     with use_emulator(), torch.no_grad():

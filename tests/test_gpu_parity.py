@@ -212,7 +212,7 @@ def test_embed_code():
     assert torch.equal(q.embed_code(idx), q.embed[idx])
 
 
-@pytest.mark.parametrize("name", by_kind("block", lambda c: c["cls"] != "EvonormResBlock"))
+@pytest.mark.parametrize("name", by_kind("block"))
 def test_block_golden(name):
     c, g = CASES[name], load(name)
     with torch.no_grad():
@@ -235,7 +235,7 @@ def _golden_model(name):
     return c, m.to(DEV)
 
 
-@pytest.mark.parametrize("name", ["tiny2_preact", "tiny3_preact", "tiny2_regular"])
+@pytest.mark.parametrize("name", ["tiny2_preact", "tiny3_preact", "tiny2_regular", "tiny2_evonorm"])
 def test_model_golden(name):
     g = load(name)
     c, m = _golden_model(name)
