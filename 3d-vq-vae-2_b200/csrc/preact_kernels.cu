@@ -412,6 +412,7 @@ extern "C" int vq3d_preact_block(const vq3d_preact_desc *d, void *stream) {
     rc = preact_row_dispatch(d, stream, &handled);
     if (rc || handled) return rc;
     if (d->out_w) return fail(VQ3D_ERR_UNSUPPORTED, "preact_block: no kernel fuses the trailing 1x1 convolution for this shape");
+    if (d->pre_w) return fail(VQ3D_ERR_UNSUPPORTED, "preact_block: no kernel fuses the leading 1x1 convolution for this shape");
     const FusedEntry *e = find_fused(d);
     if (!e) return fail(VQ3D_ERR_UNSUPPORTED, "preact_block: no fused instantiation for Cin=%d Cb=%d Cout=%d mode=%d", d->Cin, d->Cb, d->Cout, d->mode);
     return e->fn(d, stream);

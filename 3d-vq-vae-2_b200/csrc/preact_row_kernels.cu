@@ -212,6 +212,245 @@ static int launch_row(const vq3d_preact_desc *d, void *stream) {
     return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(RowThreads<C>::value), SM::floats(th, tw, d->Z) * 4, stream, p);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 'down' blocks at the big levels (4 -> 4 -> 8 at 512^3, 8 -> 8 -> 16 at 256^3; layers.py:124-126,164-171):
+// conv1 1x1, conv2 k4 s2 circular, conv3 1x1, skip k2 s2.  Same depth-row organisation: stage A computes t1
+// for the (2t+2)^2 input rows of a (t x t) output-row tile over the FULL depth and keeps the raw centre rows
+// for the skip convolution; stage B gives each thread 4 consecutive output z of ONE branch channel (the CB
+// threads of a voxel sit in adjacent lanes and exchange t2 by shuffles for conv3).  Optionally the encoder's
+// parse_input 1x1 convolution (layers.py:535,578) is applied on the fly to a 1-channel input.
+constexpr int kDownThreads = 256;
+
+struct DownParams {
+    int B, H, W, Z;                   // input extent
+    int tho, two, ntho, ntwo;         // output-row tile
+    const float *x, *w1, *w2, *w3, *ws;
+    const float *b1a, *b1b, *b2a, *b2b, *b3a, *b3b, *b4, *scale, *b1c, *b1d;
+    const float *pre_w, *pre_b;       // fused parse_input (1 -> CIN) or NULL
+    float *y;
+};
+
+template <int CIN, int CB, int COUT, bool PARSE>
+struct DownSmem {
+    static constexpr int CX = PARSE ? 1 : CIN;
+    static constexpr int w1 = 0;                         // [CIN][CB]
+    static constexpr int w2 = w1 + CIN * CB;             // [CB ci][16 (kh,kw)][CB co][4 kz]
+    static constexpr int w3 = w2 + CB * 16 * CB * 4;     // [CB][COUT]
+    static constexpr int ws = w3 + CB * COUT;            // [CIN][8 taps][COUT]
+    static constexpr int pw = ws + CIN * 8 * COUT;       // [CIN] w, [CIN] b
+    static constexpr int tile = (pw + 2 * CIN + 3) & ~3;
+    static size_t floats(int tho, int two, int Z) {
+        return tile + (size_t)CB * (2 * tho + 2) * (2 * two + 2) * (Z + 8) + (size_t)CX * 4 * tho * two * Z;
+    }
+};
+
+template <int CIN, int CB, int COUT, bool PARSE>
+__global__ void __launch_bounds__(kDownThreads)
+preact_down_row_kernel(DownParams p) {
+    using SM = DownSmem<CIN, CB, COUT, PARSE>;
+    constexpr int CX = SM::CX, NPC = COUT / CB;
+    static_assert(COUT % CB == 0 && (CB & (CB - 1)) == 0 && CB <= 32, "one branch channel per lane, CB lanes per voxel");
+    VQ3D_DYN_SMEM(float, smem);
+    float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_ws = smem + SM::ws, *s_pw = smem + SM::pw;
+    const int tid = threadIdx.x;
+    const int Z = p.Z, ZQ = Z >> 2, ZQo = Z >> 3, ZP = Z + 8, Zo = Z >> 1;
+    const int IW = 2 * p.two + 2, nrows_in = (2 * p.tho + 2) * IW, nrows_out = p.tho * p.two, ICW = 2 * p.two;
+    float *s_t1 = smem + SM::tile;
+    float *s_x = s_t1 + (size_t)CB * nrows_in * ZP;       // [CX][4*tho*two centre rows][Z]
+    const int ncentre = 4 * p.tho * p.two;
+    const int64_t S = (int64_t)p.H * p.W * Z, So = S >> 3;
+    const int Ho = p.H >> 1, Wo = p.W >> 1;
+
+    int bid = blockIdx.x;
+    const int twi = bid % p.ntwo; bid /= p.ntwo;
+    const int thi = bid % p.ntho; bid /= p.ntho;
+    const int b = bid, oh0 = thi * p.tho, ow0 = twi * p.two;
+    const float *xb = p.x + (size_t)b * CX * S;
+
+    for (int i = tid; i < CIN * CB; i += kDownThreads) s_w1[i] = p.w1[(i % CB) * CIN + i / CB];
+    for (int i = tid; i < CB * 16 * CB * 4; i += kDownThreads) {
+        const int kz = i & 3, co = (i >> 2) % CB, hw = (i / (4 * CB)) % 16, ci = i / (64 * CB);
+        s_w2[i] = p.w2[((size_t)co * CB + ci) * 64 + hw * 4 + kz];
+    }
+    for (int i = tid; i < CB * COUT; i += kDownThreads) s_w3[i] = p.w3[(i % COUT) * CB + i / COUT];
+    for (int i = tid; i < CIN * 8 * COUT; i += kDownThreads) {
+        const int c = i % COUT, t = (i / COUT) % 8, ci = i / (8 * COUT);
+        s_ws[i] = p.ws[((size_t)c * CIN + ci) * 8 + t];
+    }
+    if (PARSE && tid < CIN) { s_pw[tid] = p.pre_w[tid]; s_pw[CIN + tid] = p.pre_b ? p.pre_b[tid] : 0.0f; }
+    const float b1a = ld_scalar(p.b1a, 0.f), b1b = ld_scalar(p.b1b, 0.f), b2a = ld_scalar(p.b2a, 0.f), b2b = ld_scalar(p.b2b, 0.f);
+    __syncthreads();
+
+    // ---- stage A: t1 on the haloed input rows, raw centre rows for the skip ---------------------------------
+    {
+        const int zq = tid % ZQ, slot = tid / ZQ, nslots = kDownThreads / ZQ;
+        for (int rs = slot; rs < nrows_in; rs += nslots) {
+            const int lh = rs / IW, lw = rs - lh * IW;
+            const int gh = rmod(2 * oh0 - 1 + lh, p.H), gw = rmod(2 * ow0 - 1 + lw, p.W);
+            const float *px = xb + ((size_t)gh * p.W + gw) * Z + 4 * zq;
+            float4 raw[CX];
+#pragma unroll
+            for (int c = 0; c < CX; ++c) raw[c] = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
+            const bool centre = lh >= 1 && lh <= 2 * p.tho && lw >= 1 && lw <= 2 * p.two;
+            if (centre) {
+                const int ir = (lh - 1) * ICW + (lw - 1);
+#pragma unroll
+                for (int c = 0; c < CX; ++c) *reinterpret_cast<float4 *>(s_x + ((size_t)c * ncentre + ir) * Z + 4 * zq) = raw[c];
+            }
+            float t[CB][4];
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[cb][k] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                float4 v;
+                if (PARSE) {
+                    const float w = s_pw[c], bb = s_pw[CIN + c];
+                    v.x = __fmaf_rn(w, raw[0].x, bb); v.y = __fmaf_rn(w, raw[0].y, bb); v.z = __fmaf_rn(w, raw[0].z, bb); v.w = __fmaf_rn(w, raw[0].w, bb);
+                } else {
+                    v = raw[PARSE ? 0 : c];
+                }
+                const float a0 = elu1(v.x + b1a) + b1b, a1 = elu1(v.y + b1a) + b1b, a2 = elu1(v.z + b1a) + b1b, a3 = elu1(v.w + b1a) + b1b;
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float w = s_w1[c * CB + cb];
+                    t[cb][0] = __fmaf_rn(w, a0, t[cb][0]); t[cb][1] = __fmaf_rn(w, a1, t[cb][1]);
+                    t[cb][2] = __fmaf_rn(w, a2, t[cb][2]); t[cb][3] = __fmaf_rn(w, a3, t[cb][3]);
+                }
+            }
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                float4 o;
+                o.x = elu1(t[cb][0] + b2a) + b2b; o.y = elu1(t[cb][1] + b2a) + b2b;
+                o.z = elu1(t[cb][2] + b2a) + b2b; o.w = elu1(t[cb][3] + b2a) + b2b;
+                float *row = s_t1 + ((size_t)cb * nrows_in + rs) * ZP;
+                *reinterpret_cast<float4 *>(row + 4 + 4 * zq) = o;
+                if (zq == 0) row[Z + 4] = o.x;
+                if (zq == ZQ - 1) row[3] = o.w;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B + C: thread = (output row slot, 4 output z, ONE branch channel co) ---------------------------
+    const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
+    const float b1c = ld_scalar(p.b1c, 0.f), b1d = ld_scalar(p.b1d, 0.f);
+    const int co = tid % CB, lane = (tid / CB) % ZQo, slot = tid / (CB * ZQo), nslots = kDownThreads / (CB * ZQo);
+    const int nrounds = (nrows_out + nslots - 1) / nslots;
+    for (int rd = 0; rd < nrounds; ++rd) {             // every thread runs every round: the shuffles below are warp-wide
+        const int ro = rd * nslots + slot;
+        const bool live = ro < nrows_out;
+        const int lho = live ? ro / p.two : 0, lwo = live ? ro - lho * p.two : 0;
+        const int oh = oh0 + lho, ow = ow0 + lwo;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+            for (int hw = 0; hw < 16; ++hw) {
+                const int kh = hw >> 2, kw = hw & 3;
+                const float *row = s_t1 + ((size_t)ci * nrows_in + (2 * lho + kh) * IW + 2 * lwo + kw) * ZP + 8 * lane;
+                const float4 m0 = *reinterpret_cast<const float4 *>(row + 4), m1 = *reinterpret_cast<const float4 *>(row + 8);
+                const float v[10] = {row[3], m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, row[12]};
+                const float4 w = *reinterpret_cast<const float4 *>(s_w2 + (((size_t)ci * 16 + hw) * CB + co) * 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[k] = __fmaf_rn(w.x, v[2 * k], acc[k]); acc[k] = __fmaf_rn(w.y, v[2 * k + 1], acc[k]);
+                    acc[k] = __fmaf_rn(w.z, v[2 * k + 2], acc[k]); acc[k] = __fmaf_rn(w.w, v[2 * k + 3], acc[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = elu1(acc[k] + b3a) + b3b;
+        // conv3: this lane produces output channels co*NPC .. co*NPC+NPC-1 from the CB lanes' t2
+        float out[NPC][4];
+#pragma unroll
+        for (int j = 0; j < NPC; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[j][k] = 0.0f;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+            float tv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tv[k] = __shfl_sync(0xffffffffu, acc[k], cb, CB);
+#pragma unroll
+            for (int j = 0; j < NPC; ++j) {
+                const float w = s_w3[cb * COUT + co * NPC + j];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out[j][k] = __fmaf_rn(w, tv[k], out[j][k]);
+            }
+        }
+        if (live && oh < Ho && ow < Wo) {
+            // skip: k2 s2 on (x + b1c), zero padding never reached (even extents)
+            float sk[NPC][4];
+#pragma unroll
+            for (int j = 0; j < NPC; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sk[j][k] = 0.0f;
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+                const int ir = (2 * lho + (t2 >> 1)) * ICW + 2 * lwo + (t2 & 1);
+                float4 r0[CX], r1[CX];
+#pragma unroll
+                for (int c = 0; c < CX; ++c) {
+                    const float *rx = s_x + ((size_t)c * ncentre + ir) * Z + 8 * lane;
+                    r0[c] = *reinterpret_cast<const float4 *>(rx); r1[c] = *reinterpret_cast<const float4 *>(rx + 4);
+                }
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    float xv[8];
+                    const float4 a = r0[PARSE ? 0 : ci], bq = r1[PARSE ? 0 : ci];
+                    xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = bq.x; xv[5] = bq.y; xv[6] = bq.z; xv[7] = bq.w;
+                    if (PARSE) {
+                        const float w = s_pw[ci], bb = s_pw[CIN + ci];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) xv[e] = __fmaf_rn(w, xv[e], bb);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) xv[e] += b1c;
+#pragma unroll
+                    for (int j = 0; j < NPC; ++j) {
+                        const float w0 = s_ws[(ci * 8 + t2 * 2 + 0) * COUT + co * NPC + j], w1 = s_ws[(ci * 8 + t2 * 2 + 1) * COUT + co * NPC + j];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sk[j][k] = __fmaf_rn(w1, xv[2 * k + 1], __fmaf_rn(w0, xv[2 * k], sk[j][k]));
+                    }
+                }
+            }
+            const size_t off = ((size_t)oh * Wo + ow) * Zo + 4 * lane;
+#pragma unroll
+            for (int j = 0; j < NPC; ++j) {
+                float4 yv;
+                yv.x = __fmaf_rn(out[j][0], sc, b4) + (sk[j][0] + b1d); yv.y = __fmaf_rn(out[j][1], sc, b4) + (sk[j][1] + b1d);
+                yv.z = __fmaf_rn(out[j][2], sc, b4) + (sk[j][2] + b1d); yv.w = __fmaf_rn(out[j][3], sc, b4) + (sk[j][3] + b1d);
+                *reinterpret_cast<float4 *>(p.y + ((size_t)b * COUT + co * NPC + j) * So + off) = yv;
+            }
+        }
+    }
+}
+
+template <int CIN, int CB, int COUT, bool PARSE>
+static int launch_down_row(const vq3d_preact_desc *d, void *stream) {
+    using SM = DownSmem<CIN, CB, COUT, PARSE>;
+    DownParams p;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z;
+    const int Ho = d->H / 2, Wo = d->W / 2;
+    int tho = Ho < 2 ? Ho : 2, two = Wo < 2 ? Wo : 2;
+    const size_t cap = 112 * 1024;
+    while (SM::floats(tho, two, d->Z) * 4 > cap) {
+        if (tho >= two && tho > 1) tho = 1;
+        else if (two > 1) two = 1;
+        else return fail(VQ3D_ERR_UNSUPPORTED, "preact_block(down row): tile does not fit shared memory");
+    }
+    p.tho = tho; p.two = two; p.ntho = (int)ceil_div(Ho, tho); p.ntwo = (int)ceil_div(Wo, two);
+    p.x = d->x; p.w1 = d->w1; p.w2 = d->w2; p.w3 = d->w3; p.ws = d->wskip;
+    p.b1a = d->b1a; p.b1b = d->b1b; p.b2a = d->b2a; p.b2b = d->b2b; p.b3a = d->b3a; p.b3b = d->b3b; p.b4 = d->b4; p.scale = d->scale;
+    p.b1c = d->b1c; p.b1d = d->b1d; p.pre_w = d->pre_w; p.pre_b = d->pre_b; p.y = d->y;
+    const int64_t grid = (int64_t)d->B * p.ntho * p.ntwo;
+    if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(down row): grid too large");
+    return launch("preact_down_row", preact_down_row_kernel<CIN, CB, COUT, PARSE>, dim3((unsigned)grid), dim3(kDownThreads),
+                  SM::floats(tho, two, d->Z) * 4, stream, p);
+}
+
 // Z must be a multiple of 4 with Z/4 a power of two <= 32 (a row of Z/4 float4 lanes divides the CTA)
 static bool row_shape_ok(const vq3d_preact_desc *d) {
     const int zq = d->Z / 4;
@@ -221,6 +460,17 @@ static bool row_shape_ok(const vq3d_preact_desc *d) {
 
 int preact_row_dispatch(const vq3d_preact_desc *d, void *stream, bool *handled) {
     *handled = false;
+    if (d->mode == 1 && d->wskip && !d->out_w) {
+        // down: even extents, Z/8 output lanes per row and CB lanes per voxel must tile the 256-thread CTA
+        const int zqo = d->Z / 8;
+        const bool shape = d->Z % 8 == 0 && zqo >= 1 && (zqo & (zqo - 1)) == 0 && d->Z / 4 <= 32 && !((d->H | d->W) & 1) &&
+                           (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0;
+        int (*fn)(const vq3d_preact_desc *, void *) = nullptr;
+        if (shape && d->Cin == 4 && d->Cb == 4 && d->Cout == 8 && zqo * 4 <= kDownThreads) fn = d->pre_w ? launch_down_row<4, 4, 8, true> : launch_down_row<4, 4, 8, false>;
+        else if (shape && !d->pre_w && d->Cin == 8 && d->Cb == 8 && d->Cout == 16 && zqo * 8 <= kDownThreads) fn = launch_down_row<8, 8, 16, false>;
+        if (fn) { *handled = true; return fn(d, stream); }
+        return VQ3D_OK;
+    }
     if (d->mode != 0 || d->wskip || d->Cin != d->Cout || !row_shape_ok(d)) return VQ3D_OK;
     const bool outc = d->out_w != nullptr;
     int (*fn)(const vq3d_preact_desc *, void *) = nullptr;

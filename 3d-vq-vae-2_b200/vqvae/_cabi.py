@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -28,7 +28,7 @@ class PreactDesc(C.Structure):
     """struct vq3d_preact_desc"""
     _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "Z", "Cin", "Cb", "Cout", "mode")] + \
                [(n, _fp) for n in ("x", "w1", "w2", "w3", "wskip", "b1a", "b1b", "b2a", "b2b", "b3a", "b3b", "b4",
-                                   "scale", "b1c", "b1d", "y", "out_w", "out_b", "out_y")]
+                                   "scale", "b1c", "b1d", "y", "out_w", "out_b", "out_y", "pre_w", "pre_b")]
 
 
 # name -> (restype, argtypes); the single source of truth for tests/test_cabi_symbols.py

@@ -205,8 +205,11 @@ class Ops:
                     self.stream()), nbytes=4 * B * Cc * H * W * Z * 9, tag=f"{Cc}ch @{H}x{W}x{Z}")
         return y
 
-    def preact_desc(self, x: Tensor, y: Optional[Tensor], blk, mode: int, tail=None, out_y: Optional[Tensor] = None) -> "_cabi.PreactDesc":
+    def preact_desc(self, x: Tensor, y: Optional[Tensor], blk, mode: int, tail=None, out_y: Optional[Tensor] = None,
+                    pre=None) -> "_cabi.PreactDesc":
         B, Cin, H, W, Z = x.shape
+        if pre is not None:          # fused leading 1x1 conv: x is its 1-channel input, the block sees pre's output channels
+            Cin = pre.weight.shape[0]
         w1, w2, w3 = blk.branch_conv1.weight, blk.branch_conv2.weight, blk.branch_conv3.weight
         skip = blk.skip_conv.weight if blk.skip_conv is not None else None
         g = lambda n: self._p(self._t(getattr(blk, n).data)) if hasattr(blk, n) else None
@@ -218,23 +221,30 @@ class Ops:
                                 y=None if y is None else self._p(y),
                                 out_w=None if tail is None else self._p(self._t(tail.weight.data)),
                                 out_b=None if tail is None or tail.bias is None else self._p(self._t(tail.bias.data)),
-                                out_y=None if out_y is None else self._p(out_y))
+                                out_y=None if out_y is None else self._p(out_y),
+                                pre_w=None if pre is None else self._p(self._t(pre.weight.data)),
+                                pre_b=None if pre is None or pre.bias is None else self._p(self._t(pre.bias.data)))
 
-    def preact_block(self, x: Tensor, blk, mode: int) -> Optional[Tensor]:
-        """Whole PreActFixupResBlock in one launch; None if no fused kernel covers the shape."""
+    def preact_block(self, x: Tensor, blk, mode: int, pre=None) -> Optional[Tensor]:
+        """Whole PreActFixupResBlock in one launch; None if no fused kernel covers the shape.  pre: a 1x1 Conv3d
+        (1 -> Cin channels) applied to x on the fly (the encoder's parse_input)."""
         x = self._t(x)
         B, Cin, H, W, Z = x.shape
+        if pre is not None:
+            if Cin != 1 or pre.weight.shape[1] != 1:
+                return None
+            Cin = pre.weight.shape[0]
         Cout = blk.branch_conv3.weight.shape[0]
         sp = {0: (H, W, Z), 1: (H // 2, W // 2, Z // 2), 2: (2 * H, 2 * W, 2 * Z)}[mode]
         y = torch.empty((B, Cout) + sp, dtype=torch.float32, device=x.device)
-        d = self.preact_desc(x, y, blk, mode)
+        d = self.preact_desc(x, y, blk, mode, pre=pre)
         si, so = H * W * Z, sp[0] * sp[1] * sp[2]
         Cb = blk.branch_conv1.weight.shape[0]
         k3 = blk.branch_conv2.weight.shape[2] ** 3
         ok = self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()), allow_unsupported=True,
-                        nbytes=4 * B * (Cin * si + Cout * so),
+                        nbytes=4 * B * ((1 if pre is not None else Cin) * si + Cout * so),
                         flops=2 * B * (Cin * Cb * si + Cb * Cb * k3 * so + Cb * Cout * so + (Cin * Cout * so * (8 if mode == 1 else 1) if blk.skip_conv is not None else 0)),
-                        tag=f"{('same', 'down', 'up')[mode]} {Cin}->{Cb}->{Cout} @{H}x{W}x{Z}")
+                        tag=f"{'in+' if pre is not None else ''}{('same', 'down', 'up')[mode]} {Cin}->{Cb}->{Cout} @{H}x{W}x{Z}")
         return y if ok else None
 
     # (C, Cb) pairs whose 'same' blocks run on the tensor-core stack kernel in bf16 mode

@@ -241,12 +241,23 @@ class BlockSequence(nn.Sequential):
     equal-shape 'same' PreAct blocks to one vq3d_preact_stack call (the 50/150-deep stacks of
     layers.py:492-494,566-569 are launch-latency bound when run block by block)."""
 
-    def forward(self, x: torch.Tensor, tail: Optional[nn.Module] = None) -> torch.Tensor:  # type: ignore[override]
-        """tail: a 1x1 convolution applied after the last block (the decoder's `out`, layers.py:516); it is
-        fused into the last block's kernel where one covers the shape, otherwise run after it."""
+    def forward(self, x: torch.Tensor, tail: Optional[nn.Module] = None, pre: Optional[nn.Module] = None) -> torch.Tensor:  # type: ignore[override]
+        """tail: a 1x1 convolution applied after the last block (the decoder's `out`, layers.py:516); pre: one
+        applied before the first block (the encoder's parse_input, layers.py:578).  Each is fused into the
+        neighbouring block's kernel where one covers the shape, otherwise run on its own."""
         mods = list(self)
         i = 0
         done_tail = tail is None
+        if pre is not None:
+            y = None
+            m0 = mods[0] if mods else None
+            if isinstance(m0, PreActFixupResBlock) and m0.mode == "down":
+                _no_conv_backward(*m0.parameters(), *pre.parameters())
+                y = ops().preact_block(x, m0, _MODE_ID[m0.mode], pre=pre)
+            if y is not None:
+                x, i = y, 1
+            else:
+                x = pre(x)
         while i < len(mods):
             m = mods[i]
             j = i
@@ -289,8 +300,8 @@ class DownBlock(nn.Module):
                for _ in range(n_post_downscale_blocks)))
             for i in range(n_down)))
 
-    def forward(self, data):
-        return self.layers(data)
+    def forward(self, data, pre=None):
+        return self.layers(data, pre=pre)
 
 
 class UpBlock(nn.Module):
@@ -387,10 +398,10 @@ class Encoder2(nn.Module):
             before = after
 
     def forward(self, data: torch.Tensor):
-        down = self.parse_input(data)
+        down = data
         pyramid = []
-        for block in self.down:
-            down = block(down)
+        for i, block in enumerate(self.down):
+            down = block(down, pre=self.parse_input) if i == 0 else block(down)     # parse_input rides on the first block
             pyramid.append(down)
         aux = None
         levels = []

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 6
+#define VQ3D_ABI_VERSION 7
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -180,6 +180,11 @@ typedef struct vq3d_preact_desc {
      * VQ3D_ERR_UNSUPPORTED (run the block and the convolution separately). */
     const float *out_w, *out_b;
     float *out_y;
+    /* optional leading 1x1 convolution fused into the block's loads (the encoder's parse_input, layers.py:535,578:
+     * 1 -> Cin channels with bias): when pre_w != NULL, x is a ONE-channel tensor [B, 1, S] and the block's input is
+     * pre_w[c] * x + pre_b[c].  Honoured by vq3d_preact_block for the 'down' shapes the row kernel covers;
+     * otherwise VQ3D_ERR_UNSUPPORTED. */
+    const float *pre_w, *pre_b;
 } vq3d_preact_desc;
 
 #define VQ3D_OK 0

@@ -126,6 +126,10 @@ inline void __syncthreads() { emu::ctx.b->bar.arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.w->bar.arrive_and_wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
+// width < 32: the warp is split into segments of `width` lanes, src is relative to the caller's segment
+template <typename T> inline T __shfl_sync(unsigned, T v, int src, int width) {
+    return emu::shfl(v, (emu::ctx.lane / width) * width + (src % width));
+}
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl(v, emu::ctx.lane ^ m); }
 template <typename T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu::shfl(v, emu::ctx.lane + d); }
 template <typename T> inline T __shfl_up_sync(unsigned, T v, int d) { return emu::shfl(v, emu::ctx.lane - d); }

@@ -204,3 +204,27 @@ def test_emu_row_kernel(c, shape, n, tail):
         assert o.launches - n0 == n, "expected one fused launch per block (trailing conv included)"
         assert y.shape == ref.shape
         assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())
+
+
+@pytest.mark.parametrize("cin,cout,shape,parse", [
+    (4, 8, (1, 4, 8, 12, 16), False),      # down row kernel: 2x2 output-row tiles, wrap on every axis
+    (4, 8, (2, 1, 6, 4, 8), True),         # fused parse_input (1 -> 4), batch 2, Z/8 = 1 output lane
+    (8, 16, (1, 8, 4, 8, 32), False),
+    (4, 8, (1, 1, 10, 6, 64), True),       # ragged number of tiles in H (5 output rows)
+])
+def test_emu_down_row_kernel(cin, cout, shape, parse):
+    """preact_row_kernels.cu::preact_down_row_kernel (the encoder's 512^3 / 256^3 down blocks) vs the composed path."""
+    torch.manual_seed(cin + cout + shape[-1])
+    with use_emulator() as o, torch.no_grad():
+        blk = L.PreActFixupResBlock(cin, cout, "down").eval()
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        pre = L.Conv3d(1, cin, kernel_size=1) if parse else None
+        x = torch.randn(shape)
+        ref = blk.forward_composed(pre(x) if parse else x)
+        seq = L.BlockSequence(blk)
+        n0 = o.launches
+        y = seq(x, pre=pre) if parse else seq(x)
+        assert o.launches - n0 == 1, "expected one fused launch"
+        assert y.shape == ref.shape
+        assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())
