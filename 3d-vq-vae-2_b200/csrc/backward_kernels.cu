@@ -1,0 +1,349 @@
+// backward_kernels.cu -- gradients of the generic fused convolution (vq3d_conv3d), of the trilinear x2
+// upsampling and of the Huber epilogue: what torch.autograd derives for the reference's nn.Conv3d / F.pad /
+// F.elu / nn.Upsample / F.smooth_l1_loss chains (vqvae/layers.py:176-195,591-597; model.py:120-163).
+// Shape-generic fp32 SIMT kernels (correctness first: the training step composes blocks from them).
+//
+//   forward:  u = pre_act ? ELU(x + a) + b : x + b ;  raw = conv(u, w) ;  y = raw * s + pb + bias[co] + residual
+//   backward: g_raw = gy * s
+//             gu[ci, i]   = sum_{co, taps that read i} w[co, ci, tap] * g_raw[co, o]           (dgrad, gather form)
+//             gx          = gu * (pre_act ? ELU'(x + a) : 1);   d a = sum gx;   d b = sum gu
+//             gw[co,ci,t] = sum_o g_raw[co, o] * u[ci, in(o, t)]                                (wgrad)
+//             d bias[co]  = sum_o gy[co, o];   d pb = sum gy;   d s = sum gy * raw;   d residual = gy
+#include "vq3d_rt.h"
+
+namespace vq3d {
+
+struct BwdParams {
+    int B, H, W, Z, C1, C2, Cout, k, stride, pad, circ, pre_act;
+    int Ho, Wo, Zo;
+    const float *x1, *x2, *w, *pre_a, *pre_b, *post_scale;
+    const float *gy, *raw;
+    float *gx1, *gx2, *gw, *gbias, *gscal;      // gscal: [d pre_a, d pre_b, d post_scale, d post_b]
+};
+
+__device__ __forceinline__ float block_sum(float v, float *red /* [32] shared */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.0f;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += red[w];
+    return t;    // valid in thread 0
+}
+
+// outputs o (per axis) whose window tap kk reads input index i: o*stride - pad + kk == i (mod n when circular)
+__device__ __forceinline__ int taps_of(int i, int n_in, int n_out, int k, int stride, int pad, int circ, int *o_list, int *k_list) {
+    int cnt = 0;
+    for (int kk = 0; kk < k; ++kk) {
+        for (int sh = (circ ? -1 : 0); sh <= (circ ? 1 : 0); ++sh) {
+            const int num = i + sh * n_in + pad - kk;
+            if (num < 0 || num % stride != 0) continue;
+            const int o = num / stride;
+            if (o >= n_out) continue;
+            const int src = o * stride - pad + kk;          // the un-wrapped coordinate the forward pass read
+            if (circ ? (src < -n_in || src >= 2 * n_in) : (src < 0 || src >= n_in)) continue;
+            if (cnt < 12) { o_list[cnt] = o; k_list[cnt] = kk; ++cnt; }
+        }
+    }
+    return cnt;
+}
+
+// one thread = one input voxel x one input channel (blockIdx.y)
+__global__ void __launch_bounds__(128)
+conv3d_dgrad_kernel(BwdParams p) {
+    __shared__ float red[32];
+    const int Cin = p.C1 + p.C2, k = p.k, k3 = k * k * k;
+    const int ci = blockIdx.y;
+    const int64_t S = (int64_t)p.H * p.W * p.Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = v < (int64_t)p.B * S;
+    const float sc = ld_scalar(p.post_scale, 1.0f);
+    float gu = 0.0f, gx = 0.0f;
+    if (active) {
+        const int b = (int)(v / S);
+        int64_t r = v - (int64_t)b * S;
+        const int ih = (int)(r / ((int64_t)p.W * p.Z));
+        r -= (int64_t)ih * p.W * p.Z;
+        const int iw = (int)(r / p.Z), iz = (int)(r - (int64_t)iw * p.Z);
+        int oh[12], kh[12], ow[12], kw[12], oz[12], kz[12];
+        const int nh = taps_of(ih, p.H, p.Ho, k, p.stride, p.pad, p.circ, oh, kh);
+        const int nw = taps_of(iw, p.W, p.Wo, k, p.stride, p.pad, p.circ, ow, kw);
+        const int nz = taps_of(iz, p.Z, p.Zo, k, p.stride, p.pad, p.circ, oz, kz);
+        for (int co = 0; co < p.Cout; ++co) {
+            const float *g = p.gy + ((size_t)b * p.Cout + co) * So;
+            const float *wp = p.w + ((size_t)co * Cin + ci) * k3;
+            for (int a = 0; a < nh; ++a)
+                for (int c = 0; c < nw; ++c)
+                    for (int e = 0; e < nz; ++e)
+                        gu = __fmaf_rn(wp[(kh[a] * k + kw[c]) * k + kz[e]], g[((size_t)oh[a] * p.Wo + ow[c]) * p.Zo + oz[e]], gu);
+        }
+        gu *= sc;
+        const bool first = ci < p.C1;
+        const float *xs = first ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+        float *gxs = first ? (p.gx1 ? p.gx1 + ((size_t)b * p.C1 + ci) * S : nullptr) : (p.gx2 ? p.gx2 + ((size_t)b * p.C2 + (ci - p.C1)) * S : nullptr);
+        const int64_t off = v - (int64_t)b * S;
+        gx = gu;
+        if (p.pre_act) {
+            const float t = xs[off] + ld_scalar(p.pre_a, 0.0f);
+            gx = t > 0.0f ? gu : gu * __expf(t);
+        }
+        if (gxs) gxs[off] = gx;
+    }
+    if (p.gscal) {
+        const float sa = block_sum(p.pre_act ? gx : 0.0f, red);
+        const float sb = block_sum(gu, red);
+        if (threadIdx.x == 0) {
+            if (p.pre_act && p.pre_a) atomicAdd(p.gscal + 0, sa);
+            if (p.pre_b) atomicAdd(p.gscal + 1, sb);
+        }
+    }
+}
+
+// grid (voxel chunks, Cin, Cout): every thread accumulates the k^3 taps of one (co, ci) pair over its voxels
+__global__ void __launch_bounds__(128)
+conv3d_wgrad_kernel(BwdParams p) {
+    __shared__ float red[32];
+    const int Cin = p.C1 + p.C2, k = p.k, k3 = k * k * k;
+    const int ci = blockIdx.y, co = blockIdx.z;
+    const int64_t S = (int64_t)p.H * p.W * p.Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
+    const int64_t total = (int64_t)p.B * So;
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    float acc[64];
+#pragma unroll
+    for (int t = 0; t < 64; ++t) acc[t] = 0.0f;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(v / So);
+        int64_t r = v - (int64_t)b * So;
+        const int oh = (int)(r / ((int64_t)p.Wo * p.Zo));
+        r -= (int64_t)oh * p.Wo * p.Zo;
+        const int ow = (int)(r / p.Zo), oz = (int)(r - (int64_t)ow * p.Zo);
+        const float g = p.gy[((size_t)b * p.Cout + co) * So + (v - (int64_t)b * So)] * sc;
+        const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+#pragma unroll 1
+        for (int kh = 0; kh < k; ++kh) {
+            int ih = oh * p.stride - p.pad + kh;
+            if (p.circ) ih = wrap(ih, p.H); else if (ih < 0 || ih >= p.H) continue;
+#pragma unroll 1
+            for (int kw = 0; kw < k; ++kw) {
+                int iw = ow * p.stride - p.pad + kw;
+                if (p.circ) iw = wrap(iw, p.W); else if (iw < 0 || iw >= p.W) continue;
+                for (int kz = 0; kz < 4; ++kz) {
+                    if (kz >= k) break;
+                    int iz = oz * p.stride - p.pad + kz;
+                    if (p.circ) iz = wrap(iz, p.Z); else if (iz < 0 || iz >= p.Z) continue;
+                    float u = src[((size_t)ih * p.W + iw) * p.Z + iz];
+                    u = p.pre_act ? elu1(u + pa) + pb : u + pb;
+                    const int t = (kh * k + kw) * k + kz;
+                    // static indexing keeps acc in registers
+#pragma unroll
+                    for (int tt = 0; tt < 64; ++tt)
+                        if (tt == t) acc[tt] = __fmaf_rn(g, u, acc[tt]);
+                }
+            }
+        }
+    }
+    float *gw = p.gw + ((size_t)co * Cin + ci) * k3;
+#pragma unroll
+    for (int t = 0; t < 64; ++t) {
+        if (t < k3) {
+            const float s = block_sum(acc[t], red);
+            if (threadIdx.x == 0) atomicAdd(gw + t, s);
+        }
+    }
+}
+
+// grid (chunks, Cout, B): d bias[co], d post_b, d post_scale
+__global__ void __launch_bounds__(256)
+conv3d_outgrads_kernel(const float *__restrict__ gy, const float *__restrict__ raw, int Cout, int64_t So, float *gbias, float *gscal,
+                       int want_scale, int want_pb) {
+    __shared__ float red[32];
+    const int co = blockIdx.y, b = blockIdx.z;
+    const size_t base = ((size_t)b * Cout + co) * So;
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < So; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = gy[base + i];
+        s1 += g;
+        if (raw) s2 = __fmaf_rn(g, raw[base + i], s2);
+    }
+    const float t1 = block_sum(s1, red);
+    const float t2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        if (gbias) atomicAdd(gbias + co, t1);
+        if (gscal && want_pb) atomicAdd(gscal + 3, t1);
+        if (gscal && want_scale && raw) atomicAdd(gscal + 2, t2);
+    }
+}
+
+__device__ __forceinline__ void up_taps_b(int o, int n, int &i0, int &i1, float &l1) {
+    float src = 0.5f * (float)o - 0.25f;
+    if (src < 0.0f) src = 0.0f;
+    i0 = (int)src;
+    l1 = src - (float)i0;
+    i1 = i0 + (i0 < n - 1 ? 1 : 0);
+}
+
+// transposed trilinear x2 (align_corners=False): thread = one low-res element, gathers the <= 4^3 hi-res outputs that read it.
+// The optional input transform u = pre_act ? ELU(x+a)+b : x+b of vq3d_upsample2x is differentiated as in dgrad.
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float *__restrict__ gy, const float *__restrict__ x, int64_t BC, int H, int W, int Z, int pre_act,
+                      const float *pre_a, const float *pre_b, float *__restrict__ gx, float *gscal) {
+    __shared__ float red[32];
+    const int Ho = 2 * H, Wo = 2 * W, Zo = 2 * Z;
+    const int64_t S = (int64_t)H * W * Z, So = 8 * S;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float gu = 0.0f, g = 0.0f;
+    if (i < BC * S) {
+        const int64_t bc = i / S;
+        int64_t r = i - bc * S;
+        const int ih = (int)(r / ((int64_t)W * Z));
+        r -= (int64_t)ih * W * Z;
+        const int iw = (int)(r / Z), iz = (int)(r - (int64_t)iw * Z);
+        const float *gp = gy + bc * So;
+        for (int oh = max(2 * ih - 2, 0); oh <= min(2 * ih + 2, Ho - 1); ++oh) {
+            int h0, h1; float lh;
+            up_taps_b(oh, H, h0, h1, lh);
+            const float ch = (h0 == ih ? 1.0f - lh : 0.0f) + (h1 == ih ? lh : 0.0f);
+            if (ch == 0.0f) continue;
+            for (int ow = max(2 * iw - 2, 0); ow <= min(2 * iw + 2, Wo - 1); ++ow) {
+                int w0, w1; float lw;
+                up_taps_b(ow, W, w0, w1, lw);
+                const float cw = (w0 == iw ? 1.0f - lw : 0.0f) + (w1 == iw ? lw : 0.0f);
+                if (cw == 0.0f) continue;
+                for (int oz = max(2 * iz - 2, 0); oz <= min(2 * iz + 2, Zo - 1); ++oz) {
+                    int z0, z1; float lz;
+                    up_taps_b(oz, Z, z0, z1, lz);
+                    const float cz = (z0 == iz ? 1.0f - lz : 0.0f) + (z1 == iz ? lz : 0.0f);
+                    if (cz == 0.0f) continue;
+                    gu = __fmaf_rn(ch * cw * cz, gp[((size_t)oh * Wo + ow) * Zo + oz], gu);
+                }
+            }
+        }
+        g = gu;
+        if (pre_act) {
+            const float t = x[i] + ld_scalar(pre_a, 0.0f);
+            g = t > 0.0f ? gu : gu * __expf(t);
+        }
+        gx[i] = g;
+    }
+    if (gscal) {
+        const float sa = block_sum(pre_act ? g : 0.0f, red);
+        const float sb = block_sum(gu, red);
+        if (threadIdx.x == 0) {
+            if (pre_act && pre_a) atomicAdd(gscal + 0, sa);
+            if (pre_b) atomicAdd(gscal + 1, sb);
+        }
+    }
+}
+
+// d/d decoded of mean smooth_l1(mask(ELU(decoded)), x): model.py:120-152
+__global__ void __launch_bounds__(256)
+huber_elu_mask_bwd_kernel(const float *__restrict__ dec, const float *__restrict__ x, const int *__restrict__ num_valid,
+                          const uint8_t *__restrict__ mask_hw, int64_t B, int HW, int Z, const double *__restrict__ count,
+                          const float *__restrict__ gloss, float *__restrict__ gdec) {
+    const int64_t total = B * (int64_t)HW * Z;
+    const float scale = __ldg(gloss) / (float)(*count);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i % Z);
+        const int64_t r = i / Z;
+        const int hw = (int)(r % HW), b = (int)(r / HW);
+        float g = 0.0f;
+        if ((!mask_hw || mask_hw[hw]) && !(num_valid && z >= num_valid[b])) {
+            const float d = dec[i];
+            const float loc = elu1(d);
+            const float diff = loc - x[i];
+            const float dl = fabsf(diff) < 1.0f ? diff : (diff > 0.0f ? 1.0f : -1.0f);
+            g = dl * (d > 0.0f ? 1.0f : __expf(d)) * scale;
+        }
+        gdec[i] = g;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_amsgrad_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, float *__restrict__ vmax,
+                    int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        const float vm = fmaxf(vmax[i], vi);
+        m[i] = mi; v[i] = vi; vmax[i] = vm;
+        p[i] -= (lr / bc1) * mi / (sqrtf(vm) / sqrtf(bc2) + eps);       // torch.optim.Adam(amsgrad=True), model.py:91-93
+    }
+}
+
+}  // namespace vq3d
+
+using namespace vq3d;
+
+extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd *g, void *stream) {
+    if (!d || !g || !g->gy) return fail(VQ3D_ERR_INVALID, "conv3d_backward: null descriptor / gy");
+    if (!d->x1 || !d->w) return fail(VQ3D_ERR_INVALID, "conv3d_backward: null x1/w");
+    if (d->post_act) return fail(VQ3D_ERR_UNSUPPORTED, "conv3d_backward: post_act (FixupResBlock) has no backward in this build");
+    if (d->k < 1 || d->k > 4 || d->stride < 1 || d->stride > 2 || d->pad < 0 || d->pad >= d->k) return fail(VQ3D_ERR_INVALID, "conv3d_backward: unsupported geometry");
+    BwdParams p;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z; p.C1 = d->C1; p.C2 = d->C2; p.Cout = d->Cout;
+    p.k = d->k; p.stride = d->stride; p.pad = d->pad; p.circ = d->pad_circular; p.pre_act = d->pre_act;
+    p.Ho = (d->H + 2 * d->pad - d->k) / d->stride + 1;
+    p.Wo = (d->W + 2 * d->pad - d->k) / d->stride + 1;
+    p.Zo = (d->Z + 2 * d->pad - d->k) / d->stride + 1;
+    p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.pre_a = d->pre_a; p.pre_b = d->pre_b; p.post_scale = d->post_scale;
+    p.gy = g->gy; p.raw = g->raw; p.gx1 = g->gx1; p.gx2 = g->gx2; p.gw = g->gw; p.gbias = g->gbias; p.gscal = g->gscalars;
+    const int Cin = d->C1 + d->C2;
+    const int64_t S = (int64_t)d->H * d->W * d->Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
+    int rc;
+    if (p.gx1 || p.gx2 || (p.gscal && (d->pre_a || d->pre_b))) {
+        rc = launch("conv3d_dgrad", conv3d_dgrad_kernel, dim3((unsigned)ceil_div((int64_t)d->B * S, 128), (unsigned)Cin), dim3(128), 0, stream, p);
+        if (rc) return rc;
+    }
+    if (p.gw) {
+        int64_t chunks = ceil_div((int64_t)d->B * So, 128 * 8);
+        const int64_t cap = (int64_t)kNumSMs * 8 / ((int64_t)Cin * d->Cout) + 1;
+        if (chunks > cap) chunks = cap;
+        rc = launch("conv3d_wgrad", conv3d_wgrad_kernel, dim3((unsigned)chunks, (unsigned)Cin, (unsigned)d->Cout), dim3(128), 0, stream, p);
+        if (rc) return rc;
+    }
+    const int want_scale = d->post_scale != nullptr, want_pb = d->post_b != nullptr;
+    if (p.gbias || (p.gscal && (want_scale || want_pb))) {
+        if (want_scale && p.gscal && !g->raw) return fail(VQ3D_ERR_INVALID, "conv3d_backward: d post_scale needs the raw convolution output");
+        int64_t chunks = ceil_div(So, 256 * 8);
+        if (chunks > 256) chunks = 256;
+        rc = launch("conv3d_outgrads", conv3d_outgrads_kernel, dim3((unsigned)chunks, (unsigned)d->Cout, (unsigned)d->B), dim3(256), 0, stream,
+                    g->gy, g->raw, d->Cout, So, g->gbias, g->gscalars, want_scale, want_pb);
+        if (rc) return rc;
+    }
+    return VQ3D_OK;
+}
+
+extern "C" int vq3d_upsample2x_backward(const float *gy, const float *x, int64_t B, int C, int H, int W, int Z, int pre_act,
+                                        const float *pre_a, const float *pre_b, float *gx, float *gscalars, void *stream) {
+    if (!gy || !gx || B < 1 || C < 1 || H < 1 || W < 1 || Z < 1) return fail(VQ3D_ERR_INVALID, "upsample2x_backward: bad arguments");
+    if (pre_act && !x) return fail(VQ3D_ERR_INVALID, "upsample2x_backward: pre_act needs x");
+    const int64_t total = B * C * (int64_t)H * W * Z;
+    return launch("upsample2x_bwd", upsample2x_bwd_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, gy, x, B * C, H, W, Z,
+                  pre_act, pre_a, pre_b, gx, gscalars);
+}
+
+extern "C" int vq3d_huber_elu_mask_backward(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                                            int64_t B, int H, int W, int Z, const double *count, const float *grad_loss, float *grad_decoded,
+                                            void *stream) {
+    if (!decoded || !x || !count || !grad_loss || !grad_decoded || B < 1 || H < 1 || W < 1 || Z < 1) return fail(VQ3D_ERR_INVALID, "huber backward: bad arguments");
+    const int64_t total = B * (int64_t)H * W * Z;
+    int64_t blocks = ceil_div(total, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    return launch("huber_elu_mask_bwd", huber_elu_mask_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x, (const int *)num_valid,
+                  mask_hw, B, H * W, Z, count, grad_loss, grad_decoded);
+}
+
+extern "C" int vq3d_adam_amsgrad_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t n,
+                                      double lr, double beta1, double beta2, double eps, int64_t step, void *stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || n < 0 || step < 1) return fail(VQ3D_ERR_INVALID, "adam: bad arguments");
+    if (n == 0) return VQ3D_OK;
+    int64_t blocks = ceil_div(n, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    return launch("adam_amsgrad", adam_amsgrad_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq,
+                  n, (float)lr, (float)beta1, (float)beta2, (float)eps, (float)bc1, (float)bc2);
+}

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -31,6 +31,11 @@ class PreactDesc(C.Structure):
                                    "scale", "b1c", "b1d", "y", "out_w", "out_b", "out_y", "pre_w", "pre_b")]
 
 
+class ConvBwd(C.Structure):
+    """struct vq3d_conv_bwd"""
+    _fields_ = [(n, _fp) for n in ("gy", "raw", "gx1", "gx2", "gw", "gbias", "gscalars")]
+
+
 # name -> (restype, argtypes); the single source of truth for tests/test_cabi_symbols.py
 SIGNATURES = {
     "vq3d_abi_version": (C.c_int, []),
@@ -48,6 +53,10 @@ SIGNATURES = {
     "vq3d_conv3d": (C.c_int, [C.POINTER(ConvDesc), _fp]),
     "vq3d_conv3d_tc_workspace": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "vq3d_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), _fp, C.c_size_t, _fp]),
+    "vq3d_conv3d_backward": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvBwd), _fp]),
+    "vq3d_upsample2x_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp]),
+    "vq3d_huber_elu_mask_backward": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
+    "vq3d_adam_amsgrad_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, _fp]),
     "vq3d_upsample2x": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_preact_block": (C.c_int, [C.POINTER(PreactDesc), _fp]),
     "vq3d_preact_stack": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),

@@ -164,6 +164,52 @@ class Ops:
                pad: int = 0, circular: bool = False, pre_act: bool = False, pre_a: Optional[Tensor] = None,
                pre_b: Optional[Tensor] = None, post_scale: Optional[Tensor] = None, post_b: Optional[Tensor] = None,
                residual: Optional[Tensor] = None, post_act: bool = False) -> Tensor:
+        """The fused convolution of include/vqvae3d_b200.h (vq3d_conv3d / vq3d_conv3d_tc).  Differentiable: when
+        autograd is recording and an input requires grad, the backward is vq3d_conv3d_backward."""
+        tensors = (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual)
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+            if post_act:
+                raise NotImplementedError("3d-vq-vae-2_b200: the trailing ELU of FixupResBlock has no backward in this build")
+            return _ConvFn.apply(self, dict(stride=stride, pad=pad, circular=circular, pre_act=pre_act), *tensors)
+        return self._conv3d_fwd(x1, w, x2=x2, bias=bias, stride=stride, pad=pad, circular=circular, pre_act=pre_act, pre_a=pre_a,
+                                pre_b=pre_b, post_scale=post_scale, post_b=post_b, residual=residual, post_act=post_act)
+
+    def conv_desc(self, x1, x2, w, stride, pad, circular, pre_act, pre_a, pre_b, post_scale=None, post_b=None, bias=None,
+                  residual=None, y=None, post_act=False):
+        B, C1, H, W, Z = x1.shape
+        return _cabi.ConvDesc(B=B, H=H, W=W, Z=Z, C1=C1, C2=0 if x2 is None else x2.shape[1], Cout=w.shape[0], k=w.shape[2],
+                              stride=stride, pad=pad, pad_circular=int(circular), pre_act=int(pre_act), post_act=int(post_act),
+                              x1=self._p(x1), x2=self._p(x2), w=self._p(w), bias=self._p(bias), pre_a=self._p(pre_a), pre_b=self._p(pre_b),
+                              post_scale=self._p(post_scale), post_b=self._p(post_b), residual=self._p(residual), y=self._p(y))
+
+    def conv3d_backward(self, cfg, x1, x2, w, pre_a, pre_b, post_scale, post_b, gy, need):
+        """need: dict of booleans (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b).  Returns the gradients (or None)."""
+        D = lambda t: None if t is None else self._t(t.detach())
+        x1, x2, w, pre_a, pre_b, post_scale, post_b, gy = D(x1), D(x2), D(w), D(pre_a), D(pre_b), D(post_scale), D(post_b), D(gy)
+        raw = None
+        if need["post_scale"]:        # d scale = sum(gy * conv output before the post transform): recompute it
+            raw = self._conv3d_fwd(x1, w, x2=x2, stride=cfg["stride"], pad=cfg["pad"], circular=cfg["circular"], pre_act=cfg["pre_act"],
+                                   pre_a=pre_a, pre_b=pre_b, force_fp32=True)
+        dev = x1.device
+        gx1 = torch.empty_like(x1) if need["x1"] else None
+        gx2 = torch.empty_like(x2) if (x2 is not None and need["x2"]) else None
+        gw = torch.zeros_like(w) if need["w"] else None
+        gbias = torch.zeros(w.shape[0], dtype=torch.float32, device=dev) if need["bias"] else None
+        want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
+        gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
+        d = self.conv_desc(x1, x2, w, cfg["stride"], cfg["pad"], cfg["circular"], cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
+        g = _cabi.ConvBwd(gy=self._p(gy), raw=self._p(raw), gx1=self._p(gx1), gx2=self._p(gx2), gw=self._p(gw), gbias=self._p(gbias),
+                          gscalars=self._p(gscal))
+        self._call("conv3d_backward", self.lib.vq3d_conv3d_backward, (C.byref(d), C.byref(g), self.stream()), kernels=3,
+                   tag=f"{w.shape[1]}->{w.shape[0]} k{w.shape[2]}s{cfg['stride']} @{x1.shape[2]}x{x1.shape[3]}x{x1.shape[4]}")
+        return gx1, gx2, gw, gbias, gscal
+
+    def _conv3d_fwd(self, x1: Tensor, w: Tensor, *, x2: Optional[Tensor] = None, bias: Optional[Tensor] = None, stride: int = 1,
+                    pad: int = 0, circular: bool = False, pre_act: bool = False, pre_a: Optional[Tensor] = None,
+                    pre_b: Optional[Tensor] = None, post_scale: Optional[Tensor] = None, post_b: Optional[Tensor] = None,
+                    residual: Optional[Tensor] = None, post_act: bool = False, force_fp32: bool = False) -> Tensor:
+        detach = lambda t: None if t is None else t.detach()
+        x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual = map(detach, (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual))
         x1, x2, w = self._t(x1), self._t(x2), self._t(w)
         B, C1, H, W, Z = x1.shape
         C2 = 0 if x2 is None else x2.shape[1]
@@ -186,7 +232,7 @@ class Ops:
         so = y[0, 0].numel()
         meta = dict(nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
                     flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
-        if self.precision == "bf16" and Cout >= 8 and Cin * k ** 3 >= 32:
+        if self.precision == "bf16" and not force_fp32 and Cout >= 8 and Cin * k ** 3 >= 32:
             need = self.lib.vq3d_conv3d_tc_workspace(C.byref(d))       # > 0: few voxels, long K -> split-K through a workspace
             ws = self._workspace(need, x1.device) if need else None
             if self._call("conv3d_tc", self.lib.vq3d_conv3d_tc, (C.byref(d), self._p(ws), need, self.stream()),
@@ -197,6 +243,25 @@ class Ops:
 
     def upsample2x(self, x: Tensor, *, pre_act: bool = False, pre_a: Optional[Tensor] = None,
                    pre_b: Optional[Tensor] = None) -> Tensor:
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, pre_a, pre_b)):
+            return _UpsampleFn.apply(self, pre_act, x, pre_a, pre_b)
+        return self._upsample2x_fwd(x, pre_act=pre_act, pre_a=pre_a, pre_b=pre_b)
+
+    def upsample2x_backward(self, gy, x, pre_act, pre_a, pre_b, want_scal):
+        gy, x = self._t(gy.detach()), self._t(x.detach())
+        B, Cc, H, W, Z = x.shape
+        gx = torch.empty_like(x)
+        gscal = torch.zeros(4, dtype=torch.float32, device=x.device) if want_scal else None
+        D = lambda t: None if t is None else self._t(t.detach())
+        self._call("upsample2x_backward", self.lib.vq3d_upsample2x_backward,
+                   (self._p(gy), self._p(x), B, Cc, H, W, Z, int(pre_act), self._p(D(pre_a)), self._p(D(pre_b)), self._p(gx), self._p(gscal),
+                    self.stream()), tag=f"{Cc}ch @{H}x{W}x{Z}")
+        return gx, gscal
+
+    def _upsample2x_fwd(self, x: Tensor, *, pre_act: bool = False, pre_a: Optional[Tensor] = None,
+                        pre_b: Optional[Tensor] = None) -> Tensor:
+        detach = lambda t: None if t is None else t.detach()
+        x, pre_a, pre_b = detach(x), detach(pre_a), detach(pre_b)
         x = self._t(x)
         B, Cc, H, W, Z = x.shape
         y = torch.empty((B, Cc, 2 * H, 2 * W, 2 * Z), dtype=torch.float32, device=x.device)
@@ -306,14 +371,92 @@ class Ops:
                    (self._p(x), flat(v), flat(gamma), flat(beta), self._p(std), Cc, S, self._p(y), self.stream()), nbytes=8 * x.numel())
         return y
 
+    def huber_loss(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]) -> Tensor:
+        """mean smooth_l1(mask(ELU(decoded)), x) as a 0-d fp32 tensor (model.py:120-152); differentiable wrt decoded."""
+        if torch.is_grad_enabled() and decoded.requires_grad:
+            return _HuberFn.apply(self, decoded, x, num_valid, mask_hw)
+        acc = self.huber_elu_mask(decoded, x, num_valid, mask_hw)
+        return (acc[0] / acc[1]).float()
+
+    def huber_backward(self, decoded, x, num_valid, mask_hw, count, gloss) -> Tensor:
+        decoded, x = self._t(decoded.detach()), self._t(x.detach())
+        B, _, H, W, Z = x.shape
+        gdec = torch.empty_like(decoded)
+        self._call("huber_elu_mask_backward", self.lib.vq3d_huber_elu_mask_backward,
+                   (self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)), self._p(self._t(mask_hw, torch.uint8)), B, H, W, Z,
+                    self._p(count), self._p(self._t(gloss.detach().reshape(1).float())), self._p(gdec), self.stream()), nbytes=12 * x.numel())
+        return gdec
+
+    def adam_amsgrad_step(self, p: Tensor, g: Tensor, m: Tensor, v: Tensor, vmax: Tensor, lr, b1, b2, eps, step) -> None:
+        for t in (p, g, m, v, vmax):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        self._call("adam_amsgrad_step", self.lib.vq3d_adam_amsgrad_step,
+                   (self._p(p), self._p(g), self._p(m), self._p(v), self._p(vmax), p.numel(), float(lr), float(b1), float(b2), float(eps),
+                    int(step), self.stream()), nbytes=28 * p.numel())
+
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
-        decoded, x = self._t(decoded), self._t(x)
+        decoded, x = self._t(decoded.detach()), self._t(x.detach())
         B, _, H, W, Z = x.shape
         acc = torch.zeros(2, dtype=torch.float64, device=x.device)
         self._call("huber_elu_mask", self.lib.vq3d_huber_elu_mask,
                    (self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)), self._p(self._t(mask_hw, torch.uint8)),
                     B, H, W, Z, acc[0:1].data_ptr(), acc[1:2].data_ptr(), self.stream()), nbytes=8 * x.numel())
         return acc
+
+
+class _ConvFn(torch.autograd.Function):
+    """Autograd edge of Ops.conv3d; residual's gradient is gy itself."""
+
+    @staticmethod
+    def forward(ctx, ops, cfg, x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual):
+        y = ops._conv3d_fwd(x1, w, x2=x2, bias=bias, pre_a=pre_a, pre_b=pre_b, post_scale=post_scale, post_b=post_b, residual=residual, **cfg)
+        ctx.ops, ctx.cfg = ops, cfg
+        ctx.save_for_backward(x1, x2, w, pre_a, pre_b, post_scale, post_b)
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x1, x2, w, pre_a, pre_b, post_scale, post_b = ctx.saved_tensors
+        n = ctx.needs_input_grad      # (ops, cfg, x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual)
+        need = dict(x1=n[2], x2=n[3] and x2 is not None, w=n[4], bias=n[5] and ctx.has_bias, pre_a=n[6] and pre_a is not None,
+                    pre_b=n[7] and pre_b is not None, post_scale=n[8] and post_scale is not None, post_b=n[9] and post_b is not None)
+        gy = gy.contiguous()
+        gx1, gx2, gw, gbias, gs = ctx.ops.conv3d_backward(ctx.cfg, x1, x2, w, pre_a, pre_b, post_scale, post_b, gy, need)
+        pick = lambda flag, i: gs[i:i + 1].clone() if flag else None
+        return (None, None, gx1, gx2, gw, gbias, pick(need["pre_a"], 0), pick(need["pre_b"], 1), pick(need["post_scale"], 2),
+                pick(need["post_b"], 3), gy if (ctx.has_res and n[10]) else None)
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ops, pre_act, x, pre_a, pre_b):
+        ctx.ops, ctx.pre_act = ops, pre_act
+        ctx.save_for_backward(x, pre_a, pre_b)
+        return ops._upsample2x_fwd(x, pre_act=pre_act, pre_a=pre_a, pre_b=pre_b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, pre_a, pre_b = ctx.saved_tensors
+        n = ctx.needs_input_grad
+        want = (n[3] and pre_a is not None) or (n[4] and pre_b is not None)
+        gx, gs = ctx.ops.upsample2x_backward(gy.contiguous(), x, ctx.pre_act, pre_a, pre_b, want)
+        return (None, None, gx if n[2] else None, gs[0:1].clone() if (n[3] and pre_a is not None) else None,
+                gs[1:2].clone() if (n[4] and pre_b is not None) else None)
+
+
+class _HuberFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ops, decoded, x, num_valid, mask_hw):
+        acc = ops.huber_elu_mask(decoded, x, num_valid, mask_hw)
+        ctx.ops, ctx.nv, ctx.mask = ops, num_valid, mask_hw
+        ctx.save_for_backward(decoded, x, acc)
+        return (acc[0] / acc[1]).float()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        decoded, x, acc = ctx.saved_tensors
+        return None, ctx.ops.huber_backward(decoded, x, ctx.nv, ctx.mask, acc[1:2], gloss), None, None, None
 
 
 _DEFAULT: Optional[Ops] = None

@@ -30,10 +30,19 @@ def ops() -> "_ops.Ops":
 
 
 def _no_conv_backward(*params) -> None:
+    """Blocks without backward kernels (FixupResBlock's trailing ELU, EvoNorm) refuse to record a graph."""
     if torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params):
         raise NotImplementedError(
-            "3d-vq-vae-2_b200: convolution backward kernels are not part of this build; run the "
-            "encoder/decoder under torch.no_grad() (the quantizer's straight-through backward is available)")
+            "3d-vq-vae-2_b200: this block type has no backward kernels in this build (pre-activation blocks, 1x1 "
+            "convolutions, the quantizer and the Huber epilogue do); run it under torch.no_grad()")
+
+
+def _recording(x, *params) -> bool:
+    """True when autograd is recording and something upstream wants a gradient: the fused inference kernels
+    (one launch per block / stack) are bypassed and the block is composed from the differentiable generic ops."""
+    if not torch.is_grad_enabled():
+        return False
+    return (x is not None and x.requires_grad) or any(p is not None and p.requires_grad for p in params)
 
 
 class Conv3d(nn.Conv3d):
@@ -42,7 +51,6 @@ class Conv3d(nn.Conv3d):
     parse_input / proj / out (layers.py:377,490,508,535)."""
 
     def forward(self, input: torch.Tensor, input2: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _no_conv_backward(self.weight, self.bias)
         return ops().conv3d(input, self.weight, x2=input2, bias=self.bias, stride=self.stride[0],
                             pad=self.padding[0] if not isinstance(self.padding, str) else 0,
                             circular=self.padding_mode == "circular")
@@ -97,7 +105,8 @@ class PreActFixupResBlock(nn.Module):
         return [p for p in self.parameters(recurse=True)]
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        _no_conv_backward(*self._params())
+        if _recording(input, *self._params()):
+            return self.forward_composed(input)          # training: differentiable generic ops
         o = ops()
         # wide down blocks: the fused SIMT kernel keeps all branch channels of the (2t+2)^3 input window in
         # shared memory, which leaves it a sliver of a tile at 16 channels; the composed tensor-core path wins
@@ -246,13 +255,17 @@ class BlockSequence(nn.Sequential):
         applied before the first block (the encoder's parse_input, layers.py:578).  Each is fused into the
         neighbouring block's kernel where one covers the shape, otherwise run on its own."""
         mods = list(self)
+        if _recording(x, *self.parameters(), *(pre.parameters() if pre is not None else ()), *(tail.parameters() if tail is not None else ())):
+            x = pre(x) if pre is not None else x
+            for m in mods:
+                x = m(x)
+            return tail(x) if tail is not None else x
         i = 0
         done_tail = tail is None
         if pre is not None:
             y = None
             m0 = mods[0] if mods else None
             if isinstance(m0, PreActFixupResBlock) and m0.mode == "down":
-                _no_conv_backward(*m0.parameters(), *pre.parameters())
                 y = ops().preact_block(x, m0, _MODE_ID[m0.mode], pre=pre)
             if y is not None:
                 x, i = y, 1
@@ -264,7 +277,6 @@ class BlockSequence(nn.Sequential):
             if _stackable(m):
                 while j + 1 < len(mods) and _stackable(mods[j + 1]) and _same_shape(m, mods[j + 1]):
                     j += 1
-                _no_conv_backward(*chain.from_iterable(b.parameters() for b in mods[i:j + 1]))
                 if tail is not None and j == len(mods) - 1:
                     y = ops().preact_stack(x, mods[i:j + 1], tail=tail)
                     if y is not None:

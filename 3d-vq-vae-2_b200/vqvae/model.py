@@ -121,7 +121,11 @@ class VQVAE(_Base):
         return self.decoder(quantizations)
 
     def configure_optimizers(self):
-        return torch.optim.Adam(self.parameters(), lr=self.lr, amsgrad=True)    # model.py:91-93
+        """model.py:91-93: Adam(lr, amsgrad=True).  CUDA parameters get the library's fused step kernel."""
+        if all(p.is_cuda for p in self.parameters()):
+            from .optim import FusedAdamAMSGrad
+            return FusedAdamAMSGrad(self.parameters(), lr=self.lr)
+        return torch.optim.Adam(self.parameters(), lr=self.lr, amsgrad=True)
 
     # ---- loss epilogue, model.py:115-160 ----------------------------------------------
     def huber(self, batch, batch_idx=0) -> Tuple[torch.Tensor, dict]:
@@ -135,8 +139,7 @@ class VQVAE(_Base):
             if self._cyl_mask is None or self._cyl_mask.numel() != x.shape[2] * x.shape[3]:
                 self._cyl_mask = center_cylinder_mask(x.shape[2], x.shape[3]).to(torch.uint8).reshape(-1).to(x.device)
             mask = self._cyl_mask
-        acc = _ops.default().huber_elu_mask(decoded, x, nv, mask)
-        recon = (acc[0] / acc[1]).float()
+        recon = _ops.default().huber_loss(decoded, x, nv, mask)
         commit = sum(commitment)
         log = {"recon_loss_mean": recon, **{f"commitment_loss_{i}": c for i, c in enumerate(commitment)}}
         return recon + commit, log

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 7
+#define VQ3D_ABI_VERSION 8
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -146,6 +146,40 @@ int vq3d_conv3d(const vq3d_conv_desc *desc, void *stream);
  */
 size_t vq3d_conv3d_tc_workspace(const vq3d_conv_desc *desc);
 int vq3d_conv3d_tc(const vq3d_conv_desc *desc, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * Backward of vq3d_conv3d (what autograd derives for the reference's Conv3d / F.pad / ELU / Fixup-scalar chain,
+ * layers.py:176-195), any shape, fp32.  desc is the FORWARD descriptor (residual / y / post_b values are not read):
+ *   gy [B, Cout, S_out]                 gradient wrt y (also the gradient wrt the residual)
+ *   gx1 / gx2                           out: gradient wrt x1 / x2 (NULL = not wanted)
+ *   gw [Cout, C1+C2, k, k, k], gbias [Cout]   ACCUMULATED into (caller zeroes) or NULL
+ *   gscalars float[4]                   ACCUMULATED: d pre_a, d pre_b, d post_scale, d post_b (entries whose forward
+ *                                       pointer is NULL are left alone); NULL = not wanted
+ *   raw [B, Cout, S_out]                the convolution output before the post transform (vq3d_conv3d with
+ *                                       post_scale = post_b = bias = residual = NULL); required iff d post_scale is wanted
+ * post_act (FixupResBlock) is not differentiated: VQ3D_ERR_UNSUPPORTED.
+ */
+typedef struct vq3d_conv_bwd {
+    const float *gy;
+    const float *raw;
+    float *gx1, *gx2;
+    float *gw, *gbias;
+    float *gscalars;
+} vq3d_conv_bwd;
+int vq3d_conv3d_backward(const vq3d_conv_desc *desc, const vq3d_conv_bwd *grads, void *stream);
+
+/* Backward of vq3d_upsample2x: gx [B, C, H, W, Z] from gy [B, C, 2H, 2W, 2Z]; gscalars as above (entries 0, 1). */
+int vq3d_upsample2x_backward(const float *gy, const float *x, int64_t B, int C, int H, int W, int Z, int pre_act,
+                             const float *pre_a, const float *pre_b, float *gx, float *gscalars, void *stream);
+
+/* Backward of vq3d_huber_elu_mask's mean: grad_decoded = grad_loss / count * d smooth_l1(mask(ELU(decoded)), x) / d decoded. */
+int vq3d_huber_elu_mask_backward(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                                 int64_t B, int H, int W, int Z, const double *count, const float *grad_loss,
+                                 float *grad_decoded, void *stream);
+
+/* One Adam(amsgrad=True) step on a flat fp32 tensor (model.py:91-93; torch.optim.Adam defaults otherwise). step >= 1. */
+int vq3d_adam_amsgrad_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t n,
+                           double lr, double beta1, double beta2, double eps, int64_t step, void *stream);
 
 /*
  * nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False) of ResizeConv3D

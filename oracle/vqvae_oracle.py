@@ -189,7 +189,7 @@ def quantizer_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, training: b
     if use_torch_cdist:
         idx = torch.argmin(torch.cdist(flat, embed, compute_mode="donot_use_mm_for_euclid_dist"), dim=1)
     else:
-        idx = torch.from_numpy(vq_assign_c(flat.numpy(), embed.numpy())[0])
+        idx = torch.from_numpy(vq_assign_c(flat.detach().numpy(), embed.detach().numpy())[0])
     quantized = embed[idx].reshape(shape)                 # layers.py:703 (codebook BEFORE the EMA update)
 
     if training:                                          # _update_ema, layers.py:636-663
