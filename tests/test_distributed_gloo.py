@@ -99,6 +99,33 @@ def test_quantizer_data_parallel_two_ranks_gloo(first_pass):
     assert np.allclose(r0["embed"], ea / sm[:, None], rtol=1e-4, atol=1e-5)
 
 
+def _grad_worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "3d-vq-vae-2_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vqvae.parallel import allreduce_gradients
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(1)), torch.nn.Parameter(torch.zeros(5))]
+        for i, p in enumerate(params[:2]):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        allreduce_gradients(params)          # params[2] has no grad: skipped consistently on every rank
+        out[rank] = [None if p.grad is None else p.grad.numpy().copy() for p in params]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_grad_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        assert np.allclose(out[r][0], 1.5) and np.allclose(out[r][1], 3.0) and out[r][2] is None   # mean of (1, 2) and (2, 4)
+
+
 def test_bench_shards_volumes_across_ranks():
     sys.path.insert(0, ROOT)
     import bench
