@@ -364,6 +364,23 @@ def run_b200(args):
             line["quantizer"] = quantizer_point(dev, pk)
         except Exception as ex:  # pragma: no cover
             line["quantizer"] = {"error": repr(ex)}
+        # BASELINE.json configs[3]: extract_embeddings = encode + quantize only (hierarchical code indices), same volume
+        try:
+            with torch.no_grad():
+                for _ in range(3):
+                    list(model.encode(x_dev))
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(steps):
+                    list(model.encode(x_dev))
+                a1.record()
+                torch.cuda.synchronize()
+            enc_ms = a0.elapsed_time(a1) / steps
+            line["extract"] = {"value": world * 1e3 / enc_ms, "unit": "volumes/s", "ms_per_step": enc_ms,
+                               "what": "VQVAE.encode (Encoder2 + 3 quantizers -> code indices), CUDA-graph replay, per-rank time of rank 0"}
+        except Exception as ex:  # pragma: no cover
+            line["extract"] = {"error": repr(ex)}
         traffic = ncu_traffic(f"{dom_key[0]} [{dom_key[1]}]")
         if traffic is not None:
             line["roofline"]["traffic"] = traffic["dram_bytes_per_launch"]
