@@ -451,6 +451,267 @@ static int launch_down_row(const vq3d_preact_desc *d, void *stream) {
                   SM::floats(tho, two, d->Z) * 4, stream, p);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 'up' blocks at the big levels (8 -> 4 -> 4 at 256^3 -> 512^3, 18 -> 9 -> 8 at 128^3 -> 256^3; layers.py:128-132,
+// 591-597): conv1 1x1 and the 1x1 skip are evaluated at LOW resolution (they commute with the trilinear x2
+// upsampling), the branch is upsampled into a haloed hi-res shared-memory tile (circular wrap of the k3 padding is
+// applied on the hi-res grid, the upsampling clamps at the volume edges -- as the reference), conv2 k3 runs from
+// that tile with 4 consecutive hi-res z per thread, the skip is upsampled on the fly in the epilogue.
+// Low-res rows are stored with one clamped element of padding on each side, which turns the depth interpolation of
+// hi z = 4q..4q+3 into fixed-weight blends of padded entries 2q..2q+3 with no edge cases.
+constexpr int kUpThreads = 256;
+
+struct UpParams {
+    int B, H, W, Z;                   // low-res input extent
+    int tho, two, ntho, ntwo;         // hi-res output-row tile (even)
+    const float *x, *w1, *w2, *w3, *ws;
+    const float *b1a, *b1b, *b2a, *b2b, *b3a, *b3b, *b4, *scale, *b1c, *b1d;
+    float *y;
+};
+
+template <int CIN, int CB, int COUT>
+struct UpSmem {
+    static constexpr int w1 = 0;                         // [CIN][CB]
+    static constexpr int w2 = w1 + CIN * CB;             // [CB ci][9][3 kz][CB co]
+    static constexpr int w3 = w2 + CB * 27 * CB;         // [CB][COUT]
+    static constexpr int ws = w3 + CB * COUT;            // [CIN][COUT]
+    static constexpr int tab = (ws + CIN * COUT + 3) & ~3;   // tap tables: 3 floats per hi tile row / column
+    __host__ __device__ static int zpl(int Z) { return (Z + 2 + 3) & ~3; }
+    static size_t floats(int tho, int two, int Z) {
+        const int LR = (tho / 2 + 2) * (two / 2 + 2), HR = (tho + 2) * (two + 2);
+        return tab + 3 * (size_t)(tho + 2 + two + 2) + (size_t)(CB + COUT) * LR * zpl(Z) + (size_t)CB * HR * (2 * Z + 8) + 4;
+    }
+};
+
+__device__ __forceinline__ void up_taps_row(int o, int n, int &i0, int &i1, float &l1) {
+    float src = 0.5f * (float)o - 0.25f;
+    if (src < 0.0f) src = 0.0f;
+    i0 = (int)src;
+    l1 = src - (float)i0;
+    i1 = i0 + (i0 < n - 1 ? 1 : 0);
+}
+
+// depth interpolation of 4 consecutive hi-res z from the padded low-res entries p[0..3] (= padded index 2q..2q+3)
+__device__ __forceinline__ void up_z4(const float *p, float *o) {
+    o[0] = 0.25f * p[0] + 0.75f * p[1];
+    o[1] = 0.75f * p[1] + 0.25f * p[2];
+    o[2] = 0.25f * p[1] + 0.75f * p[2];
+    o[3] = 0.75f * p[2] + 0.25f * p[3];
+}
+
+template <int CIN, int CB, int COUT>
+__global__ void __launch_bounds__(kUpThreads)
+preact_up_row_kernel(UpParams p) {
+    using SM = UpSmem<CIN, CB, COUT>;
+    VQ3D_DYN_SMEM(float, smem);
+    float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_ws = smem + SM::ws, *s_tab = smem + SM::tab;
+    const int tid = threadIdx.x;
+    const int Z = p.Z, Zo = 2 * Z, ZQ = Z >> 2, ZQo = Zo >> 2, ZPL = SM::zpl(Z), ZPH = Zo + 8;
+    const int Ho = 2 * p.H, Wo = 2 * p.W;
+    const int IH = p.tho + 2, IW = p.two + 2, HR = IH * IW;
+    const int LH = p.tho / 2 + 2, LW = p.two / 2 + 2, LR = LH * LW;
+    float *s_lo = s_tab + 3 * (IH + IW);                 // [CB][LR][ZPL]
+    s_lo = smem + (((s_lo - smem) + 3) & ~3);
+    float *s_sk = s_lo + (size_t)CB * LR * ZPL;          // [COUT][LR][ZPL]
+    float *s_hi = s_sk + (size_t)COUT * LR * ZPL;        // [CB][HR][ZPH]
+    const int64_t S = (int64_t)p.H * p.W * Z, So = 8 * S;
+
+    int bid = blockIdx.x;
+    const int twi = bid % p.ntwo; bid /= p.ntwo;
+    const int thi = bid % p.ntho; bid /= p.ntho;
+    const int b = bid, oh0 = thi * p.tho, ow0 = twi * p.two;
+    const int lh0 = oh0 / 2 - 1, lw0 = ow0 / 2 - 1;      // global low-res row / column of low tile index 0 (before wrapping)
+    const float *xb = p.x + (size_t)b * CIN * S;
+
+    for (int i = tid; i < CIN * CB; i += kUpThreads) s_w1[i] = p.w1[(i % CB) * CIN + i / CB];
+    for (int i = tid; i < CB * 27 * CB; i += kUpThreads) {
+        const int co = i % CB, t = (i / CB) % 27, ci = i / (CB * 27);
+        s_w2[i] = p.w2[((size_t)co * CB + ci) * 27 + t];
+    }
+    for (int i = tid; i < CB * COUT; i += kUpThreads) s_w3[i] = p.w3[(i % COUT) * CB + i / COUT];
+    for (int i = tid; i < CIN * COUT; i += kUpThreads) s_ws[i] = p.ws[(i % COUT) * CIN + i / COUT];
+    // tap tables of the hi tile rows / columns (hi index wraps: conv padding; low taps clamp: upsampling)
+    for (int i = tid; i < IH + IW; i += kUpThreads) {
+        const bool isw = i >= IH;
+        const int q = isw ? i - IH : i;
+        const int pos = rmod((isw ? ow0 : oh0) - 1 + q, isw ? Wo : Ho);
+        int i0, i1; float l1;
+        up_taps_row(pos, isw ? p.W : p.H, i0, i1, l1);
+        const int n = isw ? p.W : p.H, l0 = isw ? lw0 : lh0, ext = isw ? LW : LH;
+        s_tab[3 * i + 0] = (float)min(rmod(i0 - l0, n), ext - 1);
+        s_tab[3 * i + 1] = (float)min(rmod(i1 - l0, n), ext - 1);
+        s_tab[3 * i + 2] = l1;
+    }
+    const float b1a = ld_scalar(p.b1a, 0.f), b1b = ld_scalar(p.b1b, 0.f), b2a = ld_scalar(p.b2a, 0.f), b2b = ld_scalar(p.b2b, 0.f);
+    const float b1c = ld_scalar(p.b1c, 0.f);
+    __syncthreads();
+
+    // ---- stage A1: low-res t1 and skip rows (padded by one clamped element on each side) ---------------------
+    {
+        const int zq = tid % ZQ, slot = tid / ZQ, nslots = kUpThreads / ZQ;
+        for (int rs = slot; rs < LR; rs += nslots) {
+            const int lh = rs / LW, lw = rs - lh * LW;
+            const int gh = rmod(lh0 + lh, p.H), gw = rmod(lw0 + lw, p.W);
+            const float *px = xb + ((size_t)gh * p.W + gw) * Z + 4 * zq;
+            float t[CB][4], sk[COUT][4];
+#pragma unroll
+            for (int c = 0; c < CB; ++c) t[c][0] = t[c][1] = t[c][2] = t[c][3] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) sk[c][0] = sk[c][1] = sk[c][2] = sk[c][3] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
+                const float xv[4] = {v.x, v.y, v.z, v.w};
+                float a[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = elu1(xv[k] + b1a) + b1b;
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float w = s_w1[c * CB + cb];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) t[cb][k] = __fmaf_rn(w, a[k], t[cb][k]);
+                }
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float w = s_ws[c * COUT + co];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sk[co][k] = __fmaf_rn(w, xv[k] + b1c, sk[co][k]);
+                }
+            }
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                float *row = s_lo + ((size_t)cb * LR + rs) * ZPL + 1 + 4 * zq;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { t[cb][k] = elu1(t[cb][k] + b2a) + b2b; row[k] = t[cb][k]; }
+                if (zq == 0) row[-1] = t[cb][0];
+                if (zq == ZQ - 1) row[4] = t[cb][3];
+            }
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                float *row = s_sk + ((size_t)co * LR + rs) * ZPL + 1 + 4 * zq;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) row[k] = sk[co][k];
+                if (zq == 0) row[-1] = sk[co][0];
+                if (zq == ZQ - 1) row[4] = sk[co][3];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int q = tid % ZQo, slot = tid / ZQo, nslots = kUpThreads / ZQo;
+    // ---- stage A2: trilinear x2 into the haloed hi-res tile ------------------------------------------------
+    for (int hr = slot; hr < HR; hr += nslots) {
+        const int qh = hr / IW, qw = hr - qh * IW;
+        const int h0 = (int)s_tab[3 * qh], h1 = (int)s_tab[3 * qh + 1]; const float lh = s_tab[3 * qh + 2];
+        const int w0 = (int)s_tab[3 * (IH + qw)], w1 = (int)s_tab[3 * (IH + qw) + 1]; const float lw = s_tab[3 * (IH + qw) + 2];
+        const int r00 = h0 * LW + w0, r01 = h0 * LW + w1, r10 = h1 * LW + w0, r11 = h1 * LW + w1;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+            const float *base = s_lo + (size_t)cb * LR * ZPL + 2 * q;
+            float a00[4], a01[4], a10[4], a11[4];
+            up_z4(base + (size_t)r00 * ZPL, a00); up_z4(base + (size_t)r01 * ZPL, a01);
+            up_z4(base + (size_t)r10 * ZPL, a10); up_z4(base + (size_t)r11 * ZPL, a11);
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float c0 = a00[k] * (1.f - lw) + a01[k] * lw, c1 = a10[k] * (1.f - lw) + a11[k] * lw;
+                o[k] = c0 * (1.f - lh) + c1 * lh;
+            }
+            float *row = s_hi + ((size_t)cb * HR + hr) * ZPH;
+            *reinterpret_cast<float4 *>(row + 4 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            if (q == 0) row[Zo + 4] = o[0];              // circular padding on the hi-res grid
+            if (q == ZQo - 1) row[3] = o[3];
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B + C ---------------------------------------------------------------------------------------
+    const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
+    const float b1d = ld_scalar(p.b1d, 0.f);
+    for (int ro = slot; ro < p.tho * p.two; ro += nslots) {
+        const int lho = ro / p.two, lwo = ro - lho * p.two;
+        const int oh = oh0 + lho, ow = ow0 + lwo;
+        if (oh >= Ho || ow >= Wo) continue;
+        float acc[CB][4];
+#pragma unroll
+        for (int co = 0; co < CB; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = 0.0f;
+#pragma unroll
+        for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float *row = s_hi + ((size_t)ci * HR + (lho + kh) * IW + lwo + kw) * ZPH + 4 * q;
+                    const float4 m = *reinterpret_cast<const float4 *>(row + 4);
+                    const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                    const float *wt = s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB;
+#pragma unroll
+                    for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                        for (int co = 0; co < CB; ++co) {
+                            const float w = wt[kz * CB + co];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[co][k] = __fmaf_rn(w, r[k + kz], acc[co][k]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < CB; ++co)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
+        // skip: trilinear x2 of the low-res 1x1 skip at this hi row (tile rows lho+1, lwo+1 of the tap tables)
+        const int qh = lho + 1, qw = lwo + 1;
+        const int h0 = (int)s_tab[3 * qh], h1 = (int)s_tab[3 * qh + 1]; const float lh = s_tab[3 * qh + 2];
+        const int w0 = (int)s_tab[3 * (IH + qw)], w1 = (int)s_tab[3 * (IH + qw) + 1]; const float lw = s_tab[3 * (IH + qw) + 2];
+        const int r00 = h0 * LW + w0, r01 = h0 * LW + w1, r10 = h1 * LW + w0, r11 = h1 * LW + w1;
+        const size_t off = ((size_t)oh * Wo + ow) * Zo + 4 * q;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+            float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const float w = s_w3[cb * COUT + c];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+            }
+            const float *base = s_sk + (size_t)c * LR * ZPL + 2 * q;
+            float a00[4], a01[4], a10[4], a11[4];
+            up_z4(base + (size_t)r00 * ZPL, a00); up_z4(base + (size_t)r01 * ZPL, a01);
+            up_z4(base + (size_t)r10 * ZPL, a10); up_z4(base + (size_t)r11 * ZPL, a11);
+            float yv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float c0 = a00[k] * (1.f - lw) + a01[k] * lw, c1 = a10[k] * (1.f - lw) + a11[k] * lw;
+                yv[k] = __fmaf_rn(out[k], sc, b4) + (c0 * (1.f - lh) + c1 * lh + b1d);
+            }
+            *reinterpret_cast<float4 *>(p.y + ((size_t)b * COUT + c) * So + off) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        }
+    }
+}
+
+template <int CIN, int CB, int COUT>
+static int launch_up_row(const vq3d_preact_desc *d, void *stream) {
+    using SM = UpSmem<CIN, CB, COUT>;
+    UpParams p;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z;
+    const int Ho = 2 * d->H, Wo = 2 * d->W;
+    int tho = Ho < 4 ? Ho : 4, two = Wo < 4 ? Wo : 4;
+    const size_t cap = 113 * 1024;
+    while (SM::floats(tho, two, d->Z) * 4 > cap) {
+        if (tho >= two && tho > 2) tho = 2;
+        else if (two > 2) two = 2;
+        else return fail(VQ3D_ERR_UNSUPPORTED, "preact_block(up row): tile does not fit shared memory");
+    }
+    p.tho = tho; p.two = two; p.ntho = (int)ceil_div(Ho, tho); p.ntwo = (int)ceil_div(Wo, two);
+    p.x = d->x; p.w1 = d->w1; p.w2 = d->w2; p.w3 = d->w3; p.ws = d->wskip;
+    p.b1a = d->b1a; p.b1b = d->b1b; p.b2a = d->b2a; p.b2b = d->b2b; p.b3a = d->b3a; p.b3b = d->b3b; p.b4 = d->b4; p.scale = d->scale;
+    p.b1c = d->b1c; p.b1d = d->b1d; p.y = d->y;
+    const int64_t grid = (int64_t)d->B * p.ntho * p.ntwo;
+    if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(up row): grid too large");
+    return launch("preact_up_row", preact_up_row_kernel<CIN, CB, COUT>, dim3((unsigned)grid), dim3(kUpThreads), SM::floats(tho, two, d->Z) * 4, stream, p);
+}
+
 // Z must be a multiple of 4 with Z/4 a power of two <= 32 (a row of Z/4 float4 lanes divides the CTA)
 static bool row_shape_ok(const vq3d_preact_desc *d) {
     const int zq = d->Z / 4;
@@ -469,6 +730,22 @@ int preact_row_dispatch(const vq3d_preact_desc *d, void *stream, bool *handled) 
         if (shape && d->Cin == 4 && d->Cb == 4 && d->Cout == 8 && zqo * 4 <= kDownThreads) fn = d->pre_w ? launch_down_row<4, 4, 8, true> : launch_down_row<4, 4, 8, false>;
         else if (shape && !d->pre_w && d->Cin == 8 && d->Cb == 8 && d->Cout == 16 && zqo * 8 <= kDownThreads) fn = launch_down_row<8, 8, 16, false>;
         if (fn) { *handled = true; return fn(d, stream); }
+        return VQ3D_OK;
+    }
+    if (d->mode == 2 && d->wskip && !d->out_w && !d->pre_w) {
+        // up: Z/4 low-res lanes and 2Z/4 hi-res lanes per row must tile the 256-thread CTA; low-res extents >= 2
+        const int zq = d->Z / 4, zqo = d->Z / 2;
+        const bool shape = d->Z % 4 == 0 && zq >= 1 && (zq & (zq - 1)) == 0 && zqo <= 64 && zqo <= kUpThreads && d->H >= 2 && d->W >= 2 &&
+                           (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0;
+        int (*fn)(const vq3d_preact_desc *, void *) = nullptr;
+        if (shape && d->Cin == 8 && d->Cb == 4 && d->Cout == 4) fn = launch_up_row<8, 4, 4>;
+        else if (shape && d->Cin == 4 && d->Cb == 2 && d->Cout == 2) fn = launch_up_row<4, 2, 2>;
+        // (wider branches -- 16 -> 8 -> 8, 18 -> 9 -> 8 -- measured slower here than preact_fused_kernel: the fully unrolled
+        //  conv2 needs > 200 registers; they stay on the generic fused kernel)
+        if (fn) {
+            const int rc = fn(d, stream);
+            if (rc != VQ3D_ERR_UNSUPPORTED) { *handled = true; return rc; }
+        }
         return VQ3D_OK;
     }
     if (d->mode != 0 || d->wskip || d->Cin != d->Cout || !row_shape_ok(d)) return VQ3D_OK;

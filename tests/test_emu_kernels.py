@@ -228,3 +228,25 @@ def test_emu_down_row_kernel(cin, cout, shape, parse):
         assert o.launches - n0 == 1, "expected one fused launch"
         assert y.shape == ref.shape
         assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())
+
+
+@pytest.mark.parametrize("cin,cout,shape", [
+    (8, 4, (1, 8, 4, 6, 8)),        # up row kernel: hi-res 8 x 12 x 16, several tiles, wrap + clamp on every axis
+    (4, 2, (2, 4, 2, 3, 4)),        # smallest extents (tile rows clamp to the same low-res row), odd W, batch 2
+    (8, 4, (1, 8, 3, 2, 8)),        # odd H
+    (4, 2, (1, 4, 5, 4, 4)),        # ragged tiles in H (10 hi rows / 4)
+])
+def test_emu_up_row_kernel(cin, cout, shape):
+    """preact_row_kernels.cu::preact_up_row_kernel (decoder up blocks at 256^3 -> 512^3) vs the composed path."""
+    torch.manual_seed(cin + cout + shape[-1])
+    with use_emulator() as o, torch.no_grad():
+        blk = L.PreActFixupResBlock(cin, cout, "up").eval()
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        x = torch.randn(shape)
+        ref = blk.forward_composed(x)
+        n0 = o.launches
+        y = blk(x)
+        assert o.launches - n0 == 1, "expected one fused launch"
+        assert y.shape == ref.shape
+        assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())

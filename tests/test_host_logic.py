@@ -106,8 +106,11 @@ def test_no_cpu_fallback():
     blk = L.PreActFixupResBlock(4, 4, "same")
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):
         blk(torch.zeros(1, 4, 2, 2, 2))
-    with pytest.raises(NotImplementedError, match="backward"):
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):       # the training path refuses CPU tensors as well
         blk(torch.zeros(1, 4, 2, 2, 2))
+    reg = L.FixupResBlock(4, 4, "same")
+    with pytest.raises(NotImplementedError, match="backward"):          # block types without backward kernels say so
+        reg(torch.zeros(1, 4, 2, 2, 2))
 
 
 def test_product_never_imports_oracle():
