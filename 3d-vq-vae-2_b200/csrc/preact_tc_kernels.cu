@@ -44,6 +44,10 @@ constexpr int kTcsMaxBlocks = 24;          // blocks per launch (kernel paramete
 constexpr int kTcsAuxWarps = 4;            // warp 0 MMA issuer, warps 1..3 producers
 constexpr int kTcsProdWarps = 3;
 constexpr int kTcsMaxMB = 16;              // M-blocks per tile
+#ifndef VQ3D_TCS_PACE
+#define VQ3D_TCS_PACE 0
+#endif
+constexpr bool kTcsPace = VQ3D_TCS_PACE != 0;   // limit the conv2 batches queued in the tensor pipe (measured: no gain)
 
 struct TcsBlock {
     const float *w1, *w2, *w3;
@@ -319,7 +323,7 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                 if (i == 0 && lane == 0) tc_trace(p.trace, blk, 3);
                 const uint32_t a_base = sA_addr + s * sa_bytes;
                 for (int mb = 0; mb < p.NMB; ++mb) {
-                    if (pace_bar[0] != nullptr) mbarrier_wait(pace_bar[0], pace_par[0]);     // at most two batches queued in the pipe
+                    if (kTcsPace && pace_bar[0] != nullptr) mbarrier_wait(pace_bar[0], pace_par[0]);     // at most two batches queued in the pipe
                     pace_bar[0] = pace_bar[1]; pace_par[0] = pace_par[1];
                     pace_bar[1] = &bar_mb[s][mb]; pace_par[1] = u & 1u;
                     if (elect_one()) {
@@ -689,7 +693,7 @@ struct TcsEntry {
 
 #define VQ3D_TCS(C, CB, NCW, NBUF) {C, CB, launch_tcs<C, CB, NCW, NBUF>, ws_bytes<C, CB>}
 static const TcsEntry kTcs[] = {
-    VQ3D_TCS(8, 4, 16, 2), VQ3D_TCS(16, 8, 24, 2), VQ3D_TCS(18, 9, 24, 2), VQ3D_TCS(32, 16, 16, 2), VQ3D_TCS(64, 32, 8, 2), VQ3D_TCS(72, 36, 8, 1),
+    VQ3D_TCS(8, 4, 16, 2), VQ3D_TCS(16, 8, 24, 2), VQ3D_TCS(18, 9, 20, 2), VQ3D_TCS(32, 16, 16, 2), VQ3D_TCS(64, 32, 8, 2), VQ3D_TCS(72, 36, 8, 1),
 };
 
 static const TcsEntry *find_tcs(const vq3d_preact_desc *d) {

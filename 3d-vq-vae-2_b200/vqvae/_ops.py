@@ -27,7 +27,7 @@ class Ops:
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
-        self._ws = {}                # device -> uint8 workspace of the persistent stack kernels (grown on demand)
+        self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
 
     # -- plumbing ---------------------------------------------------------------------
     @property
@@ -68,12 +68,13 @@ class Ops:
         return ok
 
     def _workspace(self, nbytes: int, device) -> Tensor:
-        """Scratch for kernels that need one; work on a stream is ordered, so one buffer per device is
-        enough (its contents never outlive a call)."""
-        ws = self._ws.get(device)
+        """Scratch for kernels that need one.  Work on a stream is ordered and a workspace's contents never outlive
+        a call, so one buffer per (device, stream) is enough; it only grows."""
+        key = (device, self.stream())
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
-            self._ws[device] = ws
+            self._ws[key] = ws
         return ws
 
     def _check(self, rc: int, allow_unsupported: bool = False) -> bool:
