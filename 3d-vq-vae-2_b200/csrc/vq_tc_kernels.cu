@@ -31,29 +31,46 @@ namespace vq3d {
 
 #include "tc_common.cuh"
 
-constexpr int kVqtStages = 2;
-constexpr int kVqtMaxCand = 8;
+constexpr int kVqtMaxCand = 8;       // per half-row list (two column halves per row -> up to 16 candidates per latent vector)
 
+// Warp roles of one persistent CTA (one per SM; a "super-tile" is NG groups x 128 latent vectors):
+//   warp 0        codebook producer: bf16 B-operand tiles -> shared-memory ring by bulk copies (the whole codebook stays
+//                 resident when it fits the ring, so it is fetched from L2 once per CTA, not once per super-tile)
+//   warp 1        MMA issuer (one elected lane)
+//   warps 4..19   sweep warps, 8 per group: thread = (latent vector = TMEM lane, column half of the score tile).  They read
+//                 the score tiles out of TMEM and keep the running row minimum and the list of columns within `margin`
+//                 of it.  Two warps per TMEM lane quadrant and group = four sweep warps per SM sub-partition: TMEM reads
+//                 (64 B/clk per SM, the floor of this kernel: N*K*4 bytes have to leave TMEM) need that many to overlap.
+//   warps 20..27  load/epilogue warps, 4 per group: stage the A operand of super-tile i+2 while the sweep warps work on i
+//                 and i+1, then merge super-tile i's two half-row lists, resolve the candidates (exact fp32 re-rank only
+//                 when there is more than one), gather the codeword, write the straight-through value, index, loss
+//                 partial, statistics
+// so global-memory latency (x loads, codeword gather, stores) never sits between two MMAs of the same accumulator.
 template <int D>
 struct VqtCfg {
     static constexpr int DA = D + 16;                      // augmented reduction length
     static constexpr int KC = DA / 8;                      // 16-byte chunks per row
     static constexpr int KS = DA / 16;                     // K16 steps
-    static constexpr int NT = D <= 64 ? 128 : 64;          // codes per tile (MMA N)
-    static constexpr int NG = D <= 32 ? 4 : (D <= 64 ? 3 : 2);         // groups of 128 latent vectors per CTA (smem / TMEM budget)
-    static constexpr int THREADS = (4 + 4 * NG) * 32;      // warp 0 producer, warp 1 MMA, warps 4.. the groups
-    static constexpr uint32_t IMG = (uint32_t)NT * DA * 2; // one codebook tile image (hi or lo)
-    static constexpr uint32_t STAGE = 2 * IMG;             // hi | lo
-    static constexpr uint32_t AIMG = 128u * DA * 2;        // one group's A image (hi or lo)
+    static constexpr int NT = 128;                         // codes per tile (MMA N)
+    static constexpr int NG = 2;                           // groups of 128 latent vectors per super-tile (2 x 2 x 128 TMEM columns)
+    static constexpr int NABUF = D <= 64 ? 2 : 1;          // A-operand buffers per group
+    static constexpr int NSTAGE = D <= 32 ? 9 : (D <= 64 ? 4 : 2);    // codebook ring stages (shared-memory budget)
+    static constexpr int SWEEP_WARP0 = 4, LE_WARP0 = 4 + 8 * NG;
+    static constexpr int THREADS = (LE_WARP0 + 4 * NG) * 32;
+    static constexpr uint32_t STAGE = (uint32_t)NT * DA * 2;           // one codebook tile image
+    static constexpr uint32_t AIMG = 128u * DA * 2;                    // one group's A image
     static constexpr uint32_t LBO_A = 128 * 16, LBO_B = (uint32_t)NT * 16;
-    static constexpr size_t smem = 128 + (size_t)kVqtStages * STAGE + (size_t)NG * 2 * AIMG + (size_t)NG * 128 * kVqtMaxCand * 2;
+    // per (group, result buffer): ||x||^2 [128]; per (group, result buffer, half): row minimum [128], count [128],
+    // columns [kVqtMaxCand][128] (u16), running minimum at push time [kVqtMaxCand][128]
+    static constexpr size_t RES = (size_t)NG * 2 * 128 * 4 + (size_t)NG * 2 * 2 * 128 * (4 + 4 + 6 * kVqtMaxCand);
+    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES;
 };
 
 struct VqtParams {
     const float *x, *embed;
     int64_t B, S;
     int K, Kpad;
-    const unsigned char *wimg;       // per tile [hi image | lo image]
+    const unsigned char *wimg;       // per tile: bf16 image of [-2e | c0 c1 c2 0...]
     const float *cmax;               // max_k ||e_k||^2
     float *quant;
     int64_t *idx;
@@ -62,7 +79,7 @@ struct VqtParams {
     uint32_t tmem_cols;
 };
 
-// codebook -> bf16 hi/lo B-operand images of -2e with the ||e||^2 columns, padded to whole tiles
+// codebook -> bf16 B-operand images of -2e with the ||e||^2 columns (three bf16 pieces: exact to 2^-24), padded to whole tiles
 template <int D>
 __global__ void __launch_bounds__(256)
 vqt_prep_kernel(const float *__restrict__ embed, int K, int Kpad, unsigned char *wimg, float *cmax) {
@@ -90,75 +107,153 @@ vqt_prep_kernel(const float *__restrict__ embed, int K, int Kpad, unsigned char 
             v[0] = c0; v[1] = c1; v[2] = (c - c0) - c1;
         }
     }
-    float hi[8], lo[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        hi[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
-        lo[e] = v[e] - hi[e];
-    }
-    uint4 ph, pl;
-    ph.x = bf16x2(hi[0], hi[1]); ph.y = bf16x2(hi[2], hi[3]); ph.z = bf16x2(hi[4], hi[5]); ph.w = bf16x2(hi[6], hi[7]);
-    pl.x = bf16x2(lo[0], lo[1]); pl.y = bf16x2(lo[2], lo[3]); pl.z = bf16x2(lo[4], lo[5]); pl.w = bf16x2(lo[6], lo[7]);
-    unsigned char *base = wimg + (size_t)t * Cfg::STAGE + (size_t)kc * Cfg::LBO_B + (size_t)n * 16;
-    *reinterpret_cast<uint4 *>(base) = ph;
-    *reinterpret_cast<uint4 *>(base + Cfg::IMG) = pl;
+    uint4 ph;
+    ph.x = bf16x2(v[0], v[1]); ph.y = bf16x2(v[2], v[3]); ph.z = bf16x2(v[4], v[5]); ph.w = bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(wimg + (size_t)t * Cfg::STAGE + (size_t)kc * Cfg::LBO_B + (size_t)n * 16) = ph;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+// tcgen05.ld is asynchronous: the destination registers are valid after tcgen05.wait::ld.  The wait names them as
+// read-write operands so that the compiler cannot schedule a use above it.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 
-// exact squared distance in the reference's summation order (see oracle/vq_oracle.c); x read with a stride
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// exact squared distance in the reference's summation order (see oracle/vq_oracle.c); x read with a stride.  Loads are
+// issued 16 dimensions (x) + 4 float4 (codeword) at a time so that one evaluation costs D/16 memory round trips.
 template <int D>
 __device__ __forceinline__ float vqt_ref_dist2(const float *__restrict__ xs, int64_t xstride, const float *__restrict__ e) {
-    constexpr int NV = (D / 4) * 4;
+    static_assert(D % 16 == 0, "embedding_dim");
     float agg = 0.0f;
-#pragma unroll 8
-    for (int d = 0; d < NV; ++d) {
-        const float diff = __fsub_rn(__ldg(xs + (size_t)d * xstride), __ldg(e + d));
-        agg = __fadd_rn(agg, __fmul_rn(diff, diff));
-    }
+#pragma unroll(D <= 32 ? 2 : 1)
+    for (int ch = 0; ch < D / 16; ++ch) {
+        float xv[16];
+        float4 ev[4];
 #pragma unroll
-    for (int d = NV; d < D; ++d) {
-        const float diff = __fsub_rn(__ldg(xs + (size_t)d * xstride), __ldg(e + d));
-        agg = __fmaf_rn(diff, diff, agg);
+        for (int j = 0; j < 4; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 4 + j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xv[j] = __ldg(xs + (size_t)(ch * 16 + j) * xstride);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float q4[4] = {ev[j].x, ev[j].y, ev[j].z, ev[j].w};
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float diff = __fsub_rn(xv[j * 4 + l], q4[l]);
+                agg = __fadd_rn(agg, __fmul_rn(diff, diff));
+            }
+        }
     }
     return agg;
+}
+
+// per-thread state of a sweep: running minimum over this thread's columns and the columns that were within `margin`
+// of it when they were seen.  Instead of its score an entry keeps the minimum of its 16-column group (<= its score, and
+// equal to it for the group's smallest element, i.e. nearly always): an entry whose `seen` value is above (final
+// minimum + margin) cannot be a candidate; the others are kept (a superset).
+struct VqtSweep {
+    float m_run, m_push, margin;
+    int nc;
+    bool ovf;
+    unsigned short *cand;      // [kVqtMaxCand] entries, stride 128
+    float *seen;               // [kVqtMaxCand] entries, stride 128
+};
+
+// drop the entries that cannot be within margin of the final minimum any more; returns the new count
+__device__ __noinline__ int vqt_compact(float thr, int nc, unsigned short *cand, float *seen) {
+    int w = 0;
+    for (int c = 0; c < nc; ++c) {
+        const float sc = seen[c * 128];
+        if (sc <= thr) {
+            if (w != c) { seen[w * 128] = sc; cand[w * 128] = cand[c * 128]; }
+            ++w;
+        }
+    }
+    return w;
+}
+
+// one 16-column group of scores (registers): row minimum, then the candidates -- only lanes whose group minimum is
+// within margin of their running minimum enter the element scan
+__device__ __forceinline__ void vqt_group(VqtSweep &s, const uint32_t (&r)[16], int colbase) {
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+    const float g = fmin3(fmin3(fmin3(v[0], v[1], v[2]), fmin3(v[3], v[4], v[5]), fmin3(v[6], v[7], v[8])),
+                          fmin3(fmin3(v[9], v[10], v[11]), fmin3(v[12], v[13], v[14]), v[15]), __int_as_float(0x7f800000));
+    s.m_run = fminf(s.m_run, g);
+    const float thr = s.m_run + s.margin;
+    if (g <= thr) {
+        if (thr < s.m_push) s.nc = 0;       // every listed score is >= the minimum at its push > m_run + margin: stale
+        // branch-free hit mask (four independent OR chains), then one loop iteration per hit of the busiest lane
+        uint32_t h[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            uint32_t le;
+            asm("set.le.u32.f32 %0, %1, %2;" : "=r"(le) : "f"(v[e]), "f"(thr));
+            h[e & 3] |= le & (1u << e);
+        }
+        uint32_t hits = (h[0] | h[1]) | (h[2] | h[3]);
+#pragma unroll 1
+        while (hits) {
+            const int e = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (s.nc == kVqtMaxCand) s.nc = vqt_compact(thr, s.nc, s.cand, s.seen);
+            if (s.nc == kVqtMaxCand) { s.ovf = true; break; }    // degenerate codebook / massive ties: exact scan in the epilogue
+            s.cand[s.nc * 128] = (unsigned short)(colbase + e);
+            s.seen[s.nc * 128] = g;
+            ++s.nc;
+        }
+        s.m_push = s.m_run;
+    }
 }
 
 template <int D>
 __global__ void __launch_bounds__(VqtCfg<D>::THREADS, 1)
 vq_tc_kernel(const __grid_constant__ VqtParams p) {
     using Cfg = VqtCfg<D>;
-    constexpr int NT = Cfg::NT, KS = Cfg::KS, NG = Cfg::NG, NJ = NT / 16;
+    constexpr int NT = Cfg::NT, KS = Cfg::KS, NG = Cfg::NG, NABUF = Cfg::NABUF, NSTAGE = Cfg::NSTAGE;
     VQ3D_DYN_SMEM(unsigned char, smem_raw);
-    __shared__ __align__(8) uint64_t e_full[kVqtStages], e_empty[kVqtStages], a_full[NG], d_full[NG], d_empty[NG];
+    __shared__ __align__(8) uint64_t e_full[NSTAGE], e_empty[NSTAGE], a_full[NG][NABUF], a_empty[NG][NABUF],
+        d_full[NG][2], d_empty[NG][2], r_full[NG][2], r_empty[NG][2];
     __shared__ uint32_t tmem_slot;
     __shared__ double red[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t base = (s_u32(smem_raw) + 127u) & ~127u;
     unsigned char *smem = smem_raw + (base - s_u32(smem_raw));
-    const uint32_t ring_addr = base, a_addr = base + kVqtStages * Cfg::STAGE;
-    unsigned char *sA = smem + (size_t)kVqtStages * Cfg::STAGE;
-    unsigned short *s_cand = reinterpret_cast<unsigned short *>(sA + (size_t)NG * 2 * Cfg::AIMG);    // [kVqtMaxCand][NG*128]
+    const uint32_t ring_addr = base, a_addr = base + NSTAGE * Cfg::STAGE;
+    unsigned char *sA = smem + (size_t)NSTAGE * Cfg::STAGE;
+    float *s_xx = reinterpret_cast<float *>(sA + (size_t)NG * NABUF * Cfg::AIMG);      // [NG][2][128]
+    float *s_min = s_xx + NG * 2 * 128;                                                 // [NG][2][half][128]
+    int *s_nc = reinterpret_cast<int *>(s_min + NG * 2 * 2 * 128);                      // [NG][2][half][128]  (-1: overflow)
+    float *s_seen = reinterpret_cast<float *>(s_nc + NG * 2 * 2 * 128);                 // [NG][2][half][kVqtMaxCand][128]
+    unsigned short *s_cand = reinterpret_cast<unsigned short *>(s_seen + NG * 2 * 2 * kVqtMaxCand * 128);   // same shape
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        for (int s = 0; s < kVqtStages; ++s) { mbarrier_init(&e_full[s], 1); mbarrier_init(&e_empty[s], 1); }
-        for (int g = 0; g < NG; ++g) { mbarrier_init(&a_full[g], 4); mbarrier_init(&d_full[g], 1); mbarrier_init(&d_empty[g], 4); }
+        for (int s = 0; s < NSTAGE; ++s) { mbarrier_init(&e_full[s], 1); mbarrier_init(&e_empty[s], 1); }
+        for (int g = 0; g < NG; ++g) {
+            for (int b = 0; b < NABUF; ++b) { mbarrier_init(&a_full[g][b], 4); mbarrier_init(&a_empty[g][b], 9); }
+            for (int b = 0; b < 2; ++b) {
+                mbarrier_init(&d_full[g][b], 1); mbarrier_init(&d_empty[g][b], 8);
+                mbarrier_init(&r_full[g][b], 8); mbarrier_init(&r_empty[g][b], 4);
+            }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -171,15 +266,17 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     const int64_t nsuper = (N + NG * 128 - 1) / (NG * 128);
     const int my_super = nsuper > (int64_t)blockIdx.x ? (int)((nsuper - 1 - blockIdx.x) / gridDim.x + 1) : 0;
     const int ntiles = p.Kpad / NT;
+    const bool resident = ntiles <= NSTAGE;
     double err_acc = 0.0;
 
     if (warp == 0) {
-        // ===== producer: codebook tiles through the ring (the same tile sequence for every super-tile) =====
-        if (elect_one()) {
+        // ===== producer: codebook tiles (once when resident, else the same tile sequence for every super-tile) =====
+        if (elect_one() && my_super > 0) {
             uint32_t cnt = 0;
-            for (int i = 0; i < my_super; ++i)
+            const int rounds = resident ? 1 : my_super;
+            for (int i = 0; i < rounds; ++i)
                 for (int t = 0; t < ntiles; ++t, ++cnt) {
-                    const uint32_t slot = cnt % kVqtStages, u = cnt / kVqtStages;
+                    const uint32_t slot = cnt % NSTAGE, u = cnt / NSTAGE;
                     mbarrier_wait(&e_empty[slot], (u & 1u) ^ 1u);
                     mbarrier_arrive_expect_tx(&e_full[slot], Cfg::STAGE);
                     const unsigned char *src = p.wimg + (size_t)t * Cfg::STAGE;
@@ -190,169 +287,251 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        uint32_t cnt = 0, du = 0;
+        // ===== MMA issuer: score tile (g, t) -> accumulator g*2 + (unit & 1) =====
+        uint32_t cnt = 0, u = 0;
         for (int i = 0; i < my_super; ++i) {
-            for (int t = 0; t < ntiles; ++t, ++cnt, ++du) {
-                const uint32_t slot = cnt % kVqtStages, u = cnt / kVqtStages;
-                mbarrier_wait(&e_full[slot], u & 1u);
-                const uint32_t e_hi = ring_addr + slot * Cfg::STAGE, e_lo = e_hi + Cfg::IMG;
+            const int ab = i % NABUF;
+            const uint32_t apar = (uint32_t)(i / NABUF) & 1u;
+            for (int t = 0; t < ntiles; ++t, ++cnt, ++u) {
+                const uint32_t slot = resident ? (uint32_t)t : cnt % NSTAGE;
+                if (!resident || i == 0) mbarrier_wait(&e_full[slot], (cnt / NSTAGE) & 1u);
+                const uint32_t e_img = ring_addr + slot * Cfg::STAGE;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (t == 0) mbarrier_wait(&a_full[g], (uint32_t)i & 1u);
-                    mbarrier_wait(&d_empty[g], (du & 1u) ^ 1u);
+                    if (t == 0) mbarrier_wait(&a_full[g][ab], apar);
+                    mbarrier_wait(&d_empty[g][u & 1u], ((u >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
-                        const uint32_t ahi = a_addr + (uint32_t)g * 2 * Cfg::AIMG, alo = ahi + Cfg::AIMG;
-                        const uint32_t d_addr = tmem_d + (uint32_t)(g * NT);
+                        const uint32_t a_img = a_addr + (uint32_t)(g * NABUF + ab) * Cfg::AIMG;
+                        const uint32_t d_addr = tmem_d + (uint32_t)((g * 2 + (int)(u & 1u)) * NT);
 #pragma unroll
-                        for (int sp = 0; sp < 3; ++sp) {
-                            const uint32_t aa = sp == 2 ? alo : ahi, bb = sp == 1 ? e_lo : e_hi;
-#pragma unroll
-                            for (int ks = 0; ks < KS; ++ks)
-                                umma_f16(d_addr, umma_desc(aa + (uint32_t)(2 * ks) * Cfg::LBO_A, Cfg::LBO_A, 128),
-                                         umma_desc(bb + (uint32_t)(2 * ks) * Cfg::LBO_B, Cfg::LBO_B, 128), idesc, (sp > 0 || ks > 0) ? 1u : 0u);
-                        }
-                        umma_commit_to(&d_full[g]);
-                        if (g == NG - 1) umma_commit_to(&e_empty[slot]);      // every group's MMAs on this tile have been issued
+                        for (int ks = 0; ks < KS; ++ks)
+                            umma_f16(d_addr, umma_desc(a_img + (uint32_t)(2 * ks) * Cfg::LBO_A, Cfg::LBO_A, 128),
+                                     umma_desc(e_img + (uint32_t)(2 * ks) * Cfg::LBO_B, Cfg::LBO_B, 128), idesc, ks > 0 ? 1u : 0u);
+                        umma_commit_to(&d_full[g][u & 1u]);
+                        if (t == ntiles - 1) umma_commit_to(&a_empty[g][ab]);          // this super-tile's A image has been consumed
+                        if (!resident && g == NG - 1) umma_commit_to(&e_empty[slot]);    // every group's MMAs on this tile have been issued
                     }
                     __syncwarp();
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===== vector groups =====
-        const int g = (warp - 4) >> 2, q = warp & 3, row = q * 32 + lane;
-        unsigned char *a_hi = sA + (size_t)g * 2 * Cfg::AIMG + (size_t)row * 16, *a_lo = a_hi + Cfg::AIMG;
-        unsigned short *my_cand = s_cand + g * 128 + row;                // stride NG*128 between entries
+    } else if (warp >= Cfg::SWEEP_WARP0 && warp < Cfg::LE_WARP0) {
+        // ===== sweep warps =====
+        const int g = ((warp - Cfg::SWEEP_WARP0) >> 2) & 1, half = (warp - Cfg::SWEEP_WARP0) >> 3, q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const float cmax = __ldg(p.cmax);
-        const bool want_stats = p.counts != nullptr;
-        uint32_t du = 0;
+        constexpr int HC = NT / 2;           // columns per half
+        VqtSweep sw;
+        uint32_t u = 0;
         for (int i = 0; i < my_super; ++i) {
-            const int64_t sup = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
-            const int64_t v = (sup * NG + g) * 128 + row;
-            const bool active = v < N;
-            const int64_t b = active ? v / p.S : 0, s = active ? v - b * p.S : 0;
-            const float *xs = p.x + (size_t)b * D * p.S + s;
-            // ---- stage the A operand: [x | 1 1 1 0 ...] as bf16 hi / lo, K-major ----
-            float xx = 0.0f;
-#pragma unroll
-            for (int kc = 0; kc < D / 8; ++kc) {
-                float hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float xv = active ? __ldg(xs + (size_t)(kc * 8 + e) * p.S) : 0.0f;
-                    xx = __fmaf_rn(xv, xv, xx);
-                    hi[e] = __bfloat162float(__float2bfloat16_rn(xv));
-                    lo[e] = xv - hi[e];
-                }
-                uint4 ph, pl;
-                ph.x = bf16x2(hi[0], hi[1]); ph.y = bf16x2(hi[2], hi[3]); ph.z = bf16x2(hi[4], hi[5]); ph.w = bf16x2(hi[6], hi[7]);
-                pl.x = bf16x2(lo[0], lo[1]); pl.y = bf16x2(lo[2], lo[3]); pl.z = bf16x2(lo[4], lo[5]); pl.w = bf16x2(lo[6], lo[7]);
-                *reinterpret_cast<uint4 *>(a_hi + (size_t)kc * Cfg::LBO_A) = ph;
-                *reinterpret_cast<uint4 *>(a_lo + (size_t)kc * Cfg::LBO_A) = pl;
-            }
-            {
-                uint4 one, zero;
-                one.x = bf16x2(1.0f, 1.0f); one.y = bf16x2(1.0f, 0.0f); one.z = 0u; one.w = 0u;
-                zero.x = zero.y = zero.z = zero.w = 0u;
-                *reinterpret_cast<uint4 *>(a_hi + (size_t)(D / 8) * Cfg::LBO_A) = one;
-                *reinterpret_cast<uint4 *>(a_hi + (size_t)(D / 8 + 1) * Cfg::LBO_A) = zero;
-                *reinterpret_cast<uint4 *>(a_lo + (size_t)(D / 8) * Cfg::LBO_A) = zero;
-                *reinterpret_cast<uint4 *>(a_lo + (size_t)(D / 8 + 1) * Cfg::LBO_A) = zero;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int rb = i & 1, ab = i % NABUF;
+            mbarrier_wait(&r_empty[g][rb], (((uint32_t)i >> 1) & 1u) ^ 1u);
+            mbarrier_wait(&a_full[g][ab], (uint32_t)(i / NABUF) & 1u);
+            const float xx = s_xx[(g * 2 + rb) * 128 + row];
             __syncwarp();
-            if (lane == 0) mbarrier_arrive(&a_full[g]);
-            const float margin = 2.44140625e-4f * (xx + cmax) + 1e-30f;        // 2^-12
-            float m_run = __int_as_float(0x7f800000);
-            int nc = 0;
-            float best_r = __int_as_float(0x7f800000);       // exact (sqrt distance, index) of the best candidate folded in so far
-            int best_k = 0x7fffffff;
-            // exact re-rank of the collected candidates; lexicographic (sqrt(d2), k) minimum = the reference's argmin
-            auto flush = [&]() {
-                for (int c = 0; c < nc; ++c) {
-                    const int k = my_cand[c * (NG * 128)];
-                    if (k < p.K) {
-                        const float r = __fsqrt_rn(vqt_ref_dist2<D>(xs, p.S, p.embed + (size_t)k * D));
-                        if (r < best_r || (r == best_r && k < best_k)) { best_r = r; best_k = k; }
-                    }
-                }
-                nc = 0;
-            };
-            // ---- sweep the accumulator tiles ----
-            for (int t = 0; t < ntiles; ++t, ++du) {
-                mbarrier_wait(&d_full[g], du & 1u);
+            if (lane == 0) mbarrier_arrive(&a_empty[g][ab]);
+            // |tensor-core score - exact score| <= 2^-8 (1 + 2^-9) (||x||^2 + ||e_k||^2) (bf16 operands, fp32 accumulation), so
+            // the reference's argmin is among the columns within twice that of the row minimum
+            sw.margin = 0.00785f * (xx + cmax) + 1e-30f;
+            sw.m_run = __int_as_float(0x7f800000);
+            sw.m_push = __int_as_float(0x7f800000);
+            sw.nc = 0;
+            sw.ovf = false;
+            const int slot_res = (g * 2 + rb) * 2 + half;
+            sw.cand = s_cand + (size_t)slot_res * kVqtMaxCand * 128 + row;
+            sw.seen = s_seen + (size_t)slot_res * kVqtMaxCand * 128 + row;
+            for (int t = 0; t < ntiles; ++t, ++u) {
+                mbarrier_wait(&d_full[g][u & 1u], (u >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_addr = tmem_d + lane_sel + (uint32_t)(g * NT);
-                float lmin[NJ];
-                const float m_old = m_run;
-#pragma unroll
-                for (int j2 = 0; j2 < NJ / 2; ++j2) {
-                    float sc[32];
-                    tmem_ld32(d_addr + (uint32_t)(j2 * 32), sc);
-                    float m0 = sc[0], m1 = sc[16];
-#pragma unroll
-                    for (int e = 1; e < 16; ++e) { m0 = fminf(m0, sc[e]); m1 = fminf(m1, sc[16 + e]); }
-                    lmin[2 * j2] = m0; lmin[2 * j2 + 1] = m1;
-                    m_run = fminf(m_run, fminf(m0, m1));
-                }
-                const float thr = m_run + margin;
-                if (thr + margin < m_old) nc = 0;            // every earlier candidate is now further than margin from the minimum
-                // 16-column groups that can hold a candidate of this row; visit the union over the warp (tcgen05.ld is
-                // warp-wide) in ONE rolled loop so that the push / flush code exists once (instruction cache)
-                uint32_t gmask = 0;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) gmask |= (lmin[j] <= thr ? 1u : 0u) << j;
-                uint32_t um = __reduce_or_sync(0xffffffffu, gmask);
+                const uint32_t d_addr = tmem_d + lane_sel + (uint32_t)((g * 2 + (int)(u & 1u)) * NT + half * HC);
+                const int col0 = t * NT + half * HC;
+                // ping-pong over the 16-column groups: the next group's tcgen05.ld is in flight while this one is scanned
+                uint32_t ra[16], rb16[16];
+                tmem_ld16_async(d_addr, ra);
+                tmem_wait_ld16(ra);
 #pragma unroll 1
-                while (um) {
-                    const int j = __ffs(um) - 1;
-                    um &= um - 1;
-                    float sc[16];
-                    tmem_ld16(d_addr + (uint32_t)(j * 16), sc);
-                    uint32_t hits = 0;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) hits |= (sc[e] <= thr ? 1u : 0u) << e;
-                    if (!((gmask >> j) & 1u)) hits = 0;
-#pragma unroll 1
-                    while (hits) {
-                        const int e = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        if (nc == kVqtMaxCand) { if (active) flush(); else nc = 0; }
-                        my_cand[nc * (NG * 128)] = (unsigned short)(t * NT + j * 16 + e);
-                        ++nc;
-                    }
+                for (int c = 0; c < HC / 16; c += 2) {
+                    tmem_ld16_async(d_addr + (uint32_t)((c + 1) * 16), rb16);
+                    vqt_group(sw, ra, col0 + c * 16);
+                    tmem_wait_ld16(rb16);
+                    if (c + 2 < HC / 16) tmem_ld16_async(d_addr + (uint32_t)((c + 2) * 16), ra);
+                    vqt_group(sw, rb16, col0 + (c + 1) * 16);
+                    tmem_wait_ld16(ra);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbarrier_arrive(&d_empty[g]);
+                if (lane == 0) mbarrier_arrive(&d_empty[g][u & 1u]);
             }
-            // ---- exact re-rank, gather, straight-through value, loss partial, statistics ----
-            if (active) {
-                flush();
-                if (best_k == 0x7fffffff) {          // nothing finite collected (NaN input): exact full scan, first minimum
-                    for (int k = 0; k < p.K; ++k) {
-                        const float r = __fsqrt_rn(vqt_ref_dist2<D>(xs, p.S, p.embed + (size_t)k * D));
-                        if (r < best_r || best_k == 0x7fffffff) { best_r = r; best_k = k; }
-                    }
+            s_min[slot_res * 128 + row] = sw.m_run;
+            s_nc[slot_res * 128 + row] = sw.ovf ? -1 : sw.nc;
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(&r_full[g][rb]);
+        }
+    } else if (warp >= Cfg::LE_WARP0) {
+        // ===== load / epilogue warps =====
+        const int g = (warp - Cfg::LE_WARP0) >> 2, q = warp & 3, row = q * 32 + lane;
+        const float cmax = __ldg(p.cmax);
+        const bool want_stats = p.counts != nullptr;
+        const bool dw_vec = (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
+        auto locate = [&](int i, int64_t &b, int64_t &s) -> bool {
+            const int64_t sup = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+            const int64_t v = (sup * NG + g) * 128 + row;
+            const bool active = v < N;
+            b = active ? v / p.S : 0;
+            s = active ? v - b * p.S : 0;
+            return active;
+        };
+        // ---- stage the A operand of super-tile i: [x | 1 1 1 0 ...] as bf16, K-major; ||x||^2 for the margin ----
+        auto stage = [&](int i) {
+            const int ab = i % NABUF, rb = i & 1;
+            int64_t b, s;
+            const bool active = locate(i, b, s);
+            const float *xs = p.x + (size_t)b * D * p.S + s;
+            mbarrier_wait(&a_empty[g][ab], ((uint32_t)(i / NABUF) & 1u) ^ 1u);
+            unsigned char *a_img = sA + (size_t)(g * NABUF + ab) * Cfg::AIMG + (size_t)row * 16;
+            float xx = 0.0f;
+            const float *px = xs;
+#pragma unroll 4
+            for (int kc = 0; kc < D / 8; ++kc) {
+                float xv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e, px += p.S) xv[e] = active ? __ldg(px) : 0.0f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xx = __fmaf_rn(xv[e], xv[e], xx);
+                uint4 ph;
+                ph.x = bf16x2(xv[0], xv[1]); ph.y = bf16x2(xv[2], xv[3]); ph.z = bf16x2(xv[4], xv[5]); ph.w = bf16x2(xv[6], xv[7]);
+                *reinterpret_cast<uint4 *>(a_img + (size_t)kc * Cfg::LBO_A) = ph;
+            }
+            uint4 one, zero;
+            one.x = bf16x2(1.0f, 1.0f); one.y = bf16x2(1.0f, 0.0f); one.z = 0u; one.w = 0u;
+            zero.x = zero.y = zero.z = zero.w = 0u;
+            *reinterpret_cast<uint4 *>(a_img + (size_t)(D / 8) * Cfg::LBO_A) = one;
+            *reinterpret_cast<uint4 *>(a_img + (size_t)(D / 8 + 1) * Cfg::LBO_A) = zero;
+            s_xx[(g * 2 + rb) * 128 + row] = xx;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(&a_full[g][ab]);
+        };
+        if (my_super > 0) stage(0);
+        if (my_super > 1) stage(1);
+        for (int i = 0; i < my_super; ++i) {
+            const int rb = i & 1;
+            int64_t b, s;
+            const bool active = locate(i, b, s);
+            const float *xs = p.x + (size_t)b * D * p.S + s;
+            mbarrier_wait(&r_full[g][rb], ((uint32_t)i >> 1) & 1u);
+            // merge the two half-row lists: final minimum, then the entries that can still be within margin of it
+            const int res0 = (g * 2 + rb) * 2;
+            const float m_fin = fminf(s_min[res0 * 128 + row], s_min[(res0 + 1) * 128 + row]);
+            const float thr_fin = m_fin + (0.00785f * (s_xx[(g * 2 + rb) * 128 + row] + cmax) + 1e-30f);
+            int kk[2 * kVqtMaxCand];
+#pragma unroll
+            for (int j = 0; j < 2 * kVqtMaxCand; ++j) kk[j] = 0x7fffffff;
+            int nc = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int nh = s_nc[(res0 + h) * 128 + row];
+                if (nh < 0) nc = -100;
+#pragma unroll
+                for (int c = 0; c < kVqtMaxCand; ++c) {
+                    const bool keep = c < nh && s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <= thr_fin;
+                    const int k = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
+                    // compacting insert without dynamic register indexing
+#pragma unroll
+                    for (int j = 0; j < 2 * kVqtMaxCand; ++j)
+                        if (keep && nc == j) kk[j] = k;
+                    nc += keep ? 1 : 0;
                 }
+            }
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(&r_empty[g][rb]);
+            int best_k = 0x7fffffff;
+            bool need_scan = false;
+            if (active) {
+#ifdef VQ3D_VQT_DEBUG
+                {
+                    unsigned *dbg = reinterpret_cast<unsigned *>(const_cast<float *>(p.cmax)) + 4;
+                    atomicAdd(dbg + (nc == 1 ? 0 : (nc >= 2 ? 1 : (nc == 0 ? 2 : 3))), 1u);
+                    if (nc >= 2) atomicAdd(dbg + 4, (unsigned)nc);
+                }
+#endif
+                if (nc == 1 && kk[0] < p.K) {
+                    best_k = kk[0];                      // alone within the error bound: it IS the reference's argmin
+                } else {
+                    // exact re-rank; lexicographic (sqrt(d2), k) minimum = the reference's argmin (first minimum)
+                    float best_r = __int_as_float(0x7f800000);
+#pragma unroll 1
+                    for (int c = 0; c < nc; ++c) {
+                        const int k = kk[0];
+#pragma unroll
+                        for (int j = 0; j + 1 < 2 * kVqtMaxCand; ++j) kk[j] = kk[j + 1];
+                        if (k < p.K) {
+                            const float r = __fsqrt_rn(vqt_ref_dist2<D>(xs, p.S, p.embed + (size_t)k * D));
+                            if (r < best_r || (r == best_r && k < best_k)) { best_r = r; best_k = k; }
+                        }
+                    }
+                    need_scan = best_k == 0x7fffffff;    // list overflow or nothing finite (NaN input)
+                }
+            }
+            // exact scan of the whole codebook for the (rare) vectors without a usable list: the warp splits the codes,
+            // every lane keeps its first minimum, then a lexicographic (distance, index) reduction
+            __syncwarp();
+            unsigned scan_mask = __ballot_sync(0xffffffffu, need_scan);
+#pragma unroll 1
+            while (scan_mask) {
+                const int src = __ffs(scan_mask) - 1;
+                scan_mask &= scan_mask - 1;
+                const int64_t sb = __shfl_sync(0xffffffffu, b, src), ss = __shfl_sync(0xffffffffu, s, src);
+                const float *sxs = p.x + (size_t)sb * D * p.S + ss;
+                float r_best = __int_as_float(0x7f800000);
+                int k_best = 0x7fffffff;
+                for (int k = lane; k < p.K; k += 32) {
+                    const float r = __fsqrt_rn(vqt_ref_dist2<D>(sxs, p.S, p.embed + (size_t)k * D));
+                    if (r < r_best || k_best == 0x7fffffff) { r_best = r; k_best = k; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float r2 = __shfl_xor_sync(0xffffffffu, r_best, o);
+                    const int k2 = __shfl_xor_sync(0xffffffffu, k_best, o);
+                    const bool take = k2 != 0x7fffffff && (k_best == 0x7fffffff || r2 < r_best || (r2 == r_best && k2 < k_best) ||
+                                                           (r_best != r_best && r2 != r2 && k2 < k_best));
+                    if (take) { r_best = r2; k_best = k2; }
+                }
+                if (lane == src) best_k = k_best;
+            }
+            if (active) {
                 const float *e = p.embed + (size_t)best_k * D;
                 float err = 0.0f;
-#pragma unroll 8
-                for (int d = 0; d < D; ++d) {
-                    const float qv = __ldg(e + d);
-                    const float xv = __ldg(xs + (size_t)d * p.S);
-                    const float df = qv - xv;
-                    err = __fmaf_rn(df, df, err);
-                    p.quant[((size_t)b * D + d) * p.S + s] = __fadd_rn(xv, __fsub_rn(qv, xv));    // layers.py:720, two roundings
-                    if (want_stats) atomicAdd(&p.dw[(size_t)best_k * D + d], xv);
+#pragma unroll 1
+                for (int ch = 0; ch < D / 16; ++ch) {
+                    float4 ev[4];
+                    float xv[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 4 + j);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) xv[j] = __ldg(xs + (size_t)(ch * 16 + j) * p.S);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float qv[4] = {ev[j].x, ev[j].y, ev[j].z, ev[j].w};
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) {
+                            const float df = qv[l] - xv[j * 4 + l];
+                            err = __fmaf_rn(df, df, err);
+                            p.quant[((size_t)b * D + ch * 16 + j * 4 + l) * p.S + s] = __fadd_rn(xv[j * 4 + l], __fsub_rn(qv[l], xv[j * 4 + l]));    // layers.py:720, two roundings
+                        }
+                        if (want_stats) {
+                            float *dst = p.dw + (size_t)best_k * D + ch * 16 + j * 4;
+                            if (dw_vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xv[j * 4]), "f"(xv[j * 4 + 1]), "f"(xv[j * 4 + 2]), "f"(xv[j * 4 + 3]) : "memory");
+                            else { atomicAdd(dst, xv[j * 4]); atomicAdd(dst + 1, xv[j * 4 + 1]); atomicAdd(dst + 2, xv[j * 4 + 2]); atomicAdd(dst + 3, xv[j * 4 + 3]); }
+                        }
+                    }
                 }
                 if (want_stats) atomicAdd(&p.counts[best_k], 1.0f);
                 p.idx[(size_t)b * p.S + s] = best_k;
                 err_acc += (double)err;
             }
+            if (i + 2 < my_super) stage(i + 2);
         }
     }
     // ---- squared-error total of the CTA ----
@@ -393,16 +572,15 @@ static int launch_vqt(const float *x, const float *embed, int64_t B, int64_t S, 
     p.cmax = reinterpret_cast<float *>(wsb);
     p.wimg = wsb + 256;
     p.quant = quant; p.idx = idx; p.sqerr = sqerr; p.counts = counts; p.dw = dw;
-    uint32_t cols = 32;
-    while (cols < (uint32_t)(Cfg::NG * Cfg::NT)) cols <<= 1;
-    p.tmem_cols = cols;
+    p.tmem_cols = 512;                                                   // NG groups x 2 accumulators x NT columns
     cudaError_t e = cudaMemsetAsync(wsb, 0, 256, st);
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(memset)");
     vqt_prep_kernel<D><<<(unsigned)ceil_div((int64_t)p.Kpad * Cfg::KC, 256), 256, 0, st>>>(embed, K, p.Kpad, wsb + 256, reinterpret_cast<float *>(wsb));
     e = cudaGetLastError();
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(prep)");
     auto kernel = vq_tc_kernel<D>;
-    size_t smem = Cfg::smem < 120 * 1024 ? 120 * 1024 : Cfg::smem;       // one CTA per SM (TMEM)
+    static_assert(Cfg::NG * 2 * Cfg::NT == 512, "TMEM budget");
+    size_t smem = Cfg::smem;                                             // > 113 KB: one CTA per SM (it owns all of TMEM)
     e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(attr)");
     const int64_t nsuper = ceil_div(B * S, Cfg::NG * 128);
