@@ -12,10 +12,12 @@ __device__ __forceinline__ void mbarrier_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = s_u32(bar);
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        // the suspend-time hint lets the hardware park the warp until the phase completes instead of returning early
+        // and spinning (spinning warps take issue slots from the working warps of the same sub-partition)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
         if (ok) return;
     }
     __trap();   // a lost arrival becomes a launch error, never a hung GPU

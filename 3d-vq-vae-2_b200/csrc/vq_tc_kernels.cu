@@ -63,7 +63,8 @@ struct VqtCfg {
     // per (group, result buffer): ||x||^2 [128]; per (group, result buffer, half): row minimum [128], count [128],
     // columns [kVqtMaxCand][128] (u16), running minimum at push time [kVqtMaxCand][128]
     static constexpr size_t RES = (size_t)NG * 2 * 128 * 4 + (size_t)NG * 2 * 2 * 128 * (4 + 4 + 6 * kVqtMaxCand);
-    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES;
+    static constexpr size_t QUEUE = (size_t)4 * NG * 64 * 8;          // per load/epilogue warp: 64 (code | lane, distance) pairs
+    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES + QUEUE;
 };
 
 struct VqtParams {
@@ -197,19 +198,17 @@ __device__ __forceinline__ void vqt_group(VqtSweep &s, const uint32_t (&r)[16], 
     const float thr = s.m_run + s.margin;
     if (g <= thr) {
         if (thr < s.m_push) s.nc = 0;       // every listed score is >= the minimum at its push > m_run + margin: stale
-        // branch-free hit mask (four independent OR chains), then one loop iteration per hit of the busiest lane
-        uint32_t h[4] = {0u, 0u, 0u, 0u};
+        // branch-free miss mask: thr - v is negative exactly when v > thr; its sign bit is shifted into one of four
+        // independent chains (one FMA-pipe and one ALU-pipe instruction per column; both pipes issue every other cycle)
+        uint32_t c4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            uint32_t le;
-            asm("set.le.u32.f32 %0, %1, %2;" : "=r"(le) : "f"(v[e]), "f"(thr));
-            h[e & 3] |= le & (1u << e);
-        }
-        uint32_t hits = (h[0] | h[1]) | (h[2] | h[3]);
+        for (int e = 0; e < 16; ++e)
+            c4[e >> 2] = __funnelshift_l(__float_as_uint(__fsub_rn(thr, v[e])), c4[e >> 2], 1);
+        uint32_t hits = ~((c4[0] << 12) | (c4[1] << 8) | (c4[2] << 4) | c4[3]) & 0xffffu;      // column e is bit 15 - e
 #pragma unroll 1
         while (hits) {
-            const int e = __ffs(hits) - 1;
-            hits &= hits - 1;
+            const int e = __clz(hits) - 16;
+            hits &= ~(0x8000u >> e);
             if (s.nc == kVqtMaxCand) s.nc = vqt_compact(thr, s.nc, s.cand, s.seen);
             if (s.nc == kVqtMaxCand) { s.ovf = true; break; }    // degenerate codebook / massive ties: exact scan in the epilogue
             s.cand[s.nc * 128] = (unsigned short)(colbase + e);
@@ -240,6 +239,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     int *s_nc = reinterpret_cast<int *>(s_min + NG * 2 * 2 * 128);                      // [NG][2][half][128]  (-1: overflow)
     float *s_seen = reinterpret_cast<float *>(s_nc + NG * 2 * 2 * 128);                 // [NG][2][half][kVqtMaxCand][128]
     unsigned short *s_cand = reinterpret_cast<unsigned short *>(s_seen + NG * 2 * 2 * kVqtMaxCand * 128);   // same shape
+    uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_cand + NG * 2 * 2 * kVqtMaxCand * 128);              // [4*NG warps][64] + distances
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -378,6 +378,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             const int64_t sup = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
             const int64_t v = (sup * NG + g) * 128 + row;
             const bool active = v < N;
+            if (p.B == 1) { b = 0; s = active ? v : 0; return active; }       // the usual case: no 64-bit division
             b = active ? v / p.S : 0;
             s = active ? v - b * p.S : 0;
             return active;
@@ -425,55 +426,85 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             const int res0 = (g * 2 + rb) * 2;
             const float m_fin = fminf(s_min[res0 * 128 + row], s_min[(res0 + 1) * 128 + row]);
             const float thr_fin = m_fin + (0.00785f * (s_xx[(g * 2 + rb) * 128 + row] + cmax) + 1e-30f);
-            int kk[2 * kVqtMaxCand];
-#pragma unroll
-            for (int j = 0; j < 2 * kVqtMaxCand; ++j) kk[j] = 0x7fffffff;
-            int nc = 0;
+            int nc = 0, k_one = 0x7fffffff;
+            bool ovf = false;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int nh = s_nc[(res0 + h) * 128 + row];
-                if (nh < 0) nc = -100;
-#pragma unroll
-                for (int c = 0; c < kVqtMaxCand; ++c) {
-                    const bool keep = c < nh && s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <= thr_fin;
-                    const int k = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
-                    // compacting insert without dynamic register indexing
-#pragma unroll
-                    for (int j = 0; j < 2 * kVqtMaxCand; ++j)
-                        if (keep && nc == j) kk[j] = k;
-                    nc += keep ? 1 : 0;
-                }
+                ovf |= nh < 0;
+                for (int c = 0; c < nh; ++c)
+                    if (s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <= thr_fin) {
+                        ++nc;
+                        k_one = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
+                    }
             }
-            __syncwarp();
-            if (lane == 0) mbarrier_arrive(&r_empty[g][rb]);
             int best_k = 0x7fffffff;
             bool need_scan = false;
             if (active) {
 #ifdef VQ3D_VQT_DEBUG
                 {
                     unsigned *dbg = reinterpret_cast<unsigned *>(const_cast<float *>(p.cmax)) + 4;
-                    atomicAdd(dbg + (nc == 1 ? 0 : (nc >= 2 ? 1 : (nc == 0 ? 2 : 3))), 1u);
+                    atomicAdd(dbg + (ovf ? 3 : (nc == 1 ? 0 : (nc >= 2 ? 1 : 2))), 1u);
                     if (nc >= 2) atomicAdd(dbg + 4, (unsigned)nc);
                 }
 #endif
-                if (nc == 1 && kk[0] < p.K) {
-                    best_k = kk[0];                      // alone within the error bound: it IS the reference's argmin
-                } else {
-                    // exact re-rank; lexicographic (sqrt(d2), k) minimum = the reference's argmin (first minimum)
-                    float best_r = __int_as_float(0x7f800000);
+                if (!ovf && nc == 1 && k_one < p.K) best_k = k_one;      // alone within the error bound: it IS the reference's argmin
+            }
+            // exact re-rank of the vectors with several candidates, densely packed over the warp: the (vector, code) pairs
+            // go through a 64-entry queue, every lane evaluates one pair per round with the reference's arithmetic, the
+            // owners keep the lexicographic (sqrt(d2), k) minimum = the reference's argmin (first minimum)
+            {
+                const bool requester = active && !ovf && best_k == 0x7fffffff && nc >= 1;
+                uint32_t *q_key = s_queue + (size_t)(warp - Cfg::LE_WARP0) * 128;
+                float *q_r = reinterpret_cast<float *>(q_key + 64);
+                int remaining = requester ? nc : 0, cursor = 0;
+                float best_r = __int_as_float(0x7f800000);
 #pragma unroll 1
-                    for (int c = 0; c < nc; ++c) {
-                        const int k = kk[0];
+                while (__any_sync(0xffffffffu, remaining > 0)) {
+                    int incl = remaining;
 #pragma unroll
-                        for (int j = 0; j + 1 < 2 * kVqtMaxCand; ++j) kk[j] = kk[j + 1];
-                        if (k < p.K) {
-                            const float r = __fsqrt_rn(vqt_ref_dist2<D>(xs, p.S, p.embed + (size_t)k * D));
-                            if (r < best_r || (r == best_r && k < best_k)) { best_r = r; best_k = k; }
-                        }
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
                     }
-                    need_scan = best_k == 0x7fffffff;    // list overflow or nothing finite (NaN input)
+                    const int excl = incl - remaining;
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    int take = 64 - excl;
+                    take = take < 0 ? 0 : (take > remaining ? remaining : take);
+                    for (int j = 0; j < take; ++j) {
+                        // next kept entry of this row's two lists
+                        for (;; ++cursor) {
+                            const int h = cursor / kVqtMaxCand, c = cursor % kVqtMaxCand;
+                            if (c < s_nc[(res0 + h) * 128 + row] && s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <= thr_fin) break;
+                        }
+                        const int h = cursor / kVqtMaxCand, c = cursor % kVqtMaxCand;
+                        q_key[excl + j] = (uint32_t)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] | ((uint32_t)lane << 16);
+                        ++cursor;
+                    }
+                    __syncwarp();
+                    const int nq = total < 64 ? total : 64;
+#pragma unroll 1
+                    for (int pp = lane; pp < 64; pp += 32) {
+                        const uint32_t key = pp < nq ? q_key[pp] : 0u;
+                        const int owner = (int)(key >> 16), k = (int)(key & 0xffffu);
+                        const int64_t ob = __shfl_sync(0xffffffffu, b, owner), os = __shfl_sync(0xffffffffu, s, owner);
+                        if (pp < nq)
+                            q_r[pp] = k < p.K ? __fsqrt_rn(vqt_ref_dist2<D>(p.x + (size_t)ob * D * p.S + os, p.S, p.embed + (size_t)k * D))
+                                              : __int_as_float(0x7fc00000);
+                    }
+                    __syncwarp();
+                    for (int j = 0; j < take; ++j) {
+                        const float r = q_r[excl + j];
+                        const int k = (int)(q_key[excl + j] & 0xffffu);
+                        if (r < best_r || (r == best_r && k < best_k)) { best_r = r; best_k = k; }
+                    }
+                    remaining -= take;
+                    __syncwarp();
                 }
             }
+            if (active) need_scan = best_k == 0x7fffffff;        // list overflow or nothing finite (NaN input)
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(&r_empty[g][rb]);
             // exact scan of the whole codebook for the (rare) vectors without a usable list: the warp splits the codes,
             // every lane keeps its first minimum, then a lexicographic (distance, index) reduction
             __syncwarp();
