@@ -147,24 +147,29 @@ conv3d_tc_kernel(TcParams p) {
             int ci = kidx / k3, t = kidx - ci * k3;
             int kh = t / kk; t -= kh * kk;
             int kw = t / k, kz = t - kw * k;
-            float vals[8];
+            // addresses first, then the eight loads back to back (one memory round trip per chunk), then the transform
+            const float *src[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float xv = 0.0f;
+                src[e] = nullptr;
                 if (row_ok && ci < Cin) {
                     int ih = ih0 + kh, iw = iw0 + kw, iz = iz0 + kz;
                     bool ok = true;
                     if (p.circ) { ih = wrap(ih, p.H); iw = wrap(iw, p.W); iz = wrap(iz, p.Z); }
                     else ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;
                     if (ok) {
-                        const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
-                        xv = __ldg(src + ((size_t)ih * p.W + iw) * p.Z + iz);
-                        xv = p.pre_act ? elu1(xv + pa) + pb : xv + pb;
+                        const float *base = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+                        src[e] = base + ((size_t)ih * p.W + iw) * p.Z + iz;
                     }
                 }
-                vals[e] = xv;
                 if (++kz == k) { kz = 0; if (++kw == k) { kw = 0; if (++kh == k) { kh = 0; ++ci; } } }
             }
+            float vals[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vals[e] = src[e] ? __ldg(src[e]) : 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (src[e]) vals[e] = p.pre_act ? elu1(vals[e] + pa) + pb : vals[e] + pb;
             uint4 pk;
             pk.x = pack_bf16(vals[0], vals[1]); pk.y = pack_bf16(vals[2], vals[3]);
             pk.z = pack_bf16(vals[4], vals[5]); pk.w = pack_bf16(vals[6], vals[7]);
@@ -254,13 +259,29 @@ conv3d_tc_kernel(TcParams p) {
                 if (v2 < total) {
                     const int b2 = (int)(v2 / So);
                     const int64_t rem2 = v2 - (int64_t)b2 * So;
-                    for (int co = g; co < p.Cout; co += G) {
-                        const size_t o = ((size_t)b2 * p.Cout + co) * So + rem2;
-                        float yv = __fmaf_rn(__ldcg(p.ws + (size_t)v2 * Npad + co), sc, sbias);
-                        if (p.bias) yv += __ldg(p.bias + co);
-                        if (p.residual) yv += __ldg(p.residual + o);
-                        if (p.post_act) yv = elu1(yv);
-                        p.y[o] = yv;
+                    // eight output channels per step: the loads of a step are issued together (the loop is a latency chain otherwise)
+                    for (int co0 = g; co0 < p.Cout; co0 += 8 * G) {
+                        float acc8[8], res8[8], bias8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int co = co0 + j * G;
+                            const bool in = co < p.Cout;
+                            const size_t o = ((size_t)b2 * p.Cout + (in ? co : 0)) * So + rem2;
+                            acc8[j] = in ? __ldcg(p.ws + (size_t)v2 * Npad + co) : 0.0f;
+                            res8[j] = (in && p.residual) ? __ldg(p.residual + o) : 0.0f;
+                            bias8[j] = (in && p.bias) ? __ldg(p.bias + co) : 0.0f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int co = co0 + j * G;
+                            if (co < p.Cout) {
+                                float yv = __fmaf_rn(acc8[j], sc, sbias);
+                                if (p.bias) yv += bias8[j];
+                                if (p.residual) yv += res8[j];
+                                if (p.post_act) yv = elu1(yv);
+                                p.y[((size_t)b2 * p.Cout + co) * So + rem2] = yv;
+                            }
+                        }
                     }
                 }
             }

@@ -71,8 +71,10 @@ struct VqtParams {
     const float *x, *embed;
     int64_t B, S;
     int K, Kpad;
-    const unsigned char *wimg;       // per tile: bf16 image of [-2e | c0 c1 c2 0...]
-    const float *cmax;               // max_k ||e_k||^2
+    const unsigned char *wimg;       // per tile: bf16 image of [-2e | c0 c1 c2 0...], codes sorted by ascending norm
+    const int *perm;                 // column -> code index (the norm-sorted order)
+    const float *tnorm;              // per tile: largest ||e_k|| in it
+    const unsigned *dbg;             // debug counters (VQ3D_VQT_DEBUG builds)
     float *quant;
     int64_t *idx;
     double *sqerr;
@@ -80,32 +82,59 @@ struct VqtParams {
     uint32_t tmem_cols;
 };
 
+// ||e_k||^2 in fp32 (one fma chain per code)
+__global__ void __launch_bounds__(256)
+vqt_norm_kernel(const float *__restrict__ embed, int K, int D, float *__restrict__ cnorm) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float c = 0.0f;
+    for (int d = 0; d < D; ++d) { const float ev = __ldg(embed + (size_t)k * D + d); c = __fmaf_rn(ev, ev, c); }
+    cnorm[k] = c;
+}
+
+// columns are the codes in ascending-norm order (ties: ascending index), so that the codes of one tile have similar norms
+// and the per-tile error bound of the tensor-core scores is tight whatever outliers the codebook holds
+__global__ void __launch_bounds__(256)
+vqt_rank_kernel(const float *__restrict__ cnorm, int K, int Kpad, int *__restrict__ perm) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kpad) return;
+    if (k >= K) { perm[k] = k; return; }                 // padding columns stay at the end
+    const float c = cnorm[k];
+    const float ck = c == c ? c : __int_as_float(0x7f800000);
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+        const float cj0 = __ldg(cnorm + j);
+        const float cj = cj0 == cj0 ? cj0 : __int_as_float(0x7f800000);
+        rank += (cj < ck || (cj == ck && j < k)) ? 1 : 0;
+    }
+    perm[rank] = k;
+}
+
 // codebook -> bf16 B-operand images of -2e with the ||e||^2 columns (three bf16 pieces: exact to 2^-24), padded to whole tiles
 template <int D>
 __global__ void __launch_bounds__(256)
-vqt_prep_kernel(const float *__restrict__ embed, int K, int Kpad, unsigned char *wimg, float *cmax) {
+vqt_prep_kernel(const float *__restrict__ embed, const float *__restrict__ cnorm, const int *__restrict__ perm, int K, int Kpad,
+                unsigned char *wimg, float *tnorm) {
     using Cfg = VqtCfg<D>;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Kpad * Cfg::KC) return;
-    const int k = i / Cfg::KC, kc = i % Cfg::KC;
-    const int t = k / Cfg::NT, n = k % Cfg::NT;
+    const int col = i / Cfg::KC, kc = i % Cfg::KC;
+    const int t = col / Cfg::NT, n = col % Cfg::NT;
+    const int k = col < K ? perm[col] : -1;
     float v[8];
     if (kc * 8 < D) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = k < K ? -2.0f * __ldg(embed + (size_t)k * D + kc * 8 + e) : 0.0f;
+        for (int e = 0; e < 8; ++e) v[e] = k >= 0 ? -2.0f * __ldg(embed + (size_t)k * D + kc * 8 + e) : 0.0f;
     } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.0f;
         if (kc * 8 == D) {
-            float c = 1e30f;                              // padding rows can never be candidates
-            if (k < K) {
-                c = 0.0f;
-                for (int d = 0; d < D; ++d) { const float ev = __ldg(embed + (size_t)k * D + d); c = __fmaf_rn(ev, ev, c); }
-                atomicMax(reinterpret_cast<int *>(cmax), __float_as_int(c));      // c >= 0: int order = float order
-            }
+            const float c = k >= 0 ? cnorm[k] : 1e30f;     // padding columns can never be candidates
             const float c0 = __bfloat162float(__float2bfloat16_rn(c));
             const float c1 = __bfloat162float(__float2bfloat16_rn(c - c0));
             v[0] = c0; v[1] = c1; v[2] = (c - c0) - c1;
+            // the last real column of a tile carries the tile's largest norm
+            if (k >= 0 && (n == Cfg::NT - 1 || col == K - 1)) tnorm[t] = sqrtf(c);
         }
     }
     uint4 ph;
@@ -126,6 +155,15 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                  :: "memory");
+}
+
+// |tensor-core score - exact score| for a code k of a tile whose largest norm is tn: the bf16 roundings of x and -2e
+// change x.(-2e) by at most 2 sum|x_i||e_i| (2^-9 + 2^-9 + 2^-18) <= 2^-7 (1 + 2^-10) ||x|| ||e_k|| (Cauchy-Schwarz); the
+// ||e||^2 columns are exact to 2^-24 and the fp32 accumulation / the reference's own roundings stay below
+// 2^-17 (||x||^2 + ||e_k||^2).  With H_t this bound, true_k >= score_k - H_t(k) and true_j <= score_j + H_t(j): the
+// reference's argmin k satisfies score_k <= U + H_t(k), U = min_j (score_j + H_t(j)).
+__device__ __forceinline__ float vqt_half_margin(float xnorm, float xx, float tn) {
+    return 0.00786f * xnorm * tn + 0.8e-5f * (xx + tn * tn) + 1e-30f;
 }
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
@@ -166,7 +204,7 @@ __device__ __forceinline__ float vqt_ref_dist2(const float *__restrict__ xs, int
 // equal to it for the group's smallest element, i.e. nearly always): an entry whose `seen` value is above (final
 // minimum + margin) cannot be a candidate; the others are kept (a superset).
 struct VqtSweep {
-    float m_run, m_push, margin;
+    float m_run, m_push, u_run, hm;      // running minimum, its value at the last push, running U, this tile's half margin
     int nc;
     bool ovf;
     unsigned short *cand;      // [kVqtMaxCand] entries, stride 128
@@ -195,9 +233,10 @@ __device__ __forceinline__ void vqt_group(VqtSweep &s, const uint32_t (&r)[16], 
     const float g = fmin3(fmin3(fmin3(v[0], v[1], v[2]), fmin3(v[3], v[4], v[5]), fmin3(v[6], v[7], v[8])),
                           fmin3(fmin3(v[9], v[10], v[11]), fmin3(v[12], v[13], v[14]), v[15]), __int_as_float(0x7f800000));
     s.m_run = fminf(s.m_run, g);
-    const float thr = s.m_run + s.margin;
+    s.u_run = fminf(s.u_run, g + s.hm);
+    const float thr = s.u_run + s.hm;
     if (g <= thr) {
-        if (thr < s.m_push) s.nc = 0;       // every listed score is >= the minimum at its push > m_run + margin: stale
+        if (thr < s.m_push) s.nc = 0;       // every listed score is >= the minimum at its push > U + this tile's half margin >= U + its own: stale
         // branch-free miss mask: thr - v is negative exactly when v > thr; its sign bit is shifted into one of four
         // independent chains (one FMA-pipe and one ALU-pipe instruction per column; both pipes issue every other cycle)
         uint32_t c4[4] = {0u, 0u, 0u, 0u};
@@ -235,7 +274,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     const uint32_t ring_addr = base, a_addr = base + NSTAGE * Cfg::STAGE;
     unsigned char *sA = smem + (size_t)NSTAGE * Cfg::STAGE;
     float *s_xx = reinterpret_cast<float *>(sA + (size_t)NG * NABUF * Cfg::AIMG);      // [NG][2][128]
-    float *s_min = s_xx + NG * 2 * 128;                                                 // [NG][2][half][128]
+    float *s_min = s_xx + NG * 2 * 128;                                                 // [NG][2][half][128]  (running U of the half)
     int *s_nc = reinterpret_cast<int *>(s_min + NG * 2 * 2 * 128);                      // [NG][2][half][128]  (-1: overflow)
     float *s_seen = reinterpret_cast<float *>(s_nc + NG * 2 * 2 * 128);                 // [NG][2][half][kVqtMaxCand][128]
     unsigned short *s_cand = reinterpret_cast<unsigned short *>(s_seen + NG * 2 * 2 * kVqtMaxCand * 128);   // same shape
@@ -320,7 +359,6 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
         // ===== sweep warps =====
         const int g = ((warp - Cfg::SWEEP_WARP0) >> 2) & 1, half = (warp - Cfg::SWEEP_WARP0) >> 3, q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const float cmax = __ldg(p.cmax);
         constexpr int HC = NT / 2;           // columns per half
         VqtSweep sw;
         uint32_t u = 0;
@@ -331,9 +369,8 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             const float xx = s_xx[(g * 2 + rb) * 128 + row];
             __syncwarp();
             if (lane == 0) mbarrier_arrive(&a_empty[g][ab]);
-            // |tensor-core score - exact score| <= 2^-8 (1 + 2^-9) (||x||^2 + ||e_k||^2) (bf16 operands, fp32 accumulation), so
-            // the reference's argmin is among the columns within twice that of the row minimum
-            sw.margin = 0.00785f * (xx + cmax) + 1e-30f;
+            const float xnorm = sqrtf(xx);
+            sw.u_run = __int_as_float(0x7f800000);
             sw.m_run = __int_as_float(0x7f800000);
             sw.m_push = __int_as_float(0x7f800000);
             sw.nc = 0;
@@ -346,6 +383,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_addr = tmem_d + lane_sel + (uint32_t)((g * 2 + (int)(u & 1u)) * NT + half * HC);
                 const int col0 = t * NT + half * HC;
+                sw.hm = vqt_half_margin(xnorm, xx, __ldg(p.tnorm + t));
                 // ping-pong over the 16-column groups: the next group's tcgen05.ld is in flight while this one is scanned
                 uint32_t ra[16], rb16[16];
                 tmem_ld16_async(d_addr, ra);
@@ -363,7 +401,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 __syncwarp();
                 if (lane == 0) mbarrier_arrive(&d_empty[g][u & 1u]);
             }
-            s_min[slot_res * 128 + row] = sw.m_run;
+            s_min[slot_res * 128 + row] = sw.u_run;
             s_nc[slot_res * 128 + row] = sw.ovf ? -1 : sw.nc;
             __syncwarp();
             if (lane == 0) mbarrier_arrive(&r_full[g][rb]);
@@ -371,9 +409,12 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     } else if (warp >= Cfg::LE_WARP0) {
         // ===== load / epilogue warps =====
         const int g = (warp - Cfg::LE_WARP0) >> 2, q = warp & 3, row = q * 32 + lane;
-        const float cmax = __ldg(p.cmax);
         const bool want_stats = p.counts != nullptr;
+        #ifdef VQ3D_VQT_SCALAR_RED
+        const bool dw_vec = false;
+#else
         const bool dw_vec = (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
+#endif
         auto locate = [&](int i, int64_t &b, int64_t &s) -> bool {
             const int64_t sup = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
             const int64_t v = (sup * NG + g) * 128 + row;
@@ -424,8 +465,14 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             mbarrier_wait(&r_full[g][rb], ((uint32_t)i >> 1) & 1u);
             // merge the two half-row lists: final minimum, then the entries that can still be within margin of it
             const int res0 = (g * 2 + rb) * 2;
-            const float m_fin = fminf(s_min[res0 * 128 + row], s_min[(res0 + 1) * 128 + row]);
-            const float thr_fin = m_fin + (0.00785f * (s_xx[(g * 2 + rb) * 128 + row] + cmax) + 1e-30f);
+            const float u_fin = fminf(s_min[res0 * 128 + row], s_min[(res0 + 1) * 128 + row]);
+            const float xx_row = s_xx[(g * 2 + rb) * 128 + row], xnorm_row = sqrtf(xx_row);
+            // entry (h, c) can still hold the reference's argmin: its score lower bound is within its tile's half margin of U
+            auto kept = [&](int h, int c) -> bool {
+                const int col = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
+                return s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <=
+                       u_fin + vqt_half_margin(xnorm_row, xx_row, __ldg(p.tnorm + col / NT));
+            };
             int nc = 0, k_one = 0x7fffffff;
             bool ovf = false;
 #pragma unroll
@@ -433,7 +480,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 const int nh = s_nc[(res0 + h) * 128 + row];
                 ovf |= nh < 0;
                 for (int c = 0; c < nh; ++c)
-                    if (s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <= thr_fin) {
+                    if (kept(h, c)) {
                         ++nc;
                         k_one = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
                     }
@@ -443,12 +490,12 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             if (active) {
 #ifdef VQ3D_VQT_DEBUG
                 {
-                    unsigned *dbg = reinterpret_cast<unsigned *>(const_cast<float *>(p.cmax)) + 4;
+                    unsigned *dbg = const_cast<unsigned *>(p.dbg);
                     atomicAdd(dbg + (ovf ? 3 : (nc == 1 ? 0 : (nc >= 2 ? 1 : 2))), 1u);
                     if (nc >= 2) atomicAdd(dbg + 4, (unsigned)nc);
                 }
 #endif
-                if (!ovf && nc == 1 && k_one < p.K) best_k = k_one;      // alone within the error bound: it IS the reference's argmin
+                if (!ovf && nc == 1 && k_one < p.K) best_k = __ldg(p.perm + k_one);      // alone within the error bound: it IS the reference's argmin
             }
             // exact re-rank of the vectors with several candidates, densely packed over the warp: the (vector, code) pairs
             // go through a 64-entry queue, every lane evaluates one pair per round with the reference's arithmetic, the
@@ -475,10 +522,11 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                         // next kept entry of this row's two lists
                         for (;; ++cursor) {
                             const int h = cursor / kVqtMaxCand, c = cursor % kVqtMaxCand;
-                            if (c < s_nc[(res0 + h) * 128 + row] && s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <= thr_fin) break;
+                            if (c < s_nc[(res0 + h) * 128 + row] && kept(h, c)) break;
                         }
                         const int h = cursor / kVqtMaxCand, c = cursor % kVqtMaxCand;
-                        q_key[excl + j] = (uint32_t)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] | ((uint32_t)lane << 16);
+                        const int col = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
+                        q_key[excl + j] = (uint32_t)(col < p.K ? __ldg(p.perm + col) : 0xffff) | ((uint32_t)lane << 16);
                         ++cursor;
                     }
                     __syncwarp();
@@ -581,11 +629,15 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     }
 }
 
+// workspace: [0, 256) header (debug counters), ||e||^2 [Kpad], column -> code [Kpad], per-tile largest norm [ntiles], then
+// the tile images (256-byte aligned)
+static size_t vqt_ws_tables(int Kpad, int ntiles) { return (256 + (size_t)Kpad * 8 + (size_t)ntiles * 4 + 255) / 256 * 256; }
+
 template <int D>
 static size_t vqt_ws_bytes(int K) {
     using Cfg = VqtCfg<D>;
     const int Kpad = (K + Cfg::NT - 1) / Cfg::NT * Cfg::NT;
-    return 256 + (size_t)(Kpad / Cfg::NT) * Cfg::STAGE;
+    return vqt_ws_tables(Kpad, Kpad / Cfg::NT) + (size_t)(Kpad / Cfg::NT) * Cfg::STAGE;
 }
 
 template <int D>
@@ -594,19 +646,26 @@ static int launch_vqt(const float *x, const float *embed, int64_t B, int64_t S, 
     using Cfg = VqtCfg<D>;
     if (ws_size < vqt_ws_bytes<D>(K) || (reinterpret_cast<uintptr_t>(ws) & 255) != 0)
         return fail(VQ3D_ERR_INVALID, "vq_assign_tc: workspace too small or not 256-byte aligned");
-    if (K > 65535) return fail(VQ3D_ERR_UNSUPPORTED, "vq_assign_tc: K > 65535");
+    if (K > 16384) return fail(VQ3D_ERR_UNSUPPORTED, "vq_assign_tc: K > 16384");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VqtParams p;
     p.x = x; p.embed = embed; p.B = B; p.S = S; p.K = K;
     p.Kpad = (K + Cfg::NT - 1) / Cfg::NT * Cfg::NT;
+    const int ntiles = p.Kpad / Cfg::NT;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    p.cmax = reinterpret_cast<float *>(wsb);
-    p.wimg = wsb + 256;
+    float *cnorm = reinterpret_cast<float *>(wsb + 256);
+    int *perm = reinterpret_cast<int *>(cnorm + p.Kpad);
+    float *tnorm = reinterpret_cast<float *>(perm + p.Kpad);
+    unsigned char *wimg = wsb + vqt_ws_tables(p.Kpad, ntiles);
+    p.dbg = reinterpret_cast<const unsigned *>(wsb + 16);
+    p.perm = perm; p.tnorm = tnorm; p.wimg = wimg;
     p.quant = quant; p.idx = idx; p.sqerr = sqerr; p.counts = counts; p.dw = dw;
     p.tmem_cols = 512;                                                   // NG groups x 2 accumulators x NT columns
     cudaError_t e = cudaMemsetAsync(wsb, 0, 256, st);
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(memset)");
-    vqt_prep_kernel<D><<<(unsigned)ceil_div((int64_t)p.Kpad * Cfg::KC, 256), 256, 0, st>>>(embed, K, p.Kpad, wsb + 256, reinterpret_cast<float *>(wsb));
+    vqt_norm_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(embed, K, D, cnorm);
+    vqt_rank_kernel<<<(unsigned)ceil_div(p.Kpad, 256), 256, 0, st>>>(cnorm, K, p.Kpad, perm);
+    vqt_prep_kernel<D><<<(unsigned)ceil_div((int64_t)p.Kpad * Cfg::KC, 256), 256, 0, st>>>(embed, cnorm, perm, K, p.Kpad, wimg, tnorm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(prep)");
     auto kernel = vq_tc_kernel<D>;
@@ -631,7 +690,7 @@ extern "C" size_t vq3d_vq_assign_tc_workspace(int D, int K) {
     (void)D; (void)K;
     return 0;
 #else
-    if (K < 1 || K > 65535) return 0;
+    if (K < 1 || K > 16384) return 0;
     switch (D) {
         case 32: return vqt_ws_bytes<32>(K);
         case 64: return vqt_ws_bytes<64>(K);

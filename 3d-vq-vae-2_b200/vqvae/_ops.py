@@ -107,7 +107,7 @@ class Ops:
                 ws = self._workspace(need, x.device)
                 if self._call("vq_assign_tc", self.lib.vq3d_vq_assign_tc,
                               (self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx), self._p(sqerr), self._p(counts),
-                               self._p(dw), self._p(ws), ws.numel(), self.stream()), kernels=2, allow_unsupported=True, **meta):
+                               self._p(dw), self._p(ws), ws.numel(), self.stream()), kernels=4, allow_unsupported=True, **meta):
                     return quant, idx, sqerr, stats
         self._call("vq_assign", self.lib.vq3d_vq_assign,
                    (self._p(x), self._p(embed), B, D, S, K, self._p(quant), self._p(idx), self._p(sqerr), self._p(counts),
