@@ -274,6 +274,15 @@ adam_amsgrad_kernel(float *__restrict__ p, const float *__restrict__ g, float *_
     }
 }
 
+// trailing ELU from its output: d ELU(u) / d u = 1 (u > 0), exp(u) = y + 1 (u <= 0)
+__global__ void __launch_bounds__(256)
+elu_backward_kernel(const float *__restrict__ gy, const float *__restrict__ y, float *__restrict__ gx, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float yv = y[i];
+        gx[i] = yv > 0.0f ? gy[i] : gy[i] * (yv + 1.0f);
+    }
+}
+
 }  // namespace vq3d
 
 using namespace vq3d;
@@ -335,6 +344,14 @@ extern "C" int vq3d_huber_elu_mask_backward(const float *decoded, const float *x
     if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
     return launch("huber_elu_mask_bwd", huber_elu_mask_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x, (const int *)num_valid,
                   mask_hw, B, H * W, Z, count, grad_loss, grad_decoded);
+}
+
+extern "C" int vq3d_elu_backward(const float *gy, const float *y, float *gx, int64_t n, void *stream) {
+    if (!gy || !y || !gx || n < 0) return fail(VQ3D_ERR_INVALID, "elu_backward: bad arguments");
+    if (n == 0) return VQ3D_OK;
+    int64_t blocks = ceil_div(n, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return launch("elu_backward", elu_backward_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, gy, y, gx, n);
 }
 
 extern "C" int vq3d_adam_amsgrad_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t n,

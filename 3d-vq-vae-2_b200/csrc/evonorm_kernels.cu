@@ -58,9 +58,76 @@ evonorm_apply_kernel(const float *__restrict__ x, const float *__restrict__ v, c
     }
 }
 
+// grid (chunks, C): per-channel sums for the backward (double accumulation)
+__global__ void __launch_bounds__(256)
+evonorm_bwd_sums_kernel(const float *__restrict__ x, const float *__restrict__ gy, const float *__restrict__ v, int64_t S,
+                        double *__restrict__ sums) {
+    __shared__ double red[3][32];
+    const int c = blockIdx.y;
+    const float vc = __ldg(v + c);
+    const float *px = x + (size_t)c * S, *pg = gy + (size_t)c * S;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+        const float xv = px[i], g = pg[i];
+        const float sig = 1.0f / (1.0f + __expf(-xv * vc));
+        s0 += (double)g;
+        s1 += (double)(g * xv * sig);
+        s2 += (double)(g * xv * xv * sig * (1.0f - sig));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0, d = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; d += red[2][w]; }
+        atomicAdd(&sums[3 * c], a);
+        atomicAdd(&sums[3 * c + 1], b);
+        atomicAdd(&sums[3 * c + 2], d);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+evonorm_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ gy, const float *__restrict__ v,
+                         const float *__restrict__ coef_a, const float *__restrict__ coef_b, const float *__restrict__ mean,
+                         int64_t S, float *__restrict__ gx) {
+    const int c = blockIdx.y;
+    const float vc = __ldg(v + c), ca = __ldg(coef_a + c), cb = __ldg(coef_b + c), mu = __ldg(mean + c);
+    const float *px = x + (size_t)c * S, *pg = gy + (size_t)c * S;
+    float *po = gx + (size_t)c * S;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+        const float xv = px[i];
+        const float sig = 1.0f / (1.0f + __expf(-xv * vc));
+        po[i] = pg[i] * ca * (sig + xv * vc * sig * (1.0f - sig)) + cb * (xv - mu);      // evonorm.py:41-44 + the group-std term
+    }
+}
+
 }  // namespace vq3d
 
 using namespace vq3d;
+
+extern "C" int vq3d_evonorm_s0_backward_sums(const float *x, const float *gy, const float *v, int C, int64_t S, double *sums, void *stream) {
+    if (!x || !gy || !v || !sums || C < 1 || C > 65535 || S < 1) return fail(VQ3D_ERR_INVALID, "evonorm_s0_backward_sums: bad arguments");
+    int rc = check_cuda(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * C, (cudaStream_t)stream), "evonorm_s0_backward_sums memset");
+    if (rc) return rc;
+    int64_t chunks = ceil_div(S, 256 * 16);
+    if (chunks > 1024) chunks = 1024;
+    return launch("evonorm_bwd_sums", evonorm_bwd_sums_kernel, dim3((unsigned)chunks, (unsigned)C), dim3(256), 0, stream, x, gy, v, S, sums);
+}
+
+extern "C" int vq3d_evonorm_s0_backward_apply(const float *x, const float *gy, const float *v, const float *coef_a, const float *coef_b,
+                                              const float *mean, int C, int64_t S, float *gx, void *stream) {
+    if (!x || !gy || !v || !coef_a || !coef_b || !mean || !gx || C < 1 || C > 65535 || S < 1)
+        return fail(VQ3D_ERR_INVALID, "evonorm_s0_backward_apply: bad arguments");
+    int64_t chunks = ceil_div(S, 256 * 4);
+    if (chunks > 4096) chunks = 4096;
+    return launch("evonorm_bwd_apply", evonorm_bwd_apply_kernel, dim3((unsigned)chunks, (unsigned)C), dim3(256), 0, stream,
+                  x, gy, v, coef_a, coef_b, mean, S, gx);
+}
 
 extern "C" int vq3d_evonorm_s0_stats(const float *x, int C, int64_t S, int groups, double eps, double *scratch, float *std_out, void *stream) {
     if (!x || !scratch || !std_out || C < 1 || S < 1 || groups < 1 || C % groups != 0) return fail(VQ3D_ERR_INVALID, "evonorm_s0_stats: bad arguments");

@@ -6,6 +6,7 @@ libvqvae3d_b200.so.  Every wrapper insists on CUDA fp32 tensors -- there is no f
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -26,6 +27,7 @@ class Ops:
         self.precision = "bf16"
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
+        self.tc_min_voxels = int(os.environ.get("VQ3D_TC_MIN_VOXELS", "0"))   # convs with fewer output voxels stay on the fp32 SIMT kernel
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
 
@@ -169,9 +171,8 @@ class Ops:
         autograd is recording and an input requires grad, the backward is vq3d_conv3d_backward."""
         tensors = (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual)
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-            if post_act:
-                raise NotImplementedError("3d-vq-vae-2_b200: the trailing ELU of FixupResBlock has no backward in this build")
-            return _ConvFn.apply(self, dict(stride=stride, pad=pad, circular=circular, pre_act=pre_act), *tensors)
+            # post_act = FixupResBlock's trailing ELU (layers.py:288-289): fused in the forward kernel, undone first in backward
+            return _ConvFn.apply(self, dict(stride=stride, pad=pad, circular=circular, pre_act=pre_act, post_act=post_act), *tensors)
         return self._conv3d_fwd(x1, w, x2=x2, bias=bias, stride=stride, pad=pad, circular=circular, pre_act=pre_act, pre_a=pre_a,
                                 pre_b=pre_b, post_scale=post_scale, post_b=post_b, residual=residual, post_act=post_act)
 
@@ -233,7 +234,7 @@ class Ops:
         so = y[0, 0].numel()
         meta = dict(nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
                     flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
-        if self.precision == "bf16" and not force_fp32 and Cout >= 8 and Cin * k ** 3 >= 32:
+        if self.precision == "bf16" and not force_fp32 and Cout >= 8 and Cin * k ** 3 >= 32 and B * so >= self.tc_min_voxels:
             need = self.lib.vq3d_conv3d_tc_workspace(C.byref(d))       # > 0: few voxels, long K -> split-K through a workspace
             ws = self._workspace(need, x1.device) if need else None
             if self._call("conv3d_tc", self.lib.vq3d_conv3d_tc, (C.byref(d), self._p(ws), need, self.stream()),
@@ -354,9 +355,22 @@ class Ops:
                         kernels=n, **meta)
         return res if ok else None
 
+    def elu_backward(self, gy: Tensor, y: Tensor) -> Tensor:
+        gy, y = self._t(gy), self._t(y)
+        gx = torch.empty_like(gy)
+        self._call("elu_backward", self.lib.vq3d_elu_backward, (self._p(gy), self._p(y), self._p(gx), gy.numel(), self.stream()),
+                   nbytes=12 * gy.numel())
+        return gx
+
     def evonorm_s0(self, x: Tensor, v: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
-        """EvoNorm3D-S0 forward (evonorm.py:70-76), batch 1 like the reference."""
-        x = self._t(x)
+        """EvoNorm3D-S0 (evonorm.py:70-76), batch 1 like the reference; differentiable (x, v, gamma, beta)."""
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, v, gamma, beta)):
+            return _EvoNormFn.apply(self, float(eps), x, v, gamma, beta)
+        return self._evonorm_s0_fwd(x, v, gamma, beta, eps)[0]
+
+    def _evonorm_s0_fwd(self, x: Tensor, v: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5):
+        """-> (y, std [C], group sums scratch [2 * groups] doubles)."""
+        x = self._t(x.detach())
         B, Cc = x.shape[0], x.shape[1]
         if B != 1:
             raise RuntimeError("EvoNorm3DS0 supports batch size 1 only (as the reference, evonorm.py:24)")
@@ -370,7 +384,35 @@ class Ops:
         flat = lambda t: self._p(self._t(t.detach().reshape(-1)))
         self._call("evonorm_s0_apply", self.lib.vq3d_evonorm_s0_apply,
                    (self._p(x), flat(v), flat(gamma), flat(beta), self._p(std), Cc, S, self._p(y), self.stream()), nbytes=8 * x.numel())
-        return y
+        return y, std, scratch
+
+    def evonorm_s0_backward(self, gy: Tensor, x: Tensor, v: Tensor, gamma: Tensor, std: Tensor, scratch: Tensor):
+        """Gradients of EvoNorm3D-S0 wrt (x, v, gamma, beta): two kernels (per-channel sums, elementwise dx) around the
+        C-sized algebra (evonorm.py:12-26,36-47 differentiated by hand; batch 1)."""
+        x, gy = self._t(x.detach()), self._t(gy)
+        Cc = x.shape[1]
+        S = x[0, 0].numel()
+        groups = max(Cc // 8, 1)
+        cpg = Cc // groups
+        n = float(cpg * S)
+        vf, gf = self._t(v.detach().reshape(-1)), self._t(gamma.detach().reshape(-1))
+        sums = torch.empty(3 * Cc, dtype=torch.float64, device=x.device)
+        self._call("evonorm_s0_backward_sums", self.lib.vq3d_evonorm_s0_backward_sums,
+                   (self._p(x), self._p(gy), self._p(vf), Cc, S, self._p(sums), self.stream()), kernels=2, nbytes=8 * x.numel())
+        sums = sums.view(Cc, 3)
+        inv = 1.0 / std.double()                                              # per channel (equal within a group)
+        g_beta = sums[:, 0]
+        g_gamma = sums[:, 1] * inv
+        g_v = sums[:, 2] * gf.double() * inv
+        a_grp = (sums[:, 1] * gf.double()).view(groups, cpg).sum(1).repeat_interleave(cpg)   # d loss / d (1 / std_g)
+        coef_a = (gf.double() * inv).float().contiguous()
+        coef_b = (-a_grp * inv ** 3 / (n - 1.0)).float().contiguous()
+        mean = (scratch.view(groups, 2)[:, 0] / n).repeat_interleave(cpg).float().contiguous()
+        gx = torch.empty_like(x)
+        self._call("evonorm_s0_backward_apply", self.lib.vq3d_evonorm_s0_backward_apply,
+                   (self._p(x), self._p(gy), self._p(vf), self._p(coef_a), self._p(coef_b), self._p(mean), Cc, S, self._p(gx),
+                    self.stream()), nbytes=12 * x.numel())
+        return gx, g_v.float().view_as(v), g_gamma.float().view_as(gamma), g_beta.float().view_as(gamma)
 
     def huber_loss(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]) -> Tensor:
         """mean smooth_l1(mask(ELU(decoded)), x) as a 0-d fp32 tensor (model.py:120-152); differentiable wrt decoded."""
@@ -412,14 +454,16 @@ class _ConvFn(torch.autograd.Function):
     def forward(ctx, ops, cfg, x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual):
         y = ops._conv3d_fwd(x1, w, x2=x2, bias=bias, pre_a=pre_a, pre_b=pre_b, post_scale=post_scale, post_b=post_b, residual=residual, **cfg)
         ctx.ops, ctx.cfg = ops, cfg
-        ctx.save_for_backward(x1, x2, w, pre_a, pre_b, post_scale, post_b)
+        ctx.save_for_backward(x1, x2, w, pre_a, pre_b, post_scale, post_b, y if cfg.get("post_act") else None)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x1, x2, w, pre_a, pre_b, post_scale, post_b = ctx.saved_tensors
+        x1, x2, w, pre_a, pre_b, post_scale, post_b, y_act = ctx.saved_tensors
         n = ctx.needs_input_grad      # (ops, cfg, x1, x2, w, bias, pre_a, pre_b, post_scale, post_b, residual)
+        if y_act is not None:         # trailing ELU: everything below sees the gradient wrt its input
+            gy = ctx.ops.elu_backward(gy.contiguous(), y_act)
         need = dict(x1=n[2], x2=n[3] and x2 is not None, w=n[4], bias=n[5] and ctx.has_bias, pre_a=n[6] and pre_a is not None,
                     pre_b=n[7] and pre_b is not None, post_scale=n[8] and post_scale is not None, post_b=n[9] and post_b is not None)
         gy = gy.contiguous()
@@ -427,6 +471,22 @@ class _ConvFn(torch.autograd.Function):
         pick = lambda flag, i: gs[i:i + 1].clone() if flag else None
         return (None, None, gx1, gx2, gw, gbias, pick(need["pre_a"], 0), pick(need["pre_b"], 1), pick(need["post_scale"], 2),
                 pick(need["post_b"], 3), gy if (ctx.has_res and n[10]) else None)
+
+
+class _EvoNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ops, eps, x, v, gamma, beta):
+        y, std, scratch = ops._evonorm_s0_fwd(x, v, gamma, beta, eps)
+        ctx.ops = ops
+        ctx.save_for_backward(x, v, gamma, std, scratch)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, v, gamma, std, scratch = ctx.saved_tensors
+        gx, gv, gg, gb = ctx.ops.evonorm_s0_backward(gy.contiguous(), x, v, gamma, std, scratch)
+        n = ctx.needs_input_grad
+        return None, None, gx if n[2] else None, gv if n[3] else None, gg if n[4] else None, gb if n[5] else None
 
 
 class _UpsampleFn(torch.autograd.Function):

@@ -2,7 +2,7 @@
 
 Parameter names/shapes (v, gamma, beta: (C, 1, 1, 1); v=1, gamma=0, beta=0) match the
 reference so checkpoints load.  Forward = two kernels of libvqvae3d_b200 (group statistics in double,
-then the elementwise SiLU-velocity / normalise / affine), csrc/evonorm_kernels.cu; no backward yet."""
+then the elementwise SiLU-velocity / normalise / affine) and its hand-derived backward, csrc/evonorm_kernels.cu."""
 import torch
 from torch import nn
 
@@ -20,7 +20,5 @@ class EvoNorm3DS0(nn.Module):
 
     def forward(self, x):
         assert x.dim() == 5
-        if torch.is_grad_enabled() and (x.requires_grad or self.v.requires_grad):
-            raise NotImplementedError("3d-vq-vae-2_b200: EvoNorm3DS0 backward is not part of this build; use torch.no_grad()")
         from . import _ops
         return _ops.default().evonorm_s0(x, self.v, self.gamma, self.beta)

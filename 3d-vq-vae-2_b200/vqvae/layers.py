@@ -29,14 +29,6 @@ def ops() -> "_ops.Ops":
     return _ops.default()
 
 
-def _no_conv_backward(*params) -> None:
-    """Blocks without backward kernels (FixupResBlock's trailing ELU, EvoNorm) refuse to record a graph."""
-    if torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params):
-        raise NotImplementedError(
-            "3d-vq-vae-2_b200: this block type has no backward kernels in this build (pre-activation blocks, 1x1 "
-            "convolutions, the quantizer and the Huber epilogue do); run it under torch.no_grad()")
-
-
 def _recording(x, *params) -> bool:
     """True when autograd is recording and something upstream wants a gradient: the fused inference kernels
     (one launch per block / stack) are bypassed and the block is composed from the differentiable generic ops."""
@@ -172,7 +164,6 @@ class FixupResBlock(nn.Module):
         self.branch_conv2 = Conv3d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=False)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        _no_conv_backward(*self.parameters())
         o = ops()
         stride = 2 if self.mode == "down" else 1
         if self.mode == "up":
@@ -219,7 +210,6 @@ class EvonormResBlock(nn.Module):
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         """layers.py:84-91: conv1(EN1(x)) -> conv2(EN2(.)) -> conv3(EN3(.)) + (skip(x) | x); zero padding, conv biases."""
-        _no_conv_backward(*self.parameters())
         o = ops()
         stride = 2 if self.mode == "down" else 1
         t = o.conv3d(self.evonorm_1(input), self.branch_conv1.weight, bias=self.branch_conv1.bias)

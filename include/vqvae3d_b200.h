@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 8
+#define VQ3D_ABI_VERSION 9
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -177,6 +177,10 @@ int vq3d_huber_elu_mask_backward(const float *decoded, const float *x, const int
                                  int64_t B, int H, int W, int Z, const double *count, const float *grad_loss,
                                  float *grad_decoded, void *stream);
 
+/* Backward of a trailing ELU given its OUTPUT y (FixupResBlock's last activation, vqvae/layers.py:288-289):
+ * gx = gy * (y > 0 ? 1 : y + 1), n elements. */
+int vq3d_elu_backward(const float *gy, const float *y, float *gx, int64_t n, void *stream);
+
 /* One Adam(amsgrad=True) step on a flat fp32 tensor (model.py:91-93; torch.optim.Adam defaults otherwise). step >= 1. */
 int vq3d_adam_amsgrad_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t n,
                            double lr, double beta1, double beta2, double eps, int64_t step, void *stream);
@@ -258,6 +262,17 @@ int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void *ws, size_t
 int vq3d_evonorm_s0_stats(const float *x, int C, int64_t S, int groups, double eps, double *scratch, float *std_out, void *stream);
 int vq3d_evonorm_s0_apply(const float *x, const float *v, const float *gamma, const float *beta, const float *std_in,
                           int C, int64_t S, float *y, void *stream);
+
+/*
+ * Backward of EvoNorm3D-S0 (autograd of evonorm.py:12-26,59-76 incl. SiLUVelocityFunc.backward :36-47), batch 1, x/gy/gx [C, S].
+ * _sums: per channel c the doubles sums[3c..3c+2] = sum(gy), sum(gy * x sigmoid(v x)), sum(gy * x^2 s (1 - s)) (caller need
+ * not zero them).  The C-sized algebra in between (d gamma, d beta, d v, the group coefficients) is host code.
+ * _apply: gx = gy * coef_a[c] * (s + x v s (1 - s)) + coef_b[c] * (x - mean[c]), with coef_a = gamma / std,
+ * coef_b = -(sum over the group of gamma * sums[3c+1]) / (std^3 (n - 1)), mean = the group mean.
+ */
+int vq3d_evonorm_s0_backward_sums(const float *x, const float *gy, const float *v, int C, int64_t S, double *sums, void *stream);
+int vq3d_evonorm_s0_backward_apply(const float *x, const float *gy, const float *v, const float *coef_a, const float *coef_b,
+                                   const float *mean, int C, int64_t S, float *gx, void *stream);
 
 /*
  * Loss epilogue of VQVAE.loc_metric, model.py:120-152, fused: loc = ELU(decoded), zero where

@@ -86,3 +86,62 @@ def test_tiny_model_training_step_gradients_vs_oracle():
         scale = float(ref.abs().max()) + 1e-6
         worst = max(worst, err / scale)
         assert err <= 2e-3 * scale + 1e-6, (k, err, scale)
+
+
+def _grads_vs_oracle(blk, oracle_fn, mode, x, seed, tol=5e-4):
+    """Gradients of sum(block(x) * r) wrt x and every parameter: emulator kernels vs torch.autograd on the oracle."""
+    with use_emulator():
+        xg = x.clone().requires_grad_(True)
+        y = blk(xg)
+        r = torch.randn(y.shape, generator=torch.Generator().manual_seed(seed))
+        (y * r).sum().backward()
+        got_dx = xg.grad.clone()
+        got = {k: p.grad.clone() for k, p in blk.named_parameters()}
+    sd = {"b." + k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    yr = oracle_fn(sd, "b.", xr, mode)
+    assert torch.allclose(y.detach(), yr.detach(), rtol=1e-4, atol=1e-5)
+    (yr * r).sum().backward()
+    assert torch.allclose(got_dx, xr.grad, rtol=tol, atol=tol * 0.1 * float(xr.grad.abs().max())), float((got_dx - xr.grad).abs().max())
+    for k, g in got.items():
+        ref = sd["b." + k].grad
+        assert ref is not None, k
+        assert float((g - ref).abs().max()) <= tol * float(ref.abs().max()) + 1e-6, (k, float((g - ref).abs().max()), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("cin,cout,mode,shape", [
+    (3, 5, "same", (1, 3, 4, 5, 4)),
+    (4, 6, "down", (1, 4, 6, 4, 8)),
+    (6, 3, "up", (1, 6, 3, 4, 2)),
+    (4, 2, "out", (2, 4, 3, 4, 5)),        # no trailing ELU, batch 2
+])
+def test_fixup_block_gradients_vs_oracle_autograd(cin, cout, mode, shape):
+    """FixupResBlock (`--block-type regular`, layers.py:219-303) incl. the trailing ELU's backward."""
+    torch.manual_seed(cin * 7 + cout)
+    blk = L.FixupResBlock(cin, cout, mode)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        blk.scale.fill_(0.9)
+    _grads_vs_oracle(blk, O.fixup_block, mode, torch.randn(shape), 5)
+
+
+@pytest.mark.parametrize("cin,cout,mode,shape", [
+    (8, 8, "same", (1, 8, 4, 5, 4)),        # one group, no skip conv
+    (16, 8, "same", (1, 16, 3, 4, 4)),      # two groups, skip conv
+    (8, 16, "down", (1, 8, 4, 4, 6)),
+    (16, 8, "up", (1, 16, 2, 3, 2)),
+])
+def test_evonorm_block_gradients_vs_oracle_autograd(cin, cout, mode, shape):
+    """EvonormResBlock / EvoNorm3DS0 backward (evonorm.py:12-47,59-76 under autograd)."""
+    torch.manual_seed(cin * 3 + cout)
+    blk = L.EvonormResBlock(cin, cout, mode)
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if n.endswith(".gamma"):
+                p.copy_(1.0 + 0.2 * torch.randn(p.shape))       # reference init gamma = 0 would zero every branch gradient
+            elif n.endswith(".v") or n.endswith(".beta"):
+                p.add_(0.2 * torch.randn(p.shape))
+            else:
+                p.copy_(torch.randn(p.shape) * 0.3)
+    _grads_vs_oracle(blk, O.evonorm_block, mode, torch.randn(shape), 9, tol=2e-3)

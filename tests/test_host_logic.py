@@ -109,7 +109,7 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="CUDA tensors only"):       # the training path refuses CPU tensors as well
         blk(torch.zeros(1, 4, 2, 2, 2))
     reg = L.FixupResBlock(4, 4, "same")
-    with pytest.raises(NotImplementedError, match="backward"):          # block types without backward kernels say so
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):       # every block type trains through the CUDA kernels only
         reg(torch.zeros(1, 4, 2, 2, 2))
 
 
