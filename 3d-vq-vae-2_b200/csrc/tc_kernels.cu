@@ -35,8 +35,8 @@ struct TcParams {
     int B, H, W, Z, C1, C2, Cout, k, stride, pad, circ, pre_act, post_act;
     int Ho, Wo, Zo, Npad, Ktot, G;
     int nsplit, cps;                 // split-K: grid.y splits of cps K-chunks each (1 = no split)
-    float *ws;                       // split-K partial sums [tiles * 128][Npad] fp32 (zeroed by the host per call)
-    unsigned int *ws_cnt;            // split-K arrival counters [tiles]
+    float *ws;                       // split-K partial sums [nsplit][Npad][tiles * 128] fp32 (plain stores; reduced in a fixed
+                                     // order by conv3d_tc_reduce_kernel, so the result is bit-reproducible)
     const float *x1, *x2, *w, *bias, *pre_a, *pre_b, *post_scale, *post_b, *residual;
     float *y;
 };
@@ -225,11 +225,12 @@ conv3d_tc_kernel(TcParams p) {
                          : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (ok) {
-                if (p.nsplit > 1) {        // partial sums of this K slice -> workspace
-                    float *wrow = p.ws + (size_t)vr * Npad + c0;
+                if (p.nsplit > 1) {        // partial sums of this K slice -> its own workspace slab, [column][voxel] (coalesced)
+                    const size_t rows = (size_t)gridDim.x * kTcM;
+                    float *wcol = p.ws + ((size_t)blockIdx.y * Npad + c0) * rows + vr;
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        if (c0 + e < p.Cout) atomicAdd(wrow + e, __uint_as_float(acc[e]));
+                        if (c0 + e < p.Cout) wcol[(size_t)e * rows] = __uint_as_float(acc[e]);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -246,52 +247,40 @@ conv3d_tc_kernel(TcParams p) {
                 }
             }
         }
-        if (p.nsplit > 1) {
-            // the CTA that arrives last for this M tile owns the output transform
-            __shared__ unsigned int s_ticket;
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) s_ticket = atomicAdd(p.ws_cnt + blockIdx.x, 1u);
-            __syncthreads();
-            if (s_ticket == (unsigned int)p.nsplit - 1) {
-                __threadfence();
-                const int64_t v2 = (int64_t)blockIdx.x * kTcM + r;
-                if (v2 < total) {
-                    const int b2 = (int)(v2 / So);
-                    const int64_t rem2 = v2 - (int64_t)b2 * So;
-                    // eight output channels per step: the loads of a step are issued together (the loop is a latency chain otherwise)
-                    for (int co0 = g; co0 < p.Cout; co0 += 8 * G) {
-                        float acc8[8], res8[8], bias8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int co = co0 + j * G;
-                            const bool in = co < p.Cout;
-                            const size_t o = ((size_t)b2 * p.Cout + (in ? co : 0)) * So + rem2;
-                            acc8[j] = in ? __ldcg(p.ws + (size_t)v2 * Npad + co) : 0.0f;
-                            res8[j] = (in && p.residual) ? __ldg(p.residual + o) : 0.0f;
-                            bias8[j] = (in && p.bias) ? __ldg(p.bias + co) : 0.0f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int co = co0 + j * G;
-                            if (co < p.Cout) {
-                                float yv = __fmaf_rn(acc8[j], sc, sbias);
-                                if (p.bias) yv += bias8[j];
-                                if (p.residual) yv += res8[j];
-                                if (p.post_act) yv = elu1(yv);
-                                p.y[((size_t)b2 * p.Cout + co) * So + rem2] = yv;
-                            }
-                        }
-                    }
-                }
-            }
-        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
     }
+}
+
+// split-K reduction + output transform: thread = (voxel, output channel); the nsplit partial sums are added in slice
+// order (deterministic), then *scale + b + bias + residual (+ELU) exactly like the unsplit epilogue
+__global__ void __launch_bounds__(256)
+conv3d_tc_reduce_kernel(TcParams p, int64_t rows) {
+    const int64_t So = (int64_t)p.Ho * p.Wo * p.Zo, total = (int64_t)p.B * So;
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int co = blockIdx.y;
+    if (v >= total) return;
+    const float *src = p.ws + (size_t)co * rows + v;
+    const size_t slab = (size_t)p.Npad * rows;
+    float acc = 0.0f;
+    int s = 0;
+    for (; s + 4 <= p.nsplit; s += 4) {
+        const float a0 = __ldcg(src + (size_t)s * slab), a1 = __ldcg(src + (size_t)(s + 1) * slab),
+                    a2 = __ldcg(src + (size_t)(s + 2) * slab), a3 = __ldcg(src + (size_t)(s + 3) * slab);
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a0), a1), a2), a3);
+    }
+    for (; s < p.nsplit; ++s) acc = __fadd_rn(acc, __ldcg(src + (size_t)s * slab));
+    const int b = (int)(v / So);
+    const int64_t rem = v - (int64_t)b * So;
+    const size_t o = ((size_t)b * p.Cout + co) * So + rem;
+    float yv = __fmaf_rn(acc, ld_scalar(p.post_scale, 1.f), ld_scalar(p.post_b, 0.f));
+    if (p.bias) yv += __ldg(p.bias + co);
+    if (p.residual) yv += __ldg(p.residual + o);
+    if (p.post_act) yv = elu1(yv);
+    p.y[o] = yv;
 }
 
 }  // namespace vq3d
@@ -329,7 +318,7 @@ extern "C" size_t vq3d_conv3d_tc_workspace(const vq3d_conv_desc *d) {
     tc_split_plan(d, &tiles, &ns, &cps);
     if (ns <= 1) return 0;
     const int Npad = (d->Cout + 15) & ~15;
-    return (size_t)tiles * kTcM * Npad * 4 + (size_t)((tiles * 4 + 255) & ~255);
+    return (size_t)ns * Npad * tiles * kTcM * 4;
 #endif
 }
 
@@ -361,21 +350,22 @@ extern "C" int vq3d_conv3d_tc(const vq3d_conv_desc *d, void *ws, size_t ws_bytes
     p.post_scale = d->post_scale; p.post_b = d->post_b; p.residual = d->residual; p.y = d->y;
     int64_t tiles;
     tc_split_plan(d, &tiles, &p.nsplit, &p.cps);
-    p.ws = nullptr; p.ws_cnt = nullptr;
+    p.ws = nullptr;
     if (p.nsplit > 1) {
         const size_t need = vq3d_conv3d_tc_workspace(d);
         if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) {       // no workspace: run unsplit
             p.nsplit = 1;
             p.cps = (int)ceil_div(Ktot, kTcBK);
         } else {
-            cudaError_t e = cudaMemsetAsync(ws, 0, need, static_cast<cudaStream_t>(stream));
-            if (e != cudaSuccess) return check_cuda(e, "conv3d_tc(memset)");
-            p.ws_cnt = static_cast<unsigned int *>(ws);
-            p.ws = reinterpret_cast<float *>(static_cast<unsigned char *>(ws) + ((tiles * 4 + 255) & ~255));
+            p.ws = static_cast<float *>(ws);
         }
     }
     p.G = tiles * p.nsplit >= 2 * kNumSMs ? 2 : 4;      // few CTAs: put more gather threads on each
     const size_t smem = (size_t)kTcStages * ((size_t)kTcM * kTcBK * 2 + (size_t)p.Npad * kTcBK * 2) + 256;
-    return launch("conv3d_tc", conv3d_tc_kernel, dim3((unsigned)tiles, (unsigned)p.nsplit), dim3((unsigned)(kTcM * p.G)), smem, stream, p);
+    int rc = launch("conv3d_tc", conv3d_tc_kernel, dim3((unsigned)tiles, (unsigned)p.nsplit), dim3((unsigned)(kTcM * p.G)), smem, stream, p);
+    if (rc || p.nsplit <= 1) return rc;
+    const int64_t total = (int64_t)p.B * p.Ho * p.Wo * p.Zo;
+    return launch("conv3d_tc_reduce", conv3d_tc_reduce_kernel, dim3((unsigned)ceil_div(total, 256), (unsigned)p.Cout), dim3(256), 0, stream,
+                  p, (int64_t)tiles * kTcM);
 #endif
 }

@@ -540,3 +540,26 @@ def test_pointwise_kernel_vs_torch(C1, C2, Cout, shape, pre_act, res):
     ref = torch.einsum("oc,bchwz->bohwz", w.double().flatten(1), xin.double()) * 0.9 + 0.02 + bias.double().view(1, -1, 1, 1, 1)
     ref = (ref + (r.double() if res else 0)).float()
     assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5), float((got - ref).abs().max())
+
+
+def test_batched_forward_equals_per_volume_forward():
+    """Volumes stacked along B (bench.py --batch) are processed independently: a batch-2 forward of the downscaled
+    model equals the two single-volume forwards (fp32 mode: bit-reproducible kernels, so indices must agree exactly)."""
+    from vqvae.model import VQVAE, downscaled_config_args
+    torch.manual_seed(42)
+    m = VQVAE(downscaled_config_args())
+    g = torch.Generator().manual_seed(43)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.02)
+        for q in m.encoder.quantize:
+            q.first_pass.fill_(0)
+    m = m.eval().to(DEV)
+    xs = [O.synthetic_volume((1, 1, 64, 64, 32), seed=s).to(DEV) for s in (1, 2)]
+    with torch.no_grad():
+        dec_b, (loss_b, _, idx_b) = m(torch.cat(xs))
+        singles = [m(x) for x in xs]
+    for i, (dec, (_, _, idx)) in enumerate(singles):
+        for lvl in range(len(idx)):
+            assert torch.equal(idx_b[lvl][i:i + 1], idx[lvl]), (i, lvl)
+        assert torch.allclose(dec_b[i:i + 1], dec, rtol=1e-5, atol=1e-5)

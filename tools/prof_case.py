@@ -40,6 +40,7 @@ def main():
     ap.add_argument("case", choices=sorted(CASES))
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--batch", type=int, default=1, help="volumes stacked along B (bench.py default: 8)")
     a = ap.parse_args()
     kind, cin, cout, mode, n, sp = CASES[a.case]
     dev = torch.device("cuda", 0)
@@ -59,7 +60,7 @@ def main():
         for p in m.parameters():
             p.add_(torch.randn_like(p) * 0.05)
     m = m.to(dev).eval()
-    x = torch.rand(1, cin, *sp, device=dev) * 2 - 0.5
+    x = torch.rand(a.batch, cin, *sp, device=dev) * 2 - 0.5
     with torch.no_grad():
         for _ in range(a.reps):
             y = m(x)
@@ -70,7 +71,7 @@ def main():
             y = m(x)
         e1.record()
         torch.cuda.synchronize()
-    print(f"{a.case}: {e0.elapsed_time(e1) / a.reps * 1e3:.1f} us per call ({n} block(s))")
+    print(f"{a.case}: {e0.elapsed_time(e1) / a.reps * 1e3:.1f} us per call ({n} block(s), batch {a.batch})")
 
 
 if __name__ == "__main__":
