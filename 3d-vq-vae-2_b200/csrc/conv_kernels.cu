@@ -263,6 +263,26 @@ huber_elu_mask_kernel(const float *__restrict__ dec, const float *__restrict__ x
 
 using namespace vq3d;
 
+namespace vq3d {
+// decode_embeddings.py:43-47 fused: HU = rint(ELU(decoded) * scale - offset) as int64 (np.rint: round half to even)
+__global__ void __launch_bounds__(256)
+elu_hu_rint_kernel(const float *__restrict__ x, int64_t n, float scale, float offset, int64_t *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __fsub_rn(__fmul_rn(elu1(x[i]), scale), offset);       // two roundings like the numpy expression
+        out[i] = (int64_t)rintf(v);
+    }
+}
+}  // namespace vq3d
+
+extern "C" int vq3d_elu_hu_rint(const float *decoded, int64_t n, double scale, double offset, int64_t *out, void *stream) {
+    if (!decoded || !out || n < 0) return vq3d::fail(VQ3D_ERR_INVALID, "elu_hu_rint: bad arguments");
+    if (n == 0) return VQ3D_OK;
+    int64_t blocks = vq3d::ceil_div(n, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return vq3d::launch("elu_hu_rint", vq3d::elu_hu_rint_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, n, (float)scale,
+                        (float)offset, out);
+}
+
 extern "C" int vq3d_abi_version(void) { return VQ3D_ABI_VERSION; }
 extern "C" const char *vq3d_last_error(void) { return err_buf(); }
 extern "C" int vq3d_is_cuda_build(void) {

@@ -414,6 +414,14 @@ class Ops:
                     self.stream()), nbytes=12 * x.numel())
         return gx, g_v.float().view_as(v), g_gamma.float().view_as(gamma), g_beta.float().view_as(gamma)
 
+    def elu_hu_rint(self, decoded: Tensor, scale: float = 1000.0, offset: float = 1000.0) -> Tensor:
+        """rint(ELU(decoded) * scale - offset) as int64: the Hounsfield-unit output of decode_embeddings.py:43-47."""
+        decoded = self._t(decoded.detach())
+        out = torch.empty(decoded.shape, dtype=torch.int64, device=decoded.device)
+        self._call("elu_hu_rint", self.lib.vq3d_elu_hu_rint,
+                   (self._p(decoded), decoded.numel(), float(scale), float(offset), self._p(out), self.stream()), nbytes=12 * decoded.numel())
+        return out
+
     def huber_loss(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]) -> Tensor:
         """mean smooth_l1(mask(ELU(decoded)), x) as a 0-d fp32 tensor (model.py:120-152); differentiable wrt decoded."""
         if torch.is_grad_enabled() and decoded.requires_grad:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 9
+#define VQ3D_ABI_VERSION 10
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -282,6 +282,12 @@ int vq3d_evonorm_s0_backward_apply(const float *x, const float *gy, const float 
  */
 int vq3d_huber_elu_mask(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
                         int64_t B, int H, int W, int Z, double *sum, double *count, void *stream);
+
+/*
+ * Output epilogue of vqvae/decode_embeddings.py:43-47, fused: out[i] = rint(ELU(decoded[i]) * scale - offset) as int64
+ * (the reference: F.elu, then numpy `res * 1000 - 1000`, np.rint, astype(int)); n elements.
+ */
+int vq3d_elu_hu_rint(const float *decoded, int64_t n, double scale, double offset, int64_t *out, void *stream);
 
 #ifdef __cplusplus
 }

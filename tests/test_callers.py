@@ -1,0 +1,143 @@
+"""Host logic of the three caller scripts: the LMDB layout of extract_embeddings.py read back the way
+the reference's utils/load_lmdb_dataset.py:62-109 does, the NRRD file of decode_embeddings.py, the Lightning-format
+checkpoint of train.py, and the fused HU epilogue kernel on the host emulator."""
+import os
+import pickle
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "3d-vq-vae-2_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+class FakeTxn:
+    def __init__(self, env, write):
+        self.env, self.write = env, write
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def put(self, key, value, db=None):
+        assert self.write and isinstance(key, bytes) and isinstance(value, bytes)
+        self.env.store.setdefault(db, {})[key] = value
+
+    def get(self, key, db=None):
+        return self.env.store.get(db, {}).get(key)
+
+    def cursor(self, db=None):
+        return iter(sorted(self.env.store.get(db, {}).items()))
+
+
+class FakeEnv:
+    """The part of lmdb.Environment that extract_embeddings.py and the reference's reader use."""
+
+    def __init__(self, max_dbs):
+        self.max_dbs, self.store, self.names = max_dbs, {}, []
+
+    def open_db(self, name):
+        assert isinstance(name, bytes)
+        if name not in self.names:
+            assert len(self.names) < self.max_dbs
+            self.names.append(name)
+        return name
+
+    def begin(self, write=False, db=None):
+        return FakeTxn(self, write)
+
+
+def test_lmdb_layout_round_trip_like_the_reference_reader():
+    from vqvae.extract_embeddings import write_codes
+    rs = np.random.RandomState(0)
+    shapes = [(1, 8, 8, 4), (1, 2, 2, 1)]
+    samples = [[rs.randint(0, k, size=s).astype(np.int64) for s, k in zip(shapes, (16, 32))] for _ in range(3)]
+    env = FakeEnv(max_dbs=2)
+    assert write_codes(env, 2, [16, 32], 3, iter(samples)) == 3
+    # utils/load_lmdb_dataset.py:70-86: root metadata, then one sub-db per level keyed by str(index)
+    with env.begin() as txn:
+        num_dbs = int(txn.get(b"num_dbs"))
+        length = int(txn.get(b"length"))
+        num_embeddings = pickle.loads(txn.get(b"num_embeddings"))
+    assert (num_dbs, length) == (2, 3) and np.array_equal(num_embeddings, np.asarray([16, 32]))
+    for level in range(num_dbs):
+        sub = env.open_db(str(level).encode())
+        with env.begin(db=sub) as txn:
+            for i in range(length):
+                arr = pickle.loads(txn.get(str(i).encode(), db=sub))
+                assert arr.dtype == np.int64 and arr.shape == shapes[level]
+                assert np.array_equal(arr, samples[i][level])
+
+
+def test_output_path_rules(tmp_path):
+    from vqvae.extract_embeddings import get_output_abspath
+    ck = tmp_path / "lightning_logs" / "version_12" / "checkpoints" / "last.ckpt"
+    ck.parent.mkdir(parents=True)
+    ck.write_bytes(b"x")
+    assert get_output_abspath(ck, tmp_path).endswith("version_12_last.lmdb")          # extract_embeddings.py:33-36
+    plain = tmp_path / "model.ckpt"
+    plain.write_bytes(b"x")
+    assert get_output_abspath(plain, tmp_path).endswith("model.lmdb")
+    assert get_output_abspath(plain, tmp_path, "codes.lmdb").endswith("codes.lmdb")
+
+
+def test_nrrd_round_trip(tmp_path):
+    from utils import read_nrrd, write_nrrd
+    vol = np.arange(4 * 3 * 2, dtype=np.int64).reshape(4, 3, 2) - 7
+    path = str(tmp_path / "v.nrrd")
+    write_nrrd(path, vol, header={"spacings": (0.976, 0.976, 3)})
+    raw = open(path, "rb").read()
+    head = raw.split(b"\n\n", 1)[0].decode()
+    assert head.splitlines()[0] == "NRRD0004" and "type: int64" in head and "sizes: 4 3 2" in head and "spacings: 0.976 0.976 3" in head
+    # pynrrd's default index order: the FIRST axis varies fastest in the payload
+    payload = np.frombuffer(raw.split(b"\n\n", 1)[1], dtype="<i8")
+    assert payload[1] == vol[1, 0, 0] and payload[4] == vol[0, 1, 0]
+    back, fields = read_nrrd(path)
+    assert np.array_equal(back, vol) and fields["encoding"] == "raw"
+
+
+def test_volume_sources():
+    from utils import open_dataset
+    from utils.volumes import preprocess_hu
+    ds = open_dataset("synthetic:3:8x6x4")
+    x, nv = ds[1]
+    assert len(ds) == 3 and x.shape == (1, 8, 6, 4) and nv == 4 and -0.5 <= float(x.min()) and float(x.max()) <= 4.0
+    assert torch.equal(ds[1][0], x)                                                    # seeded
+    hu = np.array([-2000.0, -1000.0, 0.0, 3500.0])
+    assert np.allclose(preprocess_hu(hu), [-0.5, 0.0, 1.0, 4.0])                       # load_nrrd_dataset.py:73-81
+
+
+def test_train_arguments_and_checkpoint_round_trip(tmp_path):
+    from vqvae import train
+    from vqvae.model import VQVAE
+    args = train.parse_arguments(["synthetic:2:8x8x8", "--batch-size", "1", "--n-bottleneck-blocks", "2", "--num-embeddings", "8", "12",
+                                  "--n-downscales-per-bottleneck", "1", "--n-pre-quantization-blocks", "1", "--base_lr", "1e-4",
+                                  "--block-type", "pre-activation", "--extract-center-cylinder", "False"])
+    assert args.num_embeddings == [8, 12] and args.base_lr == 1e-4 and args.extract_center_cylinder is False
+    torch.manual_seed(0)
+    m = VQVAE(args)
+    train.save_checkpoint(m, args, tmp_path / "checkpoints" / "last.ckpt", step=3, epoch=0)
+    m2 = VQVAE.load_from_checkpoint(str(tmp_path / "checkpoints" / "last.ckpt"))
+    assert m2.num_embeddings == [8, 12]
+    for (k, a), (_, b) in zip(sorted(m.state_dict().items()), sorted(m2.state_dict().items())):
+        assert torch.equal(a, b), k
+
+
+def test_elu_hu_rint_kernel_on_the_emulator():
+    """rint(ELU(x) * 1000 - 1000) as int64, decode_embeddings.py:43-47 (np.rint: half to even)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu.emu_ops import use_emulator
+    from vqvae import _ops
+    x = torch.tensor([-3.0, -0.5, 0.0, 0.0005, 0.0015, 0.0025, 1.0, 2.4996, 3.99951], dtype=torch.float32).reshape(1, 1, 3, 3, 1)
+    ref = np.rint(torch.nn.functional.elu(x).numpy() * 1000 - 1000).astype(np.int64)
+    with use_emulator():
+        got = _ops.default().elu_hu_rint(x)
+    assert got.dtype == torch.int64 and np.array_equal(got.numpy(), ref)

@@ -1,0 +1,88 @@
+"""GPU parity of the caller scripts through the product kernels: extract_embeddings' index stream against a
+direct encode, decode_embeddings' Hounsfield volume against the oracle, and two steps of train.py's loop."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqvae_oracle as O
+from test_callers import FakeEnv
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CFG = dict(n_bottleneck_blocks=2, n_downscales_per_bottleneck=1, num_embeddings=[16, 24], n_pre_quantization_blocks=2,
+           n_post_quantization_blocks=2, n_post_upscale_blocks=1, n_post_downscale_blocks=1)
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    from vqvae import _ops
+    o = _ops.default()
+    prev = o.precision
+    o.precision = "fp32"
+    yield
+    o.precision = prev
+
+
+def _model():
+    from vqvae.model import VQVAE
+    torch.manual_seed(42)
+    m = VQVAE(VQVAE.default_args(extract_center_cylinder=False, **CFG))
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.05)
+        for q in m.encoder.quantize:
+            q.first_pass.fill_(0)
+    return m.eval()
+
+
+def test_extract_embeddings_stream_and_database():
+    from utils import open_dataset
+    from vqvae.extract_embeddings import extract_samples, write_codes
+    m = _model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ds = open_dataset("synthetic:3:16x16x8")
+    loader = torch.utils.data.DataLoader(ds, batch_size=1)
+    env = FakeEnv(max_dbs=2)
+    n = write_codes(env, m.n_bottleneck_blocks, m.num_embeddings, len(loader), extract_samples(m, loader, DEV))
+    assert n == 3
+    for i in range(3):
+        x = ds[i][0][None]
+        _, (_, _, ref_idx) = O.vqvae_forward(sd, O.ModelConfig(**CFG), x)
+        for level in range(2):
+            arr = pickle.loads(env.store[str(level).encode()][str(i).encode()])
+            assert arr.dtype == np.int64 and arr.shape == tuple(ref_idx[level].shape)
+            assert np.array_equal(arr, ref_idx[level].numpy()), (i, level)          # index-exact against the oracle
+
+
+def test_decode_embeddings_hounsfield_volume():
+    from vqvae.decode_embeddings import decode_codes
+    m = _model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    rs = np.random.RandomState(3)
+    codes = [torch.from_numpy(rs.randint(0, 16, size=(8, 8, 4))), torch.from_numpy(rs.randint(0, 24, size=(4, 4, 2)))]
+    got = decode_codes(m.to(DEV), codes).cpu().numpy()
+    cfg = O.ModelConfig(**CFG)
+    emb = [O.embed_code(sd, f"encoder.quantize.{l}.", c[None]).permute(0, 4, 1, 2, 3) for l, c in enumerate(codes)]
+    dec = O.decoder_forward(sd, cfg, emb)
+    ref = np.rint(torch.nn.functional.elu(dec).numpy() * 1000 - 1000).astype(np.int64)
+    assert got.shape == ref.shape == (1, 1, 16, 16, 8) and got.dtype == np.int64
+    assert np.abs(got - ref).max() <= 1                              # fp32 conv rounding can move a value across a .5 boundary
+    assert (got != ref).mean() < 1e-2
+
+
+def test_train_loop_two_steps_and_checkpoint(tmp_path):
+    from vqvae import train
+    from vqvae.model import VQVAE
+    argv = ["synthetic:4:16x16x8", "--batch-size", "2", "--n-bottleneck-blocks", "2", "--n-downscales-per-bottleneck", "1",
+            "--num-embeddings", "16", "24", "--n-pre-quantization-blocks", "1", "--n-post-quantization-blocks", "1",
+            "--extract-center-cylinder", "False", "--base_lr", "1e-3", "--max-steps", "2", "--num-workers", "0",
+            "--default-root-dir", str(tmp_path), "--log-every-n-steps", "1"]
+    train.main(train.parse_arguments(argv))
+    m = VQVAE.load_from_checkpoint(str(tmp_path / "checkpoints" / "last.ckpt"))
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+    assert int(m.encoder.quantize[0].first_pass) == 0                 # the EMA init ran (layers.py:665-683)
+    assert abs(float(m.encoder.quantize[0].cluster_size.sum()) - float(m.encoder.quantize[0].cluster_size.numel())) > 1e-3
