@@ -274,6 +274,126 @@ adam_amsgrad_kernel(float *__restrict__ p, const float *__restrict__ g, float *_
     }
 }
 
+// Weight gradient of a stride-1 "same" convolution from shared-memory tiles: a CTA stages the pre-transformed input halo
+// tile (all C_in) and the scaled output-gradient tile (all C_out) of a 4 x 4 x 32 output box once, then every thread
+// accumulates its APT (co, ci, tap) products over the box (2 LDS + 1 FMA per product; the generic kernel re-reads both
+// operands from global memory for every (co, ci) pair) and adds them to gw with one atomic each.
+constexpr int kWgTH = 4, kWgTW = 4, kWgTZ = 32, kWgThreads = 256;
+
+template <int APT>
+__global__ void __launch_bounds__(kWgThreads)
+conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ) {
+    VQ3D_DYN_SMEM(float, smem);
+    const int Cin = p.C1 + p.C2, k = p.k, k3 = k * k * k, pad = p.pad;
+    const int HH = kWgTH + k - 1, HW = kWgTW + k - 1, HZ = kWgTZ + k - 1, HV = HH * HW * HZ, TV = kWgTH * kWgTW * kWgTZ;
+    float *su = smem, *sg = smem + (size_t)Cin * HV;
+    int tile = blockIdx.x;
+    const int tz = tile % tilesZ; tile /= tilesZ;
+    const int tw = tile % tilesW; tile /= tilesW;
+    const int th = tile % tilesH;
+    const int b = tile / tilesH;
+    const int h0 = th * kWgTH, w0 = tw * kWgTW, z0 = tz * kWgTZ;
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    for (int i = threadIdx.x; i < Cin * HV; i += kWgThreads) {
+        const int ci = i / HV;
+        int r = i - ci * HV;
+        const int hh = r / (HW * HZ); r -= hh * HW * HZ;
+        const int ww = r / HZ, zz = r - ww * HZ;
+        int ih = h0 - pad + hh, iw = w0 - pad + ww, iz = z0 - pad + zz;
+        bool ok = true;
+        if (p.circ) {
+            ih = ih < 0 ? ih + p.H : (ih >= p.H ? ih - p.H : ih);
+            iw = iw < 0 ? iw + p.W : (iw >= p.W ? iw - p.W : iw);
+            iz = iz < 0 ? iz + p.Z : (iz >= p.Z ? iz - p.Z : iz);
+            ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;      // boxes past the edge (partial tiles)
+        } else {
+            ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;
+        }
+        float u = 0.0f;
+        if (ok) {
+            const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+            u = src[((size_t)ih * p.W + iw) * p.Z + iz];
+            u = p.pre_act ? elu1(u + pa) + pb : u + pb;
+        }
+        su[i] = u;
+    }
+    for (int i = threadIdx.x; i < p.Cout * TV; i += kWgThreads) {
+        const int co = i / TV;
+        int r = i - co * TV;
+        const int dh = r / (kWgTW * kWgTZ); r -= dh * kWgTW * kWgTZ;
+        const int dw = r / kWgTZ, dz = r - dw * kWgTZ;
+        const int oh = h0 + dh, ow = w0 + dw, oz = z0 + dz;
+        sg[i] = (oh < p.H && ow < p.W && oz < p.Z) ? p.gy[((size_t)b * p.Cout + co) * S + ((size_t)oh * p.W + ow) * p.Z + oz] * sc : 0.0f;
+    }
+    __syncthreads();
+    const int naccum = p.Cout * Cin * k3;
+    int gofs[APT], uofs[APT];
+    float acc[APT];
+#pragma unroll
+    for (int j = 0; j < APT; ++j) {
+        int a = threadIdx.x + j * kWgThreads;
+        if (a >= naccum) a = 0;                       // computed, never written
+        const int co = a / (Cin * k3);
+        int rem = a - co * Cin * k3;
+        const int ci = rem / k3;
+        rem -= ci * k3;
+        const int kh = rem / (k * k); rem -= kh * k * k;
+        const int kw = rem / k, kz = rem - kw * k;
+        gofs[j] = co * TV;
+        uofs[j] = ci * HV + (kh * HW + kw) * HZ + kz;
+        acc[j] = 0.0f;
+    }
+#pragma unroll 1
+    for (int dh = 0; dh < kWgTH; ++dh)
+#pragma unroll 1
+        for (int dw = 0; dw < kWgTW; ++dw) {
+            const float *gb = sg + (dh * kWgTW + dw) * kWgTZ, *ub = su + (dh * HW + dw) * HZ;
+#pragma unroll 8
+            for (int dz = 0; dz < kWgTZ; ++dz)
+#pragma unroll
+                for (int j = 0; j < APT; ++j) acc[j] = __fmaf_rn(gb[gofs[j] + dz], ub[uofs[j] + dz], acc[j]);
+        }
+#pragma unroll
+    for (int j = 0; j < APT; ++j) {
+        const int a = threadIdx.x + j * kWgThreads;
+        if (a < naccum) atomicAdd(p.gw + a, acc[j]);
+    }
+}
+
+// grid (chunks, Cin, B): finish of the forward-convolution form of dgrad (see vq3d_conv3d_dgrad_finish)
+__global__ void __launch_bounds__(256)
+conv3d_dgrad_finish_kernel(BwdParams p, const float *__restrict__ gu_all) {
+    __shared__ float red[32];
+    const int ci = blockIdx.y, b = blockIdx.z, Cin = p.C1 + p.C2;
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f);
+    const bool first = ci < p.C1;
+    const float *xs = first ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+    float *gxs = first ? (p.gx1 ? p.gx1 + ((size_t)b * p.C1 + ci) * S : nullptr) : (p.gx2 ? p.gx2 + ((size_t)b * p.C2 + (ci - p.C1)) * S : nullptr);
+    const float *gsrc = gu_all + ((size_t)b * Cin + ci) * S;
+    float sa = 0.0f, sb = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gu = gsrc[i] * sc;
+        float gx = gu;
+        if (p.pre_act) {
+            const float t = xs[i] + pa;
+            gx = t > 0.0f ? gu : gu * __expf(t);
+        }
+        if (gxs) gxs[i] = gx;
+        sa += p.pre_act ? gx : 0.0f;
+        sb += gu;
+    }
+    if (p.gscal) {
+        const float ta = block_sum(sa, red);
+        const float tb = block_sum(sb, red);
+        if (threadIdx.x == 0) {
+            if (p.pre_act && p.pre_a) atomicAdd(p.gscal + 0, ta);
+            if (p.pre_b) atomicAdd(p.gscal + 1, tb);
+        }
+    }
+}
+
 // trailing ELU from its output: d ELU(u) / d u = 1 (u > 0), exp(u) = y + 1 (u <= 0)
 __global__ void __launch_bounds__(256)
 elu_backward_kernel(const float *__restrict__ gy, const float *__restrict__ y, float *__restrict__ gx, int64_t n) {
@@ -303,11 +423,24 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
     const int Cin = d->C1 + d->C2;
     const int64_t S = (int64_t)d->H * d->W * d->Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
     int rc;
-    if (p.gx1 || p.gx2 || (p.gscal && (d->pre_a || d->pre_b))) {
+    if (!g->skip_input_grads && (p.gx1 || p.gx2 || (p.gscal && (d->pre_a || d->pre_b)))) {
         rc = launch("conv3d_dgrad", conv3d_dgrad_kernel, dim3((unsigned)ceil_div((int64_t)d->B * S, 128), (unsigned)Cin), dim3(128), 0, stream, p);
         if (rc) return rc;
     }
-    if (p.gw) {
+    const int naccum = d->Cout * Cin * d->k * d->k * d->k;
+    const size_t wg_smem = ((size_t)Cin * (kWgTH + d->k - 1) * (kWgTW + d->k - 1) * (kWgTZ + d->k - 1) + (size_t)d->Cout * kWgTH * kWgTW * kWgTZ) * sizeof(float);
+    if (p.gw && d->stride == 1 && (d->k == 1 || d->k == 3) && d->pad == (d->k - 1) / 2 && naccum <= 16 * kWgThreads && wg_smem <= 160 * 1024 &&
+        (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
+        const int tH = (int)ceil_div(d->H, kWgTH), tW = (int)ceil_div(d->W, kWgTW), tZ = (int)ceil_div(d->Z, kWgTZ);
+        const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ));
+        const int apt = (int)ceil_div(naccum, kWgThreads);
+        if (apt <= 1) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<1>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
+        else if (apt <= 2) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<2>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
+        else if (apt <= 4) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<4>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
+        else if (apt <= 9) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<9>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
+        else rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<16>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
+        if (rc) return rc;
+    } else if (p.gw) {
         int64_t chunks = ceil_div((int64_t)d->B * So, 128 * 8);
         const int64_t cap = (int64_t)kNumSMs * 8 / ((int64_t)Cin * d->Cout) + 1;
         if (chunks > cap) chunks = cap;
@@ -324,6 +457,23 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
         if (rc) return rc;
     }
     return VQ3D_OK;
+}
+
+extern "C" int vq3d_conv3d_dgrad_finish(const vq3d_conv_desc *d, const float *gu_all, float *gx1, float *gx2, float *gscalars, void *stream) {
+    if (!d || !gu_all || !d->x1) return fail(VQ3D_ERR_INVALID, "conv3d_dgrad_finish: null descriptor / gu_all / x1");
+    if (d->stride != 1 || (d->k & 1) == 0 || d->pad != (d->k - 1) / 2) return fail(VQ3D_ERR_INVALID, "conv3d_dgrad_finish: stride-1 same convolutions only");
+    if (d->C2 > 0 && !d->x2) return fail(VQ3D_ERR_INVALID, "conv3d_dgrad_finish: C2 > 0 but x2 is NULL");
+    BwdParams p = {};
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z; p.C1 = d->C1; p.C2 = d->C2; p.Cout = d->Cout;
+    p.k = d->k; p.stride = 1; p.pad = d->pad; p.circ = d->pad_circular; p.pre_act = d->pre_act;
+    p.Ho = d->H; p.Wo = d->W; p.Zo = d->Z;
+    p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.pre_a = d->pre_a; p.pre_b = d->pre_b; p.post_scale = d->post_scale;
+    p.gx1 = gx1; p.gx2 = gx2; p.gscal = gscalars;
+    const int64_t S = (int64_t)d->H * d->W * d->Z;
+    int64_t chunks = ceil_div(S, 256 * 4);
+    if (chunks > 1024) chunks = 1024;
+    return launch("conv3d_dgrad_finish", conv3d_dgrad_finish_kernel, dim3((unsigned)chunks, (unsigned)(d->C1 + d->C2), (unsigned)d->B), dim3(256), 0,
+                  stream, p, gu_all);
 }
 
 extern "C" int vq3d_upsample2x_backward(const float *gy, const float *x, int64_t B, int C, int H, int W, int Z, int pre_act,

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -33,7 +33,7 @@ class PreactDesc(C.Structure):
 
 class ConvBwd(C.Structure):
     """struct vq3d_conv_bwd"""
-    _fields_ = [(n, _fp) for n in ("gy", "raw", "gx1", "gx2", "gw", "gbias", "gscalars")]
+    _fields_ = [(n, _fp) for n in ("gy", "raw", "gx1", "gx2", "gw", "gbias", "gscalars")] + [("skip_input_grads", C.c_int32)]
 
 
 # name -> (restype, argtypes); the single source of truth for tests/test_cabi_symbols.py
@@ -54,6 +54,7 @@ SIGNATURES = {
     "vq3d_conv3d_tc_workspace": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "vq3d_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), _fp, C.c_size_t, _fp]),
     "vq3d_conv3d_backward": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvBwd), _fp]),
+    "vq3d_conv3d_dgrad_finish": (C.c_int, [C.POINTER(ConvDesc), _fp, _fp, _fp, _fp, _fp]),
     "vq3d_upsample2x_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp]),
     "vq3d_huber_elu_mask_backward": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_elu_backward": (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp]),

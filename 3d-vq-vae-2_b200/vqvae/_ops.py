@@ -28,6 +28,7 @@ class Ops:
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
         self.tc_min_voxels = int(os.environ.get("VQ3D_TC_MIN_VOXELS", "0"))   # convs with fewer output voxels stay on the fp32 SIMT kernel
+        self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
 
@@ -200,10 +201,21 @@ class Ops:
         want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
         gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
         d = self.conv_desc(x1, x2, w, cfg["stride"], cfg["pad"], cfg["circular"], cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
-        g = _cabi.ConvBwd(gy=self._p(gy), raw=self._p(raw), gx1=self._p(gx1), gx2=self._p(gx2), gw=self._p(gw), gbias=self._p(gbias),
-                          gscalars=self._p(gscal))
-        self._call("conv3d_backward", self.lib.vq3d_conv3d_backward, (C.byref(d), C.byref(g), self.stream()), kernels=3,
-                   tag=f"{w.shape[1]}->{w.shape[0]} k{w.shape[2]}s{cfg['stride']} @{x1.shape[2]}x{x1.shape[3]}x{x1.shape[4]}")
+        k = w.shape[2]
+        tag = f"{w.shape[1]}->{w.shape[0]} k{k}s{cfg['stride']} @{x1.shape[2]}x{x1.shape[3]}x{x1.shape[4]}"
+        # stride-1 "same" convolutions: the input gradient IS a forward convolution of gy with the mirrored, transposed weight,
+        # so it runs on the forward kernels (tcgen05 in bf16 mode) and only the pre-transform chain is finished separately
+        fwd_dgrad = (self.dgrad_as_forward and cfg["stride"] == 1 and k % 2 == 1 and cfg["pad"] == (k - 1) // 2
+                     and (need["x1"] or need["x2"] or need["pre_a"] or need["pre_b"]))
+        if fwd_dgrad:
+            wt = (w.flip(2, 3, 4) if k > 1 else w).transpose(0, 1).contiguous()
+            gu = self._conv3d_fwd(gy, wt, pad=cfg["pad"], circular=cfg["circular"])
+            self._call("conv3d_dgrad_finish", self.lib.vq3d_conv3d_dgrad_finish,
+                       (C.byref(d), self._p(gu), self._p(gx1), self._p(gx2), self._p(gscal), self.stream()), tag=tag)
+        if not fwd_dgrad or need["w"] or need["bias"] or need["post_scale"] or need["post_b"]:
+            g = _cabi.ConvBwd(gy=self._p(gy), raw=self._p(raw), gx1=self._p(gx1), gx2=self._p(gx2), gw=self._p(gw), gbias=self._p(gbias),
+                              gscalars=self._p(gscal), skip_input_grads=int(fwd_dgrad))
+            self._call("conv3d_backward", self.lib.vq3d_conv3d_backward, (C.byref(d), C.byref(g), self.stream()), kernels=3, tag=tag)
         return gx1, gx2, gw, gbias, gscal
 
     def _conv3d_fwd(self, x1: Tensor, w: Tensor, *, x2: Optional[Tensor] = None, bias: Optional[Tensor] = None, stride: int = 1,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 10
+#define VQ3D_ABI_VERSION 11
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -165,8 +165,18 @@ typedef struct vq3d_conv_bwd {
     float *gx1, *gx2;
     float *gw, *gbias;
     float *gscalars;
+    int32_t skip_input_grads;     /* 1: gx1/gx2 and d pre_a / d pre_b come from vq3d_conv3d_dgrad_finish (below) */
 } vq3d_conv_bwd;
 int vq3d_conv3d_backward(const vq3d_conv_desc *desc, const vq3d_conv_bwd *grads, void *stream);
+
+/*
+ * Input gradient of a stride-1 "same" convolution (k odd, pad = (k-1)/2) as a FORWARD convolution: the caller runs
+ * vq3d_conv3d[_tc] on gy with the flipped / transposed weight (C_in <-> C_out, every tap mirrored, same padding mode),
+ * which yields gu_all [B, C1+C2, H, W, Z] = d loss / d (conv input) up to the post scale; this entry point finishes it:
+ * gu = gu_all * post_scale, gx = gu * (pre_act ? ELU'(x + pre_a) : 1) split into gx1 / gx2 (either may be NULL),
+ * gscalars[0] += sum(gx) (pre_act only), gscalars[1] += sum(gu).  desc: the forward call's descriptor.
+ */
+int vq3d_conv3d_dgrad_finish(const vq3d_conv_desc *desc, const float *gu_all, float *gx1, float *gx2, float *gscalars, void *stream);
 
 /* Backward of vq3d_upsample2x: gx [B, C, H, W, Z] from gy [B, C, 2H, 2W, 2Z]; gscalars as above (entries 0, 1). */
 int vq3d_upsample2x_backward(const float *gy, const float *x, int64_t B, int C, int H, int W, int Z, int pre_act,
