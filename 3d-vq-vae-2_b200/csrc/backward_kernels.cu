@@ -274,6 +274,28 @@ adam_amsgrad_kernel(float *__restrict__ p, const float *__restrict__ g, float *_
     }
 }
 
+// CUDA-graph friendly variant: the step counter and the two bias corrections live on the device (st[0] = step, st[1] = bc1,
+// st[2] = bc2), advanced by a one-thread kernel in front of the update, so a captured step replays correctly
+__global__ void adam_advance_kernel(double *st, double b1, double b2) {
+    st[0] += 1.0;
+    st[1] = 1.0 - pow(b1, st[0]);
+    st[2] = 1.0 - pow(b2, st[0]);
+}
+
+__global__ void __launch_bounds__(256)
+adam_amsgrad_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, float *__restrict__ vmax,
+                        int64_t n, float lr, float b1, float b2, float eps, const double *__restrict__ st) {
+    const float bc1 = (float)st[1], bc2 = (float)st[2];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        const float vm = fmaxf(vmax[i], vi);
+        m[i] = mi; v[i] = vi; vmax[i] = vm;
+        p[i] -= (lr / bc1) * mi / (sqrtf(vm) / sqrtf(bc2) + eps);
+    }
+}
+
 // Weight gradient of a stride-1 "same" convolution from shared-memory tiles: a CTA stages the pre-transformed input halo
 // tile (all C_in) and the scaled output-gradient tile (all C_out) of a 4 x 4 x 32 output box once, then every thread
 // accumulates its APT (co, ci, tap) products over the box (2 LDS + 1 FMA per product; the generic kernel re-reads both
@@ -494,6 +516,17 @@ extern "C" int vq3d_huber_elu_mask_backward(const float *decoded, const float *x
     if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
     return launch("huber_elu_mask_bwd", huber_elu_mask_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x, (const int *)num_valid,
                   mask_hw, B, H * W, Z, count, grad_loss, grad_decoded);
+}
+
+extern "C" int vq3d_adam_amsgrad_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t n,
+                                         double lr, double beta1, double beta2, double eps, double *step_state, void *stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || !step_state || n < 0) return fail(VQ3D_ERR_INVALID, "adam_amsgrad_step_dev: bad arguments");
+    int rc = launch("adam_advance", adam_advance_kernel, dim3(1), dim3(1), 0, stream, step_state, beta1, beta2);
+    if (rc || n == 0) return rc;
+    int64_t blocks = ceil_div(n, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    return launch("adam_amsgrad_dev", adam_amsgrad_dev_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, param, grad, exp_avg, exp_avg_sq,
+                  max_exp_avg_sq, n, (float)lr, (float)beta1, (float)beta2, (float)eps, (const double *)step_state);
 }
 
 extern "C" int vq3d_elu_backward(const float *gy, const float *y, float *gx, int64_t n, void *stream) {

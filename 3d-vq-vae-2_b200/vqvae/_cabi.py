@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -61,6 +61,7 @@ SIGNATURES = {
     "vq3d_evonorm_s0_backward_sums": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int64, _fp, _fp]),
     "vq3d_evonorm_s0_backward_apply": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, _fp, _fp]),
     "vq3d_adam_amsgrad_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, _fp]),
+    "vq3d_adam_amsgrad_step_dev": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _fp, _fp]),
     "vq3d_upsample2x": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_preact_block": (C.c_int, [C.POINTER(PreactDesc), _fp]),
     "vq3d_preact_stack": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),

@@ -457,6 +457,15 @@ class Ops:
                    (self._p(p), self._p(g), self._p(m), self._p(v), self._p(vmax), p.numel(), float(lr), float(b1), float(b2), float(eps),
                     int(step), self.stream()), nbytes=28 * p.numel())
 
+    def adam_amsgrad_step_dev(self, p: Tensor, g: Tensor, m: Tensor, v: Tensor, vmax: Tensor, lr, b1, b2, eps, step_state: Tensor) -> None:
+        """Same update with the step counter / bias corrections in `step_state` (3 doubles on the device): graph-capturable."""
+        for t in (p, g, m, v, vmax):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        assert step_state.dtype == torch.float64 and step_state.numel() == 3
+        self._call("adam_amsgrad_step", self.lib.vq3d_adam_amsgrad_step_dev,
+                   (self._p(p), self._p(g), self._p(m), self._p(v), self._p(vmax), p.numel(), float(lr), float(b1), float(b2), float(eps),
+                    self._p(step_state), self.stream()), kernels=2, nbytes=28 * p.numel())
+
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
         decoded, x = self._t(decoded.detach()), self._t(x.detach())
         B, _, H, W, Z = x.shape

@@ -453,6 +453,12 @@ class Quantizer(nn.Module):
         self.laplace_alpha = laplace_alpha
         self.embedding_dim = embedding_dim
         self.num_embeddings = num_embeddings
+        self._ema_ready = False      # host mirror of "first_pass == 0": once true, training forwards never read the device flag
+                                     # again (no host sync per step; lets a whole training step be captured in a CUDA graph)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._ema_ready = False      # a loaded checkpoint may carry first_pass = 1
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def embed_code(self, embed_idx: torch.Tensor) -> torch.Tensor:
         return ops().embed_code(embed_idx, self.embed)
@@ -470,12 +476,14 @@ class Quantizer(nn.Module):
             raise RuntimeError(f"Quantizer expects (B, {self.embedding_dim}, H, W, Z), got {tuple(x.shape)}")
         world = self._world()
         n_vectors = x.numel() // self.embedding_dim
-        if self.training and bool(self.first_pass):                  # _init_ema, layers.py:665-683
-            meanstd = o.vq_init_stats(x)
-            if world > 1:
-                torch.distributed.all_reduce(meanstd)
-                meanstd /= world
-            o.vq_init_apply(meanstd, n_vectors * world, self.embed, self.embed_avg, self.cluster_size, self.first_pass)
+        if self.training and not self._ema_ready:
+            if bool(self.first_pass):                                # _init_ema, layers.py:665-683
+                meanstd = o.vq_init_stats(x)
+                if world > 1:
+                    torch.distributed.all_reduce(meanstd)
+                    meanstd /= world
+                o.vq_init_apply(meanstd, n_vectors * world, self.embed, self.embed_avg, self.cluster_size, self.first_pass)
+            self._ema_ready = True
         quant, idx, sqerr, stats = o.vq_assign(x, self.embed, want_stats=self.training)
         loss = o.vq_loss(sqerr, self.commitment_cost, x.numel())
         if self.training:                                            # _update_ema, layers.py:636-663

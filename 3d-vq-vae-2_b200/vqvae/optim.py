@@ -29,6 +29,7 @@ class FusedAdamAMSGrad(torch.optim.Optimizer):
         self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self._m, self._v, self._vmax = (torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(3))
+        self._step_state = torch.zeros(3, dtype=torch.float64, device=dev)       # step, 1 - b1^step, 1 - b2^step (device side: graph replay)
         self._slices = []
         off = 0
         for p in ps:
@@ -77,7 +78,7 @@ class FusedAdamAMSGrad(torch.optim.Optimizer):
             if check_params:                            # per-parameter step counters (torch.optim.Adam's state layout) follow lazily
                 for p, _, _, _ in self._slices:
                     self.state[p]["step"] = self._step
-            o.adam_amsgrad_step(self.flat_param, self.flat_grad, self._m, self._v, self._vmax, group["lr"], b1, b2, group["eps"], self._step)
+            o.adam_amsgrad_step_dev(self.flat_param, self.flat_grad, self._m, self._v, self._vmax, group["lr"], b1, b2, group["eps"], self._step_state)
             return loss
         for group in self.param_groups:
             b1, b2 = group["betas"]

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 11
+#define VQ3D_ABI_VERSION 12
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -186,6 +186,11 @@ int vq3d_upsample2x_backward(const float *gy, const float *x, int64_t B, int C, 
 int vq3d_huber_elu_mask_backward(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
                                  int64_t B, int H, int W, int Z, const double *count, const float *grad_loss,
                                  float *grad_decoded, void *stream);
+
+/* The same step with the step counter on the device (step_state: 3 doubles = step, 1 - beta1^step, 1 - beta2^step; zero it once):
+ * the call first advances the counter, so a step captured in a CUDA graph replays with the right bias corrections. */
+int vq3d_adam_amsgrad_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t n,
+                               double lr, double beta1, double beta2, double eps, double *step_state, void *stream);
 
 /* Backward of a trailing ELU given its OUTPUT y (FixupResBlock's last activation, vqvae/layers.py:288-289):
  * gx = gy * (y > 0 ? 1 : y + 1), n elements. */

@@ -205,3 +205,38 @@ def test_silu_velocity_known_answer_backward():
     assert torch.allclose(y.detach().cpu(), yr.detach(), rtol=1e-4, atol=1e-5)
     assert torch.allclose(xg.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-4)
     assert torch.allclose(m.v.grad.cpu(), vr.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_graphed_training_step_matches_eager_steps():
+    """vqvae.parallel.GraphedTrainingStep (whole step in one CUDA graph, device-side Adam step counter) against the same
+    number of eager steps: same parameters and EMA buffers up to the atomics' summation order."""
+    import copy
+    from vqvae.model import VQVAE
+    from vqvae.parallel import GraphedTrainingStep, training_step
+    cfg = dict(n_bottleneck_blocks=2, n_downscales_per_bottleneck=1, num_embeddings=[16, 24], n_pre_quantization_blocks=2,
+               n_post_quantization_blocks=2, n_post_upscale_blocks=1, n_post_downscale_blocks=1)
+    torch.manual_seed(42)
+    base = VQVAE(VQVAE.default_args(extract_center_cylinder=False, base_lr=1e-3, **cfg))
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in base.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    x = O.synthetic_volume((1, 1, 16, 16, 8)).to(DEV)
+    batch = (x, [8])
+    eager = copy.deepcopy(base).to(DEV).train()
+    opt_e = eager.configure_optimizers()
+    for _ in range(5):
+        loss_e = training_step(eager, opt_e, batch)
+    graphed = copy.deepcopy(base).to(DEV).train()
+    opt_g = graphed.configure_optimizers()
+    step = GraphedTrainingStep(graphed, opt_g, batch, warmup=2)
+    for _ in range(3):
+        loss_g = step(batch)
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - float(loss_e)) <= 1e-3 * abs(float(loss_e)) + 1e-6
+    for (k, a), (_, b) in zip(eager.state_dict().items(), graphed.state_dict().items()):
+        if a.dtype.is_floating_point:
+            assert torch.allclose(a, b, rtol=2e-3, atol=2e-5), (k, float((a - b).abs().max()))
+        else:
+            assert torch.equal(a, b), k
+    assert float(opt_g._step_state[0]) == 5.0

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="downscaled_256x256x128", choices=sorted(bench.WORKLOADS))
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="capture the whole step in one CUDA graph (vqvae.parallel.GraphedTrainingStep)")
     a = ap.parse_args()
     kind, shape = bench.WORKLOADS[a.workload]
     dev = torch.device("cuda", 0)
@@ -31,15 +32,20 @@ def main():
     torch.cuda.reset_peak_memory_stats()
     loss = training_step(m, opt, batch)          # warm-up (first-pass codebook init)
     torch.cuda.synchronize()
+    step_fn = (lambda b: training_step(m, opt, b))
+    if a.graph:
+        from vqvae.parallel import GraphedTrainingStep
+        step_fn = GraphedTrainingStep(m, opt, batch, warmup=2)
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        loss = training_step(m, opt, batch)
+        loss = step_fn(batch)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     print(json.dumps({"workload": a.workload, "train_step_ms": ms, "volumes_per_s": 1e3 / ms, "loss": float(loss),
-                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "steps": a.steps,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "steps": a.steps, "cuda_graph": bool(a.graph),
                       "note": "fwd composed (tensor-core convs where GEMM-shaped) + generic fp32 backward + fused Adam"}))
 
 
