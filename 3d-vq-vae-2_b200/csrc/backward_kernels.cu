@@ -304,9 +304,12 @@ constexpr int kWgTH = 4, kWgTW = 4, kWgTZ = 32, kWgThreads = 256;
 
 template <int APT>
 __global__ void __launch_bounds__(kWgThreads)
-conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ) {
+conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int cic) {
     VQ3D_DYN_SMEM(float, smem);
-    const int Cin = p.C1 + p.C2, k = p.k, k3 = k * k * k, pad = p.pad;
+    // blockIdx.y selects a chunk of `cic` input channels (the accumulators of one chunk fit the CTA's registers and its
+    // halo tile fits shared memory); Cin below is the chunk's channel count, ci0 its first channel
+    const int CinAll = p.C1 + p.C2, ci0 = blockIdx.y * cic;
+    const int Cin = min(cic, CinAll - ci0), k = p.k, k3 = k * k * k, pad = p.pad;
     const int HH = kWgTH + k - 1, HW = kWgTW + k - 1, HZ = kWgTZ + k - 1, HV = HH * HW * HZ, TV = kWgTH * kWgTW * kWgTZ;
     float *su = smem, *sg = smem + (size_t)Cin * HV;
     int tile = blockIdx.x;
@@ -334,7 +337,8 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ) {
         }
         float u = 0.0f;
         if (ok) {
-            const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+            const int cg = ci0 + ci;
+            const float *src = cg < p.C1 ? p.x1 + ((size_t)b * p.C1 + cg) * S : p.x2 + ((size_t)b * p.C2 + (cg - p.C1)) * S;
             u = src[((size_t)ih * p.W + iw) * p.Z + iz];
             u = p.pre_act ? elu1(u + pa) + pb : u + pb;
         }
@@ -379,7 +383,10 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ) {
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
         const int a = threadIdx.x + j * kWgThreads;
-        if (a < naccum) atomicAdd(p.gw + a, acc[j]);
+        if (a < naccum) {
+            const int co = a / (Cin * k3), rem = a - co * Cin * k3;          // (co, local ci, tap) -> the weight's own layout
+            atomicAdd(p.gw + ((size_t)co * CinAll + ci0) * k3 + rem, acc[j]);
+        }
     }
 }
 
@@ -449,18 +456,25 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
         rc = launch("conv3d_dgrad", conv3d_dgrad_kernel, dim3((unsigned)ceil_div((int64_t)d->B * S, 128), (unsigned)Cin), dim3(128), 0, stream, p);
         if (rc) return rc;
     }
-    const int naccum = d->Cout * Cin * d->k * d->k * d->k;
-    const size_t wg_smem = ((size_t)Cin * (kWgTH + d->k - 1) * (kWgTW + d->k - 1) * (kWgTZ + d->k - 1) + (size_t)d->Cout * kWgTH * kWgTW * kWgTZ) * sizeof(float);
-    if (p.gw && d->stride == 1 && (d->k == 1 || d->k == 3) && d->pad == (d->k - 1) / 2 && naccum <= 16 * kWgThreads && wg_smem <= 160 * 1024 &&
+    // tiled weight gradient: input channels in chunks whose accumulators (<= 16 per thread) and halo tile (<= 150 KB with the
+    // output-gradient tile) fit one CTA
+    const int k3 = d->k * d->k * d->k;
+    const size_t wg_halo = (size_t)(kWgTH + d->k - 1) * (kWgTW + d->k - 1) * (kWgTZ + d->k - 1) * sizeof(float);
+    const size_t wg_gtile = (size_t)d->Cout * kWgTH * kWgTW * kWgTZ * sizeof(float);
+    int cic = d->Cout * k3 <= 16 * kWgThreads ? (16 * kWgThreads) / (d->Cout * k3) : 0;
+    if (cic > Cin) cic = Cin;
+    while (cic > 0 && wg_gtile + (size_t)cic * wg_halo > 150 * 1024) --cic;
+    if (p.gw && cic > 0 && d->stride == 1 && (d->k == 1 || d->k == 3) && d->pad == (d->k - 1) / 2 &&
         (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
         const int tH = (int)ceil_div(d->H, kWgTH), tW = (int)ceil_div(d->W, kWgTW), tZ = (int)ceil_div(d->Z, kWgTZ);
-        const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ));
-        const int apt = (int)ceil_div(naccum, kWgThreads);
-        if (apt <= 1) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<1>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
-        else if (apt <= 2) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<2>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
-        else if (apt <= 4) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<4>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
-        else if (apt <= 9) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<9>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
-        else rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<16>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ);
+        const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ), (unsigned)ceil_div(Cin, cic));
+        const size_t wg_smem = wg_gtile + (size_t)cic * wg_halo;
+        const int apt = (int)ceil_div((int64_t)d->Cout * cic * k3, kWgThreads);
+        if (apt <= 1) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<1>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
+        else if (apt <= 2) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<2>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
+        else if (apt <= 4) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<4>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
+        else if (apt <= 9) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<9>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
+        else rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<16>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
         if (rc) return rc;
     } else if (p.gw) {
         int64_t chunks = ceil_div((int64_t)d->B * So, 128 * 8);

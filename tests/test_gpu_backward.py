@@ -240,3 +240,36 @@ def test_graphed_training_step_matches_eager_steps():
         else:
             assert torch.equal(a, b), k
     assert float(opt_g._step_state[0]) == 5.0
+
+
+@pytest.mark.parametrize("cin,cout,k,circ,shape", [
+    (36, 36, 3, True, (1, 36, 6, 5, 40)),      # accumulators split over input-channel chunks, partial tiles on every axis
+    (72, 36, 1, False, (2, 72, 5, 4, 33)),     # k = 1, batch 2, halo tile bounded by shared memory
+    (5, 7, 3, False, (1, 5, 9, 6, 35)),        # zero padding, odd channel counts
+])
+def test_conv_gradients_tiled_wgrad_and_forward_dgrad(cin, cout, k, circ, shape):
+    """The shared-memory tiled weight gradient and the forward-convolution input gradient against torch.autograd."""
+    import torch.nn.functional as F
+    from vqvae import _ops
+    o = _ops.default()
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(shape, generator=g)
+    w = torch.randn(cout, cin, k, k, k, generator=g) * 0.2
+    a, b, s, pb = (torch.randn(1, generator=g) * 0.3 for _ in range(4))
+    s = s + 1.0
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, a, b, s, pb)]
+    xr, wr, ar, br, sr, pbr = leaves
+    u = F.elu(xr + ar) + br
+    pad = (k - 1) // 2
+    if pad:
+        u = F.pad(u, (pad,) * 6, mode="circular") if circ else F.pad(u, (pad,) * 6)
+    yr = F.conv3d(u, wr) * sr + pbr
+    r = torch.randn(yr.shape, generator=g)
+    (yr * r).sum().backward()
+    dl = [t.detach().clone().to(DEV).requires_grad_(True) for t in (x, w, a, b, s, pb)]
+    y = o.conv3d(dl[0], dl[1], pad=pad, circular=circ, pre_act=True, pre_a=dl[2], pre_b=dl[3], post_scale=dl[4], post_b=dl[5])
+    (y * r.to(DEV)).sum().backward()
+    assert torch.allclose(y.detach().cpu(), yr.detach(), rtol=1e-4, atol=1e-4)
+    for got, ref, name in zip(dl, leaves, ("x", "w", "pre_a", "pre_b", "scale", "post_b")):
+        err, scale = float((got.grad.cpu() - ref.grad).abs().max()), float(ref.grad.abs().max())
+        assert err <= 1e-3 * scale + 1e-5, (name, err, scale)
