@@ -113,6 +113,101 @@ conv3d_generic_kernel(ConvParams p) {
     }
 }
 
+// k = 3, stride 1, pad 1 ("same") convolutions with few input channels on big tensors (the composed blocks of the training
+// path and the forward-convolution form of their input gradients): a CTA stages the pre-transformed input halo tile of a
+// 4 x 4 x 32 output box once (the generic kernel re-applies wrap arithmetic and ELU for each of the 27 taps), then every
+// thread computes two output voxels x CO_T channels from shared memory.  Same summation order as the generic kernel
+// (ci, kh, kw, kz; zero-padded taps add an exact 0), so the results are bit-identical to it.
+constexpr int kCtTH = 4, kCtTW = 4, kCtTZ = 32, kCtThreads = 256, kCtMaxCin = 16;
+
+template <int CO_T>
+__global__ void __launch_bounds__(kCtThreads)
+conv3d_tiled_kernel(ConvParams p, int tilesH, int tilesW, int tilesZ) {
+    VQ3D_DYN_SMEM(float, smem);
+    constexpr int HH = kCtTH + 2, HW = kCtTW + 2, HZ = kCtTZ + 2, HV = HH * HW * HZ, TV = kCtTH * kCtTW * kCtTZ;
+    const int Cin = p.C1 + p.C2;
+    float *su = smem, *s_w = smem + (size_t)Cin * HV;          // s_w: [ci][tap][CO_T]
+    int tile = blockIdx.x;
+    const int tz = tile % tilesZ; tile /= tilesZ;
+    const int tw = tile % tilesW; tile /= tilesW;
+    const int th = tile % tilesH;
+    const int b = tile / tilesH;
+    const int h0 = th * kCtTH, w0 = tw * kCtTW, z0 = tz * kCtTZ, co0 = blockIdx.y * CO_T;
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const float pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    for (int i = threadIdx.x; i < Cin * 27 * CO_T; i += kCtThreads) {
+        const int j = i % CO_T, t = (i / CO_T) % 27, ci = i / (CO_T * 27), co = co0 + j;
+        s_w[i] = co < p.Cout ? p.w[((size_t)co * Cin + ci) * 27 + t] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < Cin * HV; i += kCtThreads) {
+        const int ci = i / HV;
+        int r = i - ci * HV;
+        const int hh = r / (HW * HZ); r -= hh * HW * HZ;
+        const int ww = r / HZ, zz = r - ww * HZ;
+        int ih = h0 - 1 + hh, iw = w0 - 1 + ww, iz = z0 - 1 + zz;
+        if (p.circ) {
+            ih = ih < 0 ? ih + p.H : (ih >= p.H ? ih - p.H : ih);
+            iw = iw < 0 ? iw + p.W : (iw >= p.W ? iw - p.W : iw);
+            iz = iz < 0 ? iz + p.Z : (iz >= p.Z ? iz - p.Z : iz);
+        }
+        float u = 0.0f;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z) {
+            const float *src = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+            u = __ldg(src + ((size_t)ih * p.W + iw) * p.Z + iz);
+            u = p.pre_act ? elu1(u + pa) + pb : u + pb;
+        }
+        su[i] = u;
+    }
+    __syncthreads();
+    const float sc = ld_scalar(p.post_scale, 1.0f), sb = ld_scalar(p.post_b, 0.0f);
+#pragma unroll 1
+    for (int v = threadIdx.x; v < TV; v += kCtThreads) {
+        const int dh = v / (kCtTW * kCtTZ), dw = (v / kCtTZ) % kCtTW, dz = v % kCtTZ;
+        const int oh = h0 + dh, ow = w0 + dw, oz = z0 + dz;
+        float acc[CO_T];
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = 0.0f;
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float *ub = su + (size_t)ci * HV + (dh * HW + dw) * HZ + dz;
+            const float *wp = s_w + (size_t)ci * 27 * CO_T;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                    for (int kz = 0; kz < 3; ++kz) {
+                        const float xv = ub[(kh * HW + kw) * HZ + kz];
+                        const float *wt = wp + ((kh * 3 + kw) * 3 + kz) * CO_T;
+#pragma unroll
+                        for (int j = 0; j < CO_T; ++j) acc[j] = __fmaf_rn(wt[j], xv, acc[j]);
+                    }
+        }
+        if (oh < p.H && ow < p.W && oz < p.Z) {
+            const int64_t r = ((int64_t)oh * p.W + ow) * p.Z + oz;
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) {
+                const int co = co0 + j;
+                if (co < p.Cout) {
+                    const size_t o = ((size_t)b * p.Cout + co) * S + r;
+                    float yv = __fmaf_rn(acc[j], sc, sb);
+                    if (p.bias) yv += __ldg(p.bias + co);
+                    if (p.residual) yv += __ldg(p.residual + o);
+                    if (p.post_act) yv = elu1(yv);
+                    p.y[o] = yv;
+                }
+            }
+        }
+    }
+}
+
+template <int CO_T>
+static int launch_conv_tiled(const ConvParams &p, void *stream) {
+    const int tH = (int)ceil_div(p.H, kCtTH), tW = (int)ceil_div(p.W, kCtTW), tZ = (int)ceil_div(p.Z, kCtTZ);
+    const size_t smem = ((size_t)(p.C1 + p.C2) * (kCtTH + 2) * (kCtTW + 2) * (kCtTZ + 2) + (size_t)(p.C1 + p.C2) * 27 * CO_T) * sizeof(float);
+    return launch("conv3d_tiled", conv3d_tiled_kernel<CO_T>, dim3((unsigned)((int64_t)p.B * tH * tW * tZ), (unsigned)ceil_div(p.Cout, CO_T)),
+                  dim3(kCtThreads), smem, stream, p, tH, tW, tZ);
+}
+
 // 1x1x1 convolutions on big tensors (parse_input 1 -> 4 at 512^3, the cat + proj 18 -> 18 at 128x128x32,
 // layers.py:535,385,512): pure streaming.  A thread owns 4 consecutive voxels (float4 along the contiguous
 // depth axis) x CO_T output channels; weights of the chunk sit in shared memory ([ci][CO_T], broadcast reads).
@@ -320,6 +415,12 @@ extern "C" int vq3d_conv3d(const vq3d_conv_desc *d, void *stream) {
         if (p.Cout <= 4) return launch_pointwise<4>(p, stream);
         if (p.Cout <= 8) return launch_pointwise<8>(p, stream);
         return launch_pointwise<16>(p, stream);
+    }
+    if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->C1 + d->C2 <= kCtMaxCin && d->H >= 3 && d->W >= 3 && d->Z >= 3 && total >= 16384) {
+        if (p.Cout >= 8) return launch_conv_tiled<8>(p, stream);
+        if (p.Cout >= 3) return launch_conv_tiled<4>(p, stream);
+        if (p.Cout == 2) return launch_conv_tiled<2>(p, stream);
+        return launch_conv_tiled<1>(p, stream);
     }
     const unsigned gx = (unsigned)ceil_div(total, kConvThreads);
     if (p.Cout >= 8) return launch("conv3d<8>", conv3d_generic_kernel<8>, dim3(gx, (unsigned)ceil_div(p.Cout, 8)), dim3(kConvThreads), 0, stream, p);

@@ -250,3 +250,24 @@ def test_emu_up_row_kernel(cin, cout, shape):
         assert o.launches - n0 == 1, "expected one fused launch"
         assert y.shape == ref.shape
         assert close(y.numpy(), ref.numpy(), rtol=1e-4, atol=1e-5), float((y - ref).abs().max())
+
+
+@pytest.mark.parametrize("cin,cout,circ,shape,pre_act,res", [
+    (2, 2, True, (1, 2, 24, 22, 33), True, False),        # partial tiles on every axis, circular wrap
+    (5, 3, False, (1, 5, 21, 24, 35), True, True),        # zero padding, residual, CO_T = 4 with a ragged last chunk
+])
+def test_emu_tiled_conv_matches_torch(cin, cout, circ, shape, pre_act, res):
+    """conv3d_tiled_kernel (k3 s1 p1, few input channels, >= 16384 output voxels) against torch's conv3d."""
+    import torch.nn.functional as F
+    from vqvae import _ops
+    g = torch.Generator().manual_seed(cin * 5 + cout)
+    x = torch.randn(shape, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.2
+    a, b, s, pb = (torch.randn(1, generator=g) * 0.3 for _ in range(4))
+    r = torch.randn(shape[0], cout, *shape[2:], generator=g) if res else None
+    u = (F.elu(x + a) + b) if pre_act else x + b
+    u = F.pad(u, (1,) * 6, mode="circular") if circ else F.pad(u, (1,) * 6)
+    ref = F.conv3d(u, w) * s + pb + (r if res else 0)
+    with use_emulator():
+        got = _ops.default().conv3d(x, w, pad=1, circular=circ, pre_act=pre_act, pre_a=a, pre_b=b, post_scale=s, post_b=pb, residual=r)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), float((got - ref).abs().max())
