@@ -9,7 +9,12 @@ __device__ __forceinline__ void mbarrier_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
+// sleep_ns > 0: back off between polls (a polling warp still takes issue slots from the working warps of its
+// sub-partition: in the quantizer 40 % of all issued instructions were polls before the producer/consumer roles slept)
+#ifndef VQ3D_MBAR_SLEEP_NS
+#define VQ3D_MBAR_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity, uint32_t sleep_ns = VQ3D_MBAR_SLEEP_NS) {
     const uint32_t addr = s_u32(bar);
 #pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
@@ -19,6 +24,7 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
         if (ok) return;
+        if (sleep_ns) __nanosleep(sleep_ns);
     }
     __trap();   // a lost arrival becomes a launch error, never a hung GPU
 }
