@@ -31,6 +31,14 @@ namespace vq3d {
 
 #include "tc_common.cuh"
 
+// VQ3D_VQT_DEBUG builds accumulate, per role, the clocks spent inside the named waits (debug counters 8..15 of the
+// workspace header: who waits for whom) -- tools/debug_vq.py prints them
+#ifdef VQ3D_VQT_DEBUG
+#define VQT_TIMED_WAIT(slot, call) do { const long long t0_ = clock64(); call; if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long *>(const_cast<unsigned *>(p.dbg)) + (slot), (unsigned long long)(clock64() - t0_)); } while (0)
+#else
+#define VQT_TIMED_WAIT(slot, call) call
+#endif
+
 constexpr int kVqtMaxCand = 8;       // per half-row list (two column halves per row -> up to 16 candidates per latent vector)
 
 // Warp roles of one persistent CTA (one per SM; a "super-tile" is NG groups x 128 latent vectors):
@@ -176,18 +184,20 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // issued 16 dimensions (x) + 4 float4 (codeword) at a time so that one evaluation costs D/16 memory round trips.
 template <int D>
 __device__ __forceinline__ float vqt_ref_dist2(const float *__restrict__ xs, int64_t xstride, const float *__restrict__ e) {
-    static_assert(D % 16 == 0, "embedding_dim");
+    static_assert(D % 32 == 0, "embedding_dim");
     float agg = 0.0f;
-#pragma unroll(D <= 32 ? 2 : 1)
-    for (int ch = 0; ch < D / 16; ++ch) {
-        float xv[16];
-        float4 ev[4];
+#pragma unroll 1
+    for (int ch = 0; ch < D / 32; ++ch) {
+        // 32 dimensions per memory round trip (an L2 round trip costs ~1 us under this kernel's load: they, not the
+        // arithmetic, set the pace of the load/epilogue warps)
+        float xv[32];
+        float4 ev[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 4 + j);
+        for (int j = 0; j < 8; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 8 + j);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xv[j] = __ldg(xs + (size_t)(ch * 16 + j) * xstride);
+        for (int j = 0; j < 32; ++j) xv[j] = __ldg(xs + (size_t)(ch * 32 + j) * xstride);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const float q4[4] = {ev[j].x, ev[j].y, ev[j].z, ev[j].w};
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
@@ -301,6 +311,9 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     const uint32_t tmem_d = tmem_slot;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
+#ifdef VQ3D_VQT_DEBUG
+    const long long t_kernel0 = clock64();
+#endif
     const int64_t N = p.B * p.S;
     const int64_t nsuper = (N + NG * 128 - 1) / (NG * 128);
     const int my_super = nsuper > (int64_t)blockIdx.x ? (int)((nsuper - 1 - blockIdx.x) / gridDim.x + 1) : 0;
@@ -337,8 +350,8 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 const uint32_t e_img = ring_addr + slot * Cfg::STAGE;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (t == 0) mbarrier_wait(&a_full[g][ab], apar);
-                    mbarrier_wait(&d_empty[g][u & 1u], ((u >> 1) & 1u) ^ 1u);
+                    if (t == 0) VQT_TIMED_WAIT(4, mbarrier_wait(&a_full[g][ab], apar));
+                    VQT_TIMED_WAIT(5, mbarrier_wait(&d_empty[g][u & 1u], ((u >> 1) & 1u) ^ 1u));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
                         const uint32_t a_img = a_addr + (uint32_t)(g * NABUF + ab) * Cfg::AIMG;
@@ -364,8 +377,8 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
         uint32_t u = 0;
         for (int i = 0; i < my_super; ++i) {
             const int rb = i & 1, ab = i % NABUF;
-            mbarrier_wait(&r_empty[g][rb], (((uint32_t)i >> 1) & 1u) ^ 1u);
-            mbarrier_wait(&a_full[g][ab], (uint32_t)(i / NABUF) & 1u);
+            VQT_TIMED_WAIT(6, mbarrier_wait(&r_empty[g][rb], (((uint32_t)i >> 1) & 1u) ^ 1u));
+            VQT_TIMED_WAIT(7, mbarrier_wait(&a_full[g][ab], (uint32_t)(i / NABUF) & 1u));
             const float xx = s_xx[(g * 2 + rb) * 128 + row];
             __syncwarp();
             if (lane == 0) mbarrier_arrive(&a_empty[g][ab]);
@@ -379,7 +392,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             sw.cand = s_cand + (size_t)slot_res * kVqtMaxCand * 128 + row;
             sw.seen = s_seen + (size_t)slot_res * kVqtMaxCand * 128 + row;
             for (int t = 0; t < ntiles; ++t, ++u) {
-                mbarrier_wait(&d_full[g][u & 1u], (u >> 1) & 1u);
+                VQT_TIMED_WAIT(8, mbarrier_wait(&d_full[g][u & 1u], (u >> 1) & 1u));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_addr = tmem_d + lane_sel + (uint32_t)((g * 2 + (int)(u & 1u)) * NT + half * HC);
                 const int col0 = t * NT + half * HC;
@@ -430,7 +443,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             int64_t b, s;
             const bool active = locate(i, b, s);
             const float *xs = p.x + (size_t)b * D * p.S + s;
-            mbarrier_wait(&a_empty[g][ab], ((uint32_t)(i / NABUF) & 1u) ^ 1u);
+            VQT_TIMED_WAIT(9, mbarrier_wait(&a_empty[g][ab], ((uint32_t)(i / NABUF) & 1u) ^ 1u));
             unsigned char *a_img = sA + (size_t)(g * NABUF + ab) * Cfg::AIMG + (size_t)row * 16;
             float xx = 0.0f;
             const float *px = xs;
@@ -462,7 +475,13 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             int64_t b, s;
             const bool active = locate(i, b, s);
             const float *xs = p.x + (size_t)b * D * p.S + s;
-            mbarrier_wait(&r_full[g][rb], ((uint32_t)i >> 1) & 1u);
+            VQT_TIMED_WAIT(10, mbarrier_wait(&r_full[g][rb], ((uint32_t)i >> 1) & 1u));
+#ifdef VQ3D_VQT_DEBUG
+            long long t_ph = clock64();
+            auto phase = [&](int slot) { const long long t1 = clock64(); if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(const_cast<unsigned *>(p.dbg)) + slot, (unsigned long long)(t1 - t_ph)); t_ph = t1; };
+#else
+            auto phase = [&](int) {};
+#endif
             // merge the two half-row lists: final minimum, then the entries that can still be within margin of it
             const int res0 = (g * 2 + rb) * 2;
             const float u_fin = fminf(s_min[res0 * 128 + row], s_min[(res0 + 1) * 128 + row]);
@@ -497,6 +516,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
 #endif
                 if (!ovf && nc == 1 && k_one < p.K) best_k = __ldg(p.perm + k_one);      // alone within the error bound: it IS the reference's argmin
             }
+            phase(12);       // merge
             // exact re-rank of the vectors with several candidates, densely packed over the warp: the (vector, code) pairs
             // go through a 64-entry queue, every lane evaluates one pair per round with the reference's arithmetic, the
             // owners keep the lexicographic (sqrt(d2), k) minimum = the reference's argmin (first minimum)
@@ -550,6 +570,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                     __syncwarp();
                 }
             }
+            phase(13);       // re-rank
             if (active) need_scan = best_k == 0x7fffffff;        // list overflow or nothing finite (NaN input)
             __syncwarp();
             if (lane == 0) mbarrier_arrive(&r_empty[g][rb]);
@@ -583,24 +604,24 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 const float *e = p.embed + (size_t)best_k * D;
                 float err = 0.0f;
 #pragma unroll 1
-                for (int ch = 0; ch < D / 16; ++ch) {
-                    float4 ev[4];
-                    float xv[16];
+                for (int ch = 0; ch < D / 32; ++ch) {
+                    float4 ev[8];
+                    float xv[32];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 4 + j);
+                    for (int j = 0; j < 8; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 8 + j);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) xv[j] = __ldg(xs + (size_t)(ch * 16 + j) * p.S);
+                    for (int j = 0; j < 32; ++j) xv[j] = __ldg(xs + (size_t)(ch * 32 + j) * p.S);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         const float qv[4] = {ev[j].x, ev[j].y, ev[j].z, ev[j].w};
 #pragma unroll
                         for (int l = 0; l < 4; ++l) {
                             const float df = qv[l] - xv[j * 4 + l];
                             err = __fmaf_rn(df, df, err);
-                            p.quant[((size_t)b * D + ch * 16 + j * 4 + l) * p.S + s] = __fadd_rn(xv[j * 4 + l], __fsub_rn(qv[l], xv[j * 4 + l]));    // layers.py:720, two roundings
+                            p.quant[((size_t)b * D + ch * 32 + j * 4 + l) * p.S + s] = __fadd_rn(xv[j * 4 + l], __fsub_rn(qv[l], xv[j * 4 + l]));    // layers.py:720, two roundings
                         }
                         if (want_stats) {
-                            float *dst = p.dw + (size_t)best_k * D + ch * 16 + j * 4;
+                            float *dst = p.dw + (size_t)best_k * D + ch * 32 + j * 4;
                             if (dw_vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xv[j * 4]), "f"(xv[j * 4 + 1]), "f"(xv[j * 4 + 2]), "f"(xv[j * 4 + 3]) : "memory");
                             else { atomicAdd(dst, xv[j * 4]); atomicAdd(dst + 1, xv[j * 4 + 1]); atomicAdd(dst + 2, xv[j * 4 + 2]); atomicAdd(dst + 3, xv[j * 4 + 3]); }
                         }
@@ -610,9 +631,14 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 p.idx[(size_t)b * p.S + s] = best_k;
                 err_acc += (double)err;
             }
+            phase(14);       // fallback scan + gather + stores
             if (i + 2 < my_super) stage(i + 2);
+            phase(15);       // stage (incl. its a_empty wait)
         }
     }
+#ifdef VQ3D_VQT_DEBUG
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long *>(const_cast<unsigned *>(p.dbg)) + 11, (unsigned long long)(clock64() - t_kernel0));
+#endif
     // ---- squared-error total of the CTA ----
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
