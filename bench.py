@@ -142,7 +142,7 @@ def quantizer_point(dev, pk, N=1 << 20, D=32, K=512, reps=10):
     return {"value": gc, "unit": "Gcodes/s", "config": {"N": N, "D": D, "K": K, "mode": "eval", "path": "tcgen05 bf16 candidate pass + exact fp32 re-rank"},
             "ms": t * 1e3, "roofline": {"bound": "hbm" if hbm < tens else "tensor", "peak": min(hbm, tens), "unit": "Gcodes/s", "frac": gc / min(hbm, tens),
                                         "tmem_read_ceiling": tmem, "frac_of_tmem_read_ceiling": gc / tmem},
-            "sweep": "profiles/r01y_quantizer_sweep_tc_v2.tsv (tools/bench_quantizer.py)"}
+            "sweep": "profiles/r01_final_quantizer_sweep_tc_v2.tsv (tools/bench_quantizer.py)"}
 
 
 def ncu_traffic(kernel_tag):
