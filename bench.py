@@ -145,6 +145,34 @@ def quantizer_point(dev, pk, N=1 << 20, D=32, K=512, reps=10):
             "sweep": "profiles/r01_final_quantizer_sweep_tc_v2.tsv (tools/bench_quantizer.py)"}
 
 
+def train_point(dev, steps=3):
+    from vqvae.parallel import GraphedTrainingStep, training_step
+    kind, shape = WORKLOADS["downscaled_256x256x128"]
+    torch.cuda.empty_cache()
+    m = build_model(kind).to(dev).train()
+    for q in m.encoder.quantize:
+        q.first_pass.fill_(1)
+    x = synthetic_volume(shape, 42).to(dev)
+    opt = m.configure_optimizers()
+    batch = (x, [shape[4]])
+    training_step(m, opt, batch)                      # data-dependent codebook init (layers.py:665-683)
+    step = GraphedTrainingStep(m, opt, batch, warmup=2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"workload": "downscaled_256x256x128 (BASELINE.json configs[1])", "ms_per_step": ms, "volumes_per_s": 1e3 / ms, "batch": 1,
+           "loss": float(loss), "cuda_graph": True, "steps": steps,
+           "what": "forward (training mode, EMA codebook update) + backward + fused Adam(amsgrad); fp32 master weights, bf16 tcgen05 convolutions where GEMM-shaped"}
+    del step, m, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def ncu_traffic(kernel_tag):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
     --set full capture (profiles/ncu_traffic.json, written by hand from profiles/*.summary.txt)."""
@@ -391,6 +419,13 @@ def run_b200(args):
                                "what": "VQVAE.encode (Encoder2 + 3 quantizers -> code indices), CUDA-graph replay, per-rank time of rank 0"}
         except Exception as ex:  # pragma: no cover
             line["extract"] = {"error": repr(ex)}
+        # BASELINE.json configs[1]: one training step of the 2-level downscaled model on a 256x256x128 volume (forward in training
+        # mode with EMA updates, backward, fused Adam), captured as one CUDA graph; reported next to the headline, not part of it
+        if not args.no_train and world == 1:
+            try:
+                line["train_step"] = train_point(dev)
+            except Exception as ex:  # pragma: no cover
+                line["train_step"] = {"error": repr(ex)}
         traffic = ncu_traffic(f"{dom_key[0]} [{dom_key[1]}]")
         if traffic is not None:
             line["roofline"]["traffic"] = traffic["dram_bytes_per_launch"]
@@ -417,6 +452,7 @@ def main():
     ap.add_argument("--workload", default="full_512x512x128", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=8, help="independent volumes per step and GPU (stacked along B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step point (configs[1])")
     ap.add_argument("--profile-out", default=None, help="write the per-op CUDA-event table of one eager step here")
     args = ap.parse_args()
     if args.impl == "reference":
