@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqvae3d_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "vq3d_upsample2x": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "vq3d_preact_block": (C.c_int, [C.POINTER(PreactDesc), _fp]),
     "vq3d_preact_stack": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),
+    "vq3d_preact_stack_thin_tc": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),
     "vq3d_preact_stack_tc_workspace": (C.c_size_t, [C.POINTER(PreactDesc)]),
     "vq3d_preact_stack_tc": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, C.c_size_t, _fp]),
     "vq3d_evonorm_s0_stats": (C.c_int, [_fp, C.c_int, C.c_int64, C.c_int, C.c_double, _fp, _fp, _fp]),

@@ -28,6 +28,9 @@ class Ops:
         self.launches = 0            # kernels enqueued through this object (bench.py's gpu_launches)
         self.profile = None          # list -> (name, tag, algorithmic bytes, flops, ev0, ev1) per C call
         self.tc_min_voxels = int(os.environ.get("VQ3D_TC_MIN_VOXELS", "0"))   # convs with fewer output voxels stay on the fp32 SIMT kernel
+        # merged-tap tensor-core kernel for the thin 512^3 / 256^3 blocks: correct, but measured SLOWER than the SIMT row kernel
+        # (0.72 vs 0.52 ms per 4->2->4 block and volume: the im2col copy saturates the shared-memory pipe), so off by default
+        self.thin_tc = os.environ.get("VQ3D_THIN_TC", "0") == "1"
         self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
@@ -359,6 +362,12 @@ class Ops:
                 if self._call("preact_stack_tc", self.lib.vq3d_preact_stack_tc,
                               (arr, n, self._p(ws), ws.numel(), self.stream()), allow_unsupported=True, kernels=launches, **meta):
                     return y
+        # thin blocks on big tensors: conv2 as one merged-tap GEMM per 128 voxels (the SIMT row kernel is FMA-issue bound there)
+        if (self.precision == "bf16" and self.thin_tc and (Cc, Cb) in ((4, 2), (8, 4)) and H * W * Z > 65536 and Z in (32, 64, 128)
+                and H % 8 == 0 and W % 8 == 0 and not (n == 1 and tail is not None)):
+            if self._call("preact_stack_thin_tc", self.lib.vq3d_preact_stack_thin_tc, (arr, n, self._p(tmp), self.stream()),
+                          allow_unsupported=True, kernels=n, **meta):
+                return res
         if n == 1:
             d = arr[0]
             return res if self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()),

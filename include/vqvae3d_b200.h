@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VQ3D_ABI_VERSION 12
+#define VQ3D_ABI_VERSION 13
 
 int vq3d_abi_version(void);
 const char *vq3d_last_error(void);
@@ -268,6 +268,14 @@ int vq3d_preact_stack(const vq3d_preact_desc *blocks, int n, float *tmp, void *s
  */
 size_t vq3d_preact_stack_tc_workspace(const vq3d_preact_desc *first_block);
 int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * The thin 'same' blocks (4 -> 2 -> 4, 8 -> 4 -> 8; full-depth tiles: Z in {32, 64, 128}, H and W multiples of 8) with
+ * conv2 as ONE merged-tap GEMM per 128 voxels on the tensor cores (K = 27 * C_b; bf16 operands, fp32 accumulation).
+ * Same arguments and ping-pong convention as vq3d_preact_stack (tmp may be NULL for n == 1); a last block that carries
+ * the fused out convolution runs on the fp32 row kernel.  VQ3D_ERR_UNSUPPORTED for any other shape.
+ */
+int vq3d_preact_stack_thin_tc(const vq3d_preact_desc *blocks, int n, float *tmp, void *stream);
 
 /*
  * EvoNorm3D-S0 (vqvae/evonorm.py:12-26,59-76; batch 1 like the reference): per-channel std[c] =

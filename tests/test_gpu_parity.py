@@ -563,3 +563,42 @@ def test_batched_forward_equals_per_volume_forward():
         for lvl in range(len(idx)):
             assert torch.equal(idx_b[lvl][i:i + 1], idx[lvl]), (i, lvl)
         assert torch.allclose(dec_b[i:i + 1], dec, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,n,shape,tail", [
+    (4, 2, (1, 32, 32, 128), False),     # the 512^3-level block shape (full-depth tiles, Z = 128)
+    (4, 3, (2, 16, 40, 128), True),      # batch 2, non-square tile grid, last block carries the fused out conv (row kernel)
+    (8, 2, (1, 48, 32, 64), False),      # the 256^3-level shape: C_b = 4 (K = 108 -> 112), two w columns per M-block
+    (8, 1, (1, 64, 64, 32), False),      # Z = 32: four w columns per M-block
+])
+def test_thin_tensor_core_stack_matches_fp32(C, n, shape, tail):
+    """preact_thin_tc_kernel (merged-tap conv2 GEMM, K = 27 * C_b) against the exact fp32 row kernel."""
+    from vqvae import _ops
+    o = _ops.default()
+    seq = _rand_stack(C, n, seed=3 * C + n)
+    out = None
+    if tail:
+        torch.manual_seed(5)
+        out = L.Conv3d(C, 1, kernel_size=1).to(DEV)
+    B, H, W, Z = shape
+    x = torch.randn(B, C, H, W, Z, generator=torch.Generator().manual_seed(2)).to(DEV)
+    prev, prev_thin = o.precision, o.thin_tc
+    try:
+        with torch.no_grad():
+            o.precision = "fp32"
+            ref = seq(x, tail=out) if tail else seq(x)
+            o.precision, o.thin_tc = "bf16", True           # the kernel is off by default (slower than the row kernel, DESIGN.md 3)
+            o.profile = []
+            got = seq(x, tail=out) if tail else seq(x)
+            torch.cuda.synchronize()
+            assert [e[0] for e in o.profile] == ["preact_stack_thin_tc"], [e[0] for e in o.profile]
+            got2 = seq(x, tail=out) if tail else seq(x)
+            assert torch.equal(got, got2)
+    finally:
+        o.precision, o.thin_tc = prev, prev_thin
+        o.profile = None
+    base = (out(x) if tail else x)
+    branch = ref - base
+    err, scale = float((got - ref).abs().max()), float(branch.abs().max())
+    assert err <= 2e-2 * scale, (err, scale)
+    assert float((got - ref).abs().mean()) <= 5e-3 * float(branch.abs().mean() + 1e-6)
