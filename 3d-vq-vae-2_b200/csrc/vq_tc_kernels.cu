@@ -72,7 +72,9 @@ struct VqtCfg {
     // columns [kVqtMaxCand][128] (u16), running minimum at push time [kVqtMaxCand][128]
     static constexpr size_t RES = (size_t)NG * 2 * 128 * 4 + (size_t)NG * 2 * 2 * 128 * (4 + 4 + 6 * kVqtMaxCand);
     static constexpr size_t QUEUE = (size_t)4 * NG * 64 * 8;          // per load/epilogue warp: 64 (code | lane, distance) pairs
-    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES + QUEUE;
+    static constexpr size_t TNORM = 128 * 4;                          // per-tile largest norms (K <= 16 384: 128 tiles)
+    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES + QUEUE + TNORM;
+    static constexpr size_t SMEM_LIMIT = 227 * 1024 - 1024;           // minus the static part (barriers, reduction scratch)
 };
 
 struct VqtParams {
@@ -83,6 +85,7 @@ struct VqtParams {
     const int *perm;                 // column -> code index (the norm-sorted order)
     const float *tnorm;              // per tile: largest ||e_k|| in it
     const unsigned *dbg;             // debug counters (VQ3D_VQT_DEBUG builds)
+    int perm_in_smem;                // the column -> code table fits behind the other shared-memory regions (u16 entries)
     float *quant;
     int64_t *idx;
     double *sqerr;
@@ -289,6 +292,14 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     float *s_seen = reinterpret_cast<float *>(s_nc + NG * 2 * 2 * 128);                 // [NG][2][half][kVqtMaxCand][128]
     unsigned short *s_cand = reinterpret_cast<unsigned short *>(s_seen + NG * 2 * 2 * kVqtMaxCand * 128);   // same shape
     uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_cand + NG * 2 * 2 * kVqtMaxCand * 128);              // [4*NG warps][64] + distances
+    // per-tile norms and (when it fits) the column -> code table live in shared memory: the epilogue warps look them up on
+    // their critical path, where every global-memory round trip costs ~1 us
+    float *s_tnorm = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(s_queue) + Cfg::QUEUE);
+    unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_tnorm + 128);
+    for (int i = threadIdx.x; i < p.Kpad / NT; i += Cfg::THREADS) s_tnorm[i] = __ldg(p.tnorm + i);
+    if (p.perm_in_smem)
+        for (int i = threadIdx.x; i < p.Kpad; i += Cfg::THREADS) s_perm[i] = (unsigned short)__ldg(p.perm + i);
+    auto code_of = [&](int col) -> int { return p.perm_in_smem ? (int)s_perm[col] : __ldg(p.perm + col); };
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -396,7 +407,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_addr = tmem_d + lane_sel + (uint32_t)((g * 2 + (int)(u & 1u)) * NT + half * HC);
                 const int col0 = t * NT + half * HC;
-                sw.hm = vqt_half_margin(xnorm, xx, __ldg(p.tnorm + t));
+                sw.hm = vqt_half_margin(xnorm, xx, s_tnorm[t]);
                 // ping-pong over the 16-column groups: the next group's tcgen05.ld is in flight while this one is scanned
                 uint32_t ra[16], rb16[16];
                 tmem_ld16_async(d_addr, ra);
@@ -490,7 +501,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             auto kept = [&](int h, int c) -> bool {
                 const int col = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
                 return s_seen[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row] <=
-                       u_fin + vqt_half_margin(xnorm_row, xx_row, __ldg(p.tnorm + col / NT));
+                       u_fin + vqt_half_margin(xnorm_row, xx_row, s_tnorm[col / NT]);
             };
             int nc = 0, k_one = 0x7fffffff;
             bool ovf = false;
@@ -514,7 +525,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                     if (nc >= 2) atomicAdd(dbg + 4, (unsigned)nc);
                 }
 #endif
-                if (!ovf && nc == 1 && k_one < p.K) best_k = __ldg(p.perm + k_one);      // alone within the error bound: it IS the reference's argmin
+                if (!ovf && nc == 1 && k_one < p.K) best_k = code_of(k_one);      // alone within the error bound: it IS the reference's argmin
             }
             phase(12);       // merge
             // exact re-rank of the vectors with several candidates, densely packed over the warp: the (vector, code) pairs
@@ -546,7 +557,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                         }
                         const int h = cursor / kVqtMaxCand, c = cursor % kVqtMaxCand;
                         const int col = (int)s_cand[((size_t)(res0 + h) * kVqtMaxCand + c) * 128 + row];
-                        q_key[excl + j] = (uint32_t)(col < p.K ? __ldg(p.perm + col) : 0xffff) | ((uint32_t)lane << 16);
+                        q_key[excl + j] = (uint32_t)(col < p.K ? code_of(col) : 0xffff) | ((uint32_t)lane << 16);
                         ++cursor;
                     }
                     __syncwarp();
@@ -697,6 +708,8 @@ static int launch_vqt(const float *x, const float *embed, int64_t B, int64_t S, 
     auto kernel = vq_tc_kernel<D>;
     static_assert(Cfg::NG * 2 * Cfg::NT == 512, "TMEM budget");
     size_t smem = Cfg::smem;                                             // > 113 KB: one CTA per SM (it owns all of TMEM)
+    p.perm_in_smem = smem + (size_t)p.Kpad * 2 <= Cfg::SMEM_LIMIT ? 1 : 0;
+    if (p.perm_in_smem) smem += (size_t)p.Kpad * 2;
     e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(attr)");
     const int64_t nsuper = ceil_div(B * S, Cfg::NG * 128);
