@@ -80,6 +80,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 // threads = 128 * G: thread (row r = tid % 128, group g = tid / 128); a stage holds K = 64 = 8 chunks
 // of 8 elements (16 B); group g packs chunks g, g+G, ...
+template <int KS>       // kernel size as a compile-time constant: the (ci, kh, kw, kz) decode of the gather folds to shifts / constant divisions
 __global__ void __launch_bounds__(512)
 conv3d_tc_kernel(TcParams p) {
     VQ3D_DYN_SMEM(unsigned char, smem_raw);
@@ -88,7 +89,7 @@ conv3d_tc_kernel(TcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = tid & (kTcM - 1), g = tid >> 7, G = p.G;
     const int Npad = p.Npad, Ktot = p.Ktot;
-    const int k = p.k, kk = k * k, k3 = kk * k;
+    constexpr int k = KS, kk = k * k, k3 = kk * k;
     const int Cin = p.C1 + p.C2;
     // stage layout: A [8 k-chunks][16 row-groups][128 B] = 16 KB, then B [8][Npad/8][128 B]
     const uint32_t a_bytes = kTcM * kTcBK * 2, b_bytes = (uint32_t)Npad * kTcBK * 2;
@@ -362,7 +363,14 @@ extern "C" int vq3d_conv3d_tc(const vq3d_conv_desc *d, void *ws, size_t ws_bytes
     }
     p.G = tiles * p.nsplit >= 2 * kNumSMs ? 2 : 4;      // few CTAs: put more gather threads on each
     const size_t smem = (size_t)kTcStages * ((size_t)kTcM * kTcBK * 2 + (size_t)p.Npad * kTcBK * 2) + 256;
-    int rc = launch("conv3d_tc", conv3d_tc_kernel, dim3((unsigned)tiles, (unsigned)p.nsplit), dim3((unsigned)(kTcM * p.G)), smem, stream, p);
+    const dim3 grid((unsigned)tiles, (unsigned)p.nsplit), block((unsigned)(kTcM * p.G));
+    int rc;
+    switch (p.k) {
+        case 1: rc = launch("conv3d_tc", conv3d_tc_kernel<1>, grid, block, smem, stream, p); break;
+        case 2: rc = launch("conv3d_tc", conv3d_tc_kernel<2>, grid, block, smem, stream, p); break;
+        case 3: rc = launch("conv3d_tc", conv3d_tc_kernel<3>, grid, block, smem, stream, p); break;
+        default: rc = launch("conv3d_tc", conv3d_tc_kernel<4>, grid, block, smem, stream, p); break;
+    }
     if (rc || p.nsplit <= 1) return rc;
     const int64_t total = (int64_t)p.B * p.Ho * p.Wo * p.Zo;
     return launch("conv3d_tc_reduce", conv3d_tc_reduce_kernel, dim3((unsigned)ceil_div(total, 256), (unsigned)p.Cout), dim3(256), 0, stream,
