@@ -114,6 +114,32 @@ def physical_gpu_index(local):
     return local
 
 
+_ORIGINAL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to its GPU before any pinned host buffer is allocated (first touch
+    puts the pages on that NUMA node): with 8 ranks the end-to-end leg moves ~200 GB/s through host memory, and remote-node
+    staging buffers were what capped it.  Best effort: returns the CPU count bound to, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and w * 64 + b < ncpu}
+        original = set(os.sched_getaffinity(0))
+        allowed = cpus & original
+        if allowed:
+            global _ORIGINAL_AFFINITY
+            _ORIGINAL_AFFINITY = original
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def quantizer_point(dev, pk, N=1 << 20, D=32, K=512, reps=10):
     """Quantizer.forward (eval) on N latent vectors presented as (1, D, N/4096, 64, 64): Gcodes/s and the
     fraction of min(HBM, tensor) roofline (8D+8 bytes, 2KD flops per vector)."""
@@ -190,6 +216,8 @@ def ncu_traffic(kernel_tag):
 def cpu_arm(kind, steps, warmup):
     """The reference's CPU path (oracle port, ATen fp32, all host cores) on a bounded sample."""
     from oracle import vqvae_oracle as O
+    if _ORIGINAL_AFFINITY is not None:          # the CPU arm uses every host core, not only the GPU-local ones
+        os.sched_setaffinity(0, _ORIGINAL_AFFINITY)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     m = build_model(kind)
@@ -237,6 +265,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -375,7 +404,8 @@ def run_b200(args):
                        "weights": "reference ctor RNG seed 42 + Fixup init + N(0,0.02) perturbation",
                        "l2": f"inputs larger than L2 ({134 * batch} MB of volumes, GBs of activations per step)",
                        "cuda_graph": True, "parallelism": f"dp{world} (independent volumes, no collective)",
-                       "e2e": "pinned H2D / forward / D2H on three streams, double-buffered"},
+                       "e2e": "pinned H2D / forward / D2H on three streams, double-buffered",
+                       "host_cpus_bound": numa_cpus},
             "e2e": {"value": world * e2e_steps * batch / e2e_s, "unit": "volumes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / e2e_steps},
             "gpu_launches": launches_per_step * steps,
