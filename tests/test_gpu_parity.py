@@ -602,3 +602,42 @@ def test_thin_tensor_core_stack_matches_fp32(C, n, shape, tail):
     err, scale = float((got - ref).abs().max()), float(branch.abs().max())
     assert err <= 2e-2 * scale, (err, scale)
     assert float((got - ref).abs().mean()) <= 5e-3 * float(branch.abs().mean() + 1e-6)
+
+
+@pytest.mark.parametrize("N,D,K,kind", [
+    (65536, 32, 8192, "gauss"),        # 64 codebook tiles, streamed through the ring
+    (40000, 64, 16384, "gauss"),       # the largest supported codebook (128 tiles)
+    (65536, 64, 1024, "clustered"),    # latents close to their codes (a trained model): tiny distances, large norms
+    (50000, 32, 512, "outlier"),       # a few codes with 100x the norm of the rest (dead codes after EMA updates)
+    (40000, 128, 512, "scaled"),       # latents 1000x smaller than the codebook
+])
+def test_quantizer_tensor_core_path_regimes(N, D, K, kind):
+    """Index exactness of the tensor-core candidate pass + exact re-rank outside the Gaussian sweep regime."""
+    rs = np.random.RandomState(K + D)
+    e = rs.standard_normal((K, D)).astype(np.float32)
+    if kind == "clustered":
+        e = e * 3 + 5.0
+        x = e[rs.randint(0, K, size=N)] + 0.05 * rs.standard_normal((N, D)).astype(np.float32)
+    elif kind == "outlier":
+        e[::37] *= 100.0
+        x = rs.standard_normal((N, D)).astype(np.float32)
+    elif kind == "scaled":
+        x = 1e-3 * rs.standard_normal((N, D)).astype(np.float32)
+    else:
+        x = rs.standard_normal((N, D)).astype(np.float32)
+    x = x.astype(np.float32)
+    ref_idx, _ = O.vq_assign_c(x, e)
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).reshape(1, D, N, 1, 1)
+    q = make_quantizer(K, D, torch.from_numpy(e), 0, False)
+    from vqvae import _ops
+    o = _ops.default()
+    o.profile = []
+    try:
+        _, quant, idx = q(xt.to(DEV))
+        torch.cuda.synchronize()
+        assert [p[0] for p in o.profile][0] == "vq_assign_tc"
+    finally:
+        o.profile = None
+    got = idx.cpu().numpy().reshape(-1)
+    assert np.array_equal(got, ref_idx), int((got != ref_idx).sum())
+    assert np.array_equal(quant.cpu().numpy().reshape(D, N).T, x + (e[ref_idx] - x))
