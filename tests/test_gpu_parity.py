@@ -610,6 +610,7 @@ def test_thin_tensor_core_stack_matches_fp32(C, n, shape, tail):
     (65536, 64, 1024, "clustered"),    # latents close to their codes (a trained model): tiny distances, large norms
     (50000, 32, 512, "outlier"),       # a few codes with 100x the norm of the rest (dead codes after EMA updates)
     (40000, 128, 512, "scaled"),       # latents 1000x smaller than the codebook
+    (40000, 32, 300, "nonfinite"),     # NaN / inf / all-zero latent vectors: torch.argmin's answer (index 0 on all-NaN rows)
 ])
 def test_quantizer_tensor_core_path_regimes(N, D, K, kind):
     """Index exactness of the tensor-core candidate pass + exact re-rank outside the Gaussian sweep regime."""
@@ -623,6 +624,13 @@ def test_quantizer_tensor_core_path_regimes(N, D, K, kind):
         x = rs.standard_normal((N, D)).astype(np.float32)
     elif kind == "scaled":
         x = 1e-3 * rs.standard_normal((N, D)).astype(np.float32)
+    elif kind == "nonfinite":
+        x = rs.standard_normal((N, D)).astype(np.float32)
+        x[5:40] = np.nan
+        x[1000, 3] = np.nan
+        x[2000:2010] = np.inf
+        x[3000, 7] = -np.inf
+        x[4000:4100] = 0.0
     else:
         x = rs.standard_normal((N, D)).astype(np.float32)
     x = x.astype(np.float32)
@@ -640,4 +648,4 @@ def test_quantizer_tensor_core_path_regimes(N, D, K, kind):
         o.profile = None
     got = idx.cpu().numpy().reshape(-1)
     assert np.array_equal(got, ref_idx), int((got != ref_idx).sum())
-    assert np.array_equal(quant.cpu().numpy().reshape(D, N).T, x + (e[ref_idx] - x))
+    assert np.array_equal(quant.cpu().numpy().reshape(D, N).T, x + (e[ref_idx] - x), equal_nan=True)
