@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="downscaled_256x256x128", choices=sorted(bench.WORKLOADS))
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="volumes per step (the reference's --batch-size; it trained with 1 on 24 GB cards)")
     ap.add_argument("--graph", action="store_true", help="capture the whole step in one CUDA graph (vqvae.parallel.GraphedTrainingStep)")
     a = ap.parse_args()
     kind, shape = bench.WORKLOADS[a.workload]
@@ -26,9 +27,9 @@ def main():
     m = bench.build_model(kind).to(dev).train()
     for q in m.encoder.quantize:
         q.first_pass.fill_(1)
-    x = bench.synthetic_volume(shape, 42).to(dev)
+    x = torch.cat([bench.synthetic_volume(shape, 42 + i) for i in range(a.batch)]).to(dev)
     opt = m.configure_optimizers()
-    batch = (x, [shape[4]])
+    batch = (x, [shape[4]] * a.batch)
     torch.cuda.reset_peak_memory_stats()
     loss = training_step(m, opt, batch)          # warm-up (first-pass codebook init)
     torch.cuda.synchronize()
@@ -44,7 +45,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    print(json.dumps({"workload": a.workload, "train_step_ms": ms, "volumes_per_s": 1e3 / ms, "loss": float(loss),
+    print(json.dumps({"workload": a.workload, "train_step_ms": ms, "batch": a.batch, "volumes_per_s": a.batch * 1e3 / ms, "loss": float(loss),
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "steps": a.steps, "cuda_graph": bool(a.graph),
                       "note": "fwd composed (tensor-core convs where GEMM-shaped) + generic fp32 backward + fused Adam"}))
 
