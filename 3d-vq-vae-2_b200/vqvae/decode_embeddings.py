@@ -32,29 +32,37 @@ def decode_codes(model: VQVAE, codes) -> torch.Tensor:
     return _ops.default().elu_hu_rint(res, SCALE_VAL, SCALE_VAL)
 
 
+def iter_samples(db):
+    """The sampler's database (decode_embeddings.py:27-33): every bottom-level entry names the top-level entry it was
+    conditioned on.  Yields (bottom key, top key, (bottom codes, top codes), sampled_ok); a bottom map whose last slice is
+    all zeros is the PixelCNN failure mode the reference flags in the file name."""
+    bottom, top = db[0], db[1]
+    for key0, entry0 in bottom.items():
+        key1 = entry0["condition"]
+        ok = not bool(torch.all(entry0["data"][-1] == 0))
+        yield key0, key1, (entry0["data"], top[key1]["data"]), ok
+
+
+def output_name(out_path, ok: bool, key1, key0) -> str:
+    """decode_embeddings.py:50: <out>_<success|failure>_<top key>_<bottom key>.nrrd"""
+    return f"{out_path}_{'success' if ok else 'failure'}_{key1}_{key0}.nrrd"
+
+
 @torch.no_grad()
 def main(args: Namespace):
     from utils import write_nrrd
-    print("- Loading model weights")
     model = VQVAE.load_from_checkpoint(str(args.ckpt_path)).cuda().eval()
     db = torch.load(args.db_path, weights_only=False)
-    for embedding_0_key, embedding_0 in db[0].items():
-        embedding_1_key = embedding_0["condition"]
-        embedding_1 = db[1][embedding_1_key]
-        # issue where the pixelcnn samples 0's (decode_embeddings.py:32-33)
-        success = "failure" if torch.all(embedding_0["data"][-1] == 0) else "success"
-        print("- Performing forward pass")
-        res = decode_codes(model, (embedding_0["data"], embedding_1["data"]))
-        res = res.squeeze().cpu().numpy()
-        print("- Writing to nrrd")
-        write_nrrd(str(args.out_path) + f"_{success}_{str(embedding_1_key)}_{str(embedding_0_key)}.nrrd", res,
-                   header={"spacings": (0.976, 0.976, 3)})
-        print("- Done")
+    for n, (key0, key1, codes, ok) in enumerate(iter_samples(db)):
+        hu = decode_codes(model, codes).squeeze().cpu().numpy()
+        path = output_name(args.out_path, ok, key1, key0)
+        write_nrrd(path, hu, header={"spacings": (0.976, 0.976, 3)})
+        print(f"[{n}] {path}: {hu.shape}, HU range [{int(hu.min())}, {int(hu.max())}]")
 
 
 if __name__ == "__main__":
-    parser = ArgumentParser()
-    parser.add_argument("db_path", type=Path)
-    parser.add_argument("ckpt_path", type=Path)
-    parser.add_argument("out_path", type=Path, help="outpath without extension")
-    main(parser.parse_args())
+    cli = ArgumentParser(description=__doc__.splitlines()[0])
+    cli.add_argument("db_path", type=Path, help="torch-saved sampler output")
+    cli.add_argument("ckpt_path", type=Path, help="Lightning-format VQ-VAE checkpoint")
+    cli.add_argument("out_path", type=Path, help="output path without extension")
+    main(cli.parse_args())

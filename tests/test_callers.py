@@ -141,3 +141,15 @@ def test_elu_hu_rint_kernel_on_the_emulator():
     with use_emulator():
         got = _ops.default().elu_hu_rint(x)
     assert got.dtype == torch.int64 and np.array_equal(got.numpy(), ref)
+
+
+def test_decode_database_iteration_and_names():
+    from vqvae.decode_embeddings import iter_samples, output_name
+    db = {0: {"a": {"data": torch.ones(2, 2, 2, dtype=torch.long), "condition": "t1"},
+              "b": {"data": torch.zeros(2, 2, 2, dtype=torch.long), "condition": "t1"}},
+          1: {"t1": {"data": torch.full((1, 1, 1), 3, dtype=torch.long)}}}
+    got = list(iter_samples(db))
+    assert [(k0, k1, ok) for k0, k1, _, ok in got] == [("a", "t1", True), ("b", "t1", False)]     # all-zero last slice = sampler failure
+    assert torch.equal(got[0][2][1], db[1]["t1"]["data"])
+    assert output_name("out/vol", True, "t1", "a") == "out/vol_success_t1_a.nrrd"                # decode_embeddings.py:50
+    assert output_name("out/vol", False, "t1", "b") == "out/vol_failure_t1_b.nrrd"
