@@ -71,9 +71,10 @@ struct VqtCfg {
     // per (group, result buffer): ||x||^2 [128]; per (group, result buffer, half): row minimum [128], count [128],
     // columns [kVqtMaxCand][128] (u16), running minimum at push time [kVqtMaxCand][128]
     static constexpr size_t RES = (size_t)NG * 2 * 128 * 4 + (size_t)NG * 2 * 2 * 128 * (4 + 4 + 6 * kVqtMaxCand);
-    static constexpr size_t QUEUE = (size_t)4 * NG * 64 * 8;          // per load/epilogue warp: 64 (code | lane, distance) pairs
+    static constexpr size_t QUEUE = (size_t)4 * NG * 32 * 8;          // per load/epilogue warp: 32 (code | lane, distance) pairs
+    static constexpr size_t BEST = (size_t)NG * 2 * 128 * 4;           // resolved code per row, handed to the sweep warps for the gather
     static constexpr size_t TNORM = 128 * 4;                          // per-tile largest norms (K <= 16 384: 128 tiles)
-    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES + QUEUE + TNORM;
+    static constexpr size_t smem = 128 + (size_t)NSTAGE * STAGE + (size_t)NG * NABUF * AIMG + RES + QUEUE + TNORM + BEST;
     static constexpr size_t SMEM_LIMIT = 227 * 1024 - 1024;           // minus the static part (barriers, reduction scratch)
 };
 
@@ -271,6 +272,45 @@ __device__ __forceinline__ void vqt_group(VqtSweep &s, const uint32_t (&r)[16], 
     }
 }
 
+// codeword gather, straight-through value, squared error and EMA statistics of one latent vector for the dimensions
+// [dim0, dim0 + DH); the thread with dim0 == 0 also writes the index and the code count.  Returns the squared-error partial.
+template <int D, int DH>
+__device__ __forceinline__ float vqt_gather(const VqtParams &p, int64_t b, int64_t s, int best_k, int dim0, bool want_stats, bool dw_vec) {
+    const float *xs = p.x + ((size_t)b * D + dim0) * p.S + s;
+    float *qs = p.quant + ((size_t)b * D + dim0) * p.S + s;
+    const float *e = p.embed + (size_t)best_k * D + dim0;
+    float err = 0.0f;
+#pragma unroll 1
+    for (int ch = 0; ch < DH / 16; ++ch) {
+        float4 ev[4];
+        float xv[16];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) ev[jj] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 4 + jj);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) xv[jj] = __ldg(xs + (size_t)(ch * 16 + jj) * p.S);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const float qv[4] = {ev[jj].x, ev[jj].y, ev[jj].z, ev[jj].w};
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float df = qv[l] - xv[jj * 4 + l];
+                err = __fmaf_rn(df, df, err);
+                qs[(size_t)(ch * 16 + jj * 4 + l) * p.S] = __fadd_rn(xv[jj * 4 + l], __fsub_rn(qv[l], xv[jj * 4 + l]));    // layers.py:720, two roundings
+            }
+            if (want_stats) {
+                float *dst = p.dw + (size_t)best_k * D + dim0 + ch * 16 + jj * 4;
+                if (dw_vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xv[jj * 4]), "f"(xv[jj * 4 + 1]), "f"(xv[jj * 4 + 2]), "f"(xv[jj * 4 + 3]) : "memory");
+                else { atomicAdd(dst, xv[jj * 4]); atomicAdd(dst + 1, xv[jj * 4 + 1]); atomicAdd(dst + 2, xv[jj * 4 + 2]); atomicAdd(dst + 3, xv[jj * 4 + 3]); }
+            }
+        }
+    }
+    if (dim0 == 0) {
+        if (want_stats) atomicAdd(&p.counts[best_k], 1.0f);
+        p.idx[(size_t)b * p.S + s] = best_k;
+    }
+    return err;
+}
+
 template <int D>
 __global__ void __launch_bounds__(VqtCfg<D>::THREADS, 1)
 vq_tc_kernel(const __grid_constant__ VqtParams p) {
@@ -278,7 +318,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     constexpr int NT = Cfg::NT, KS = Cfg::KS, NG = Cfg::NG, NABUF = Cfg::NABUF, NSTAGE = Cfg::NSTAGE;
     VQ3D_DYN_SMEM(unsigned char, smem_raw);
     __shared__ __align__(8) uint64_t e_full[NSTAGE], e_empty[NSTAGE], a_full[NG][NABUF], a_empty[NG][NABUF],
-        d_full[NG][2], d_empty[NG][2], r_full[NG][2], r_empty[NG][2];
+        d_full[NG][2], d_empty[NG][2], r_full[NG][2], r_empty[NG][2], b_full[NG][2], b_empty[NG][2];
     __shared__ uint32_t tmem_slot;
     __shared__ double red[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -295,7 +335,8 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     // per-tile norms and (when it fits) the column -> code table live in shared memory: the epilogue warps look them up on
     // their critical path, where every global-memory round trip costs ~1 us
     float *s_tnorm = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(s_queue) + Cfg::QUEUE);
-    unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_tnorm + 128);
+    int *s_best = reinterpret_cast<int *>(s_tnorm + 128);                               // [NG][2][128]  (-1: row past the end)
+    unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_best + NG * 2 * 128);
     for (int i = threadIdx.x; i < p.Kpad / NT; i += Cfg::THREADS) s_tnorm[i] = __ldg(p.tnorm + i);
     if (p.perm_in_smem)
         for (int i = threadIdx.x; i < p.Kpad; i += Cfg::THREADS) s_perm[i] = (unsigned short)__ldg(p.perm + i);
@@ -312,6 +353,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             for (int b = 0; b < 2; ++b) {
                 mbarrier_init(&d_full[g][b], 1); mbarrier_init(&d_empty[g][b], 8);
                 mbarrier_init(&r_full[g][b], 8); mbarrier_init(&r_empty[g][b], 4);
+                mbarrier_init(&b_full[g][b], 4); mbarrier_init(&b_empty[g][b], 8);
             }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -330,6 +372,15 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
     const int my_super = nsuper > (int64_t)blockIdx.x ? (int)((nsuper - 1 - blockIdx.x) / gridDim.x + 1) : 0;
     const int ntiles = p.Kpad / NT;
     const bool resident = ntiles <= NSTAGE;
+    // who gathers: with few codebook tiles the load/epilogue warps pace the kernel, so the sweep warps (two threads per row,
+    // idle between super-tiles) take the gather; with many tiles the sweep is the critical path and the epilogue keeps it
+    const bool gather_in_sweep = ntiles <= 8;
+    const bool want_stats = p.counts != nullptr;
+#ifdef VQ3D_VQT_SCALAR_RED
+    const bool dw_vec = false;
+#else
+    const bool dw_vec = (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
+#endif
     double err_acc = 0.0;
 
     if (warp == 0) {
@@ -386,8 +437,23 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
         constexpr int HC = NT / 2;           // columns per half
         VqtSweep sw;
         uint32_t u = 0;
+        // ---- gather / straight-through / loss partial / statistics of super-tile j for this thread's half of the dimensions
+        // (the code index comes from the load/epilogue warps through s_best) ----
+        auto gather = [&](int j) {
+            const int rb = j & 1;
+            mbarrier_wait(&b_full[g][rb], ((uint32_t)j >> 1) & 1u);
+            const int best_k = s_best[(g * 2 + rb) * 128 + row];
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(&b_empty[g][rb]);
+            if (best_k < 0) return;
+            const int64_t sup = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+            const int64_t v = (sup * NG + g) * 128 + row;
+            const int64_t b = p.B == 1 ? 0 : v / p.S, s = v - b * p.S;
+            err_acc += (double)vqt_gather<D, D / 2>(p, b, s, best_k, half * (D / 2), want_stats, dw_vec);
+        };
         for (int i = 0; i < my_super; ++i) {
             const int rb = i & 1, ab = i % NABUF;
+            if (gather_in_sweep && i >= 2) gather(i - 2);
             VQT_TIMED_WAIT(6, mbarrier_wait(&r_empty[g][rb], (((uint32_t)i >> 1) & 1u) ^ 1u));
             VQT_TIMED_WAIT(7, mbarrier_wait(&a_full[g][ab], (uint32_t)(i / NABUF) & 1u));
             const float xx = s_xx[(g * 2 + rb) * 128 + row];
@@ -430,6 +496,8 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             __syncwarp();
             if (lane == 0) mbarrier_arrive(&r_full[g][rb]);
         }
+        if (gather_in_sweep)
+            for (int j = my_super >= 2 ? my_super - 2 : 0; j < my_super; ++j) gather(j);
     } else if (warp >= Cfg::LE_WARP0) {
         // ===== load / epilogue warps =====
         const int g = (warp - Cfg::LE_WARP0) >> 2, q = warp & 3, row = q * 32 + lane;
@@ -529,12 +597,12 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
             }
             phase(12);       // merge
             // exact re-rank of the vectors with several candidates, densely packed over the warp: the (vector, code) pairs
-            // go through a 64-entry queue, every lane evaluates one pair per round with the reference's arithmetic, the
+            // go through a 32-entry queue, every lane evaluates one pair per round with the reference's arithmetic, the
             // owners keep the lexicographic (sqrt(d2), k) minimum = the reference's argmin (first minimum)
             {
                 const bool requester = active && !ovf && best_k == 0x7fffffff && nc >= 1;
-                uint32_t *q_key = s_queue + (size_t)(warp - Cfg::LE_WARP0) * 128;
-                float *q_r = reinterpret_cast<float *>(q_key + 64);
+                uint32_t *q_key = s_queue + (size_t)(warp - Cfg::LE_WARP0) * 64;
+                float *q_r = reinterpret_cast<float *>(q_key + 32);
                 int remaining = requester ? nc : 0, cursor = 0;
                 float best_r = __int_as_float(0x7f800000);
 #pragma unroll 1
@@ -547,7 +615,7 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                     }
                     const int excl = incl - remaining;
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    int take = 64 - excl;
+                    int take = 32 - excl;
                     take = take < 0 ? 0 : (take > remaining ? remaining : take);
                     for (int j = 0; j < take; ++j) {
                         // next kept entry of this row's two lists
@@ -561,9 +629,9 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                         ++cursor;
                     }
                     __syncwarp();
-                    const int nq = total < 64 ? total : 64;
+                    const int nq = total < 32 ? total : 32;
 #pragma unroll 1
-                    for (int pp = lane; pp < 64; pp += 32) {
+                    for (int pp = lane; pp < 32; pp += 32) {
                         const uint32_t key = pp < nq ? q_key[pp] : 0u;
                         const int owner = (int)(key >> 16), k = (int)(key & 0xffffu);
                         const int64_t ob = __shfl_sync(0xffffffffu, b, owner), os = __shfl_sync(0xffffffffu, s, owner);
@@ -611,38 +679,17 @@ vq_tc_kernel(const __grid_constant__ VqtParams p) {
                 }
                 if (lane == src) best_k = k_best;
             }
-            if (active) {
-                const float *e = p.embed + (size_t)best_k * D;
-                float err = 0.0f;
-#pragma unroll 1
-                for (int ch = 0; ch < D / 32; ++ch) {
-                    float4 ev[8];
-                    float xv[32];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) ev[j] = __ldg(reinterpret_cast<const float4 *>(e) + ch * 8 + j);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) xv[j] = __ldg(xs + (size_t)(ch * 32 + j) * p.S);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float qv[4] = {ev[j].x, ev[j].y, ev[j].z, ev[j].w};
-#pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            const float df = qv[l] - xv[j * 4 + l];
-                            err = __fmaf_rn(df, df, err);
-                            p.quant[((size_t)b * D + ch * 32 + j * 4 + l) * p.S + s] = __fadd_rn(xv[j * 4 + l], __fsub_rn(qv[l], xv[j * 4 + l]));    // layers.py:720, two roundings
-                        }
-                        if (want_stats) {
-                            float *dst = p.dw + (size_t)best_k * D + ch * 32 + j * 4;
-                            if (dw_vec) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(xv[j * 4]), "f"(xv[j * 4 + 1]), "f"(xv[j * 4 + 2]), "f"(xv[j * 4 + 3]) : "memory");
-                            else { atomicAdd(dst, xv[j * 4]); atomicAdd(dst + 1, xv[j * 4 + 1]); atomicAdd(dst + 2, xv[j * 4 + 2]); atomicAdd(dst + 3, xv[j * 4 + 3]); }
-                        }
-                    }
-                }
-                if (want_stats) atomicAdd(&p.counts[best_k], 1.0f);
-                p.idx[(size_t)b * p.S + s] = best_k;
-                err_acc += (double)err;
+            // the resolved code goes to the sweep warps, which gather the codeword and write the outputs in their idle time
+            // between two super-tiles (two threads per row there, half of the dimensions each)
+            if (gather_in_sweep) {
+                VQT_TIMED_WAIT(9, mbarrier_wait(&b_empty[g][rb], (((uint32_t)i >> 1) & 1u) ^ 1u));
+                s_best[(g * 2 + rb) * 128 + row] = active ? best_k : -1;
+                __syncwarp();
+                if (lane == 0) mbarrier_arrive(&b_full[g][rb]);
+            } else if (active) {
+                err_acc += (double)vqt_gather<D, D>(p, b, s, best_k, 0, want_stats, dw_vec);
             }
-            phase(14);       // fallback scan + gather + stores
+            phase(14);       // fallback scan + hand-over
             if (i + 2 < my_super) stage(i + 2);
             phase(15);       // stage (incl. its a_empty wait)
         }
