@@ -249,7 +249,11 @@ class Ops:
         so = y[0, 0].numel()
         meta = dict(nbytes=4 * B * (Cin * H * W * Z + Cout * so * (2 if residual is not None else 1)),
                     flops=2 * B * Cin * Cout * k ** 3 * so, tag=f"{Cin}->{Cout} k{k}s{stride} @{H}x{W}x{Z}")
-        if self.precision == "bf16" and not force_fp32 and Cout >= 8 and Cin * k ** 3 >= 32 and B * so >= self.tc_min_voxels:
+        # k3 "same" convolutions with few input channels on big tensors: the shared-memory tiled fp32 kernel beats the gather-based
+        # tensor-core kernel (measured 9->9 @64x64x32: 35 vs 131 us), and is exact
+        tiled_simt = k == 3 and stride == 1 and pad == 1 and Cin <= 16 and B * so >= 16384
+        if (self.precision == "bf16" and not force_fp32 and not tiled_simt and Cout >= 8 and Cin * k ** 3 >= 32
+                and B * so >= self.tc_min_voxels):
             need = self.lib.vq3d_conv3d_tc_workspace(C.byref(d))       # > 0: few voxels, long K -> split-K through a workspace
             ws = self._workspace(need, x1.device) if need else None
             if self._call("conv3d_tc", self.lib.vq3d_conv3d_tc, (C.byref(d), self._p(ws), need, self.stream()),
