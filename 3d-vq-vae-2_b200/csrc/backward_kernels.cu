@@ -300,11 +300,15 @@ adam_amsgrad_dev_kernel(float *__restrict__ p, const float *__restrict__ g, floa
 // tile (all C_in) and the scaled output-gradient tile (all C_out) of a 4 x 4 x 32 output box once, then every thread
 // accumulates its APT (co, ci, tap) products over the box (2 LDS + 1 FMA per product; the generic kernel re-reads both
 // operands from global memory for every (co, ci) pair) and adds them to gw with one atomic each.
-constexpr int kWgTH = 4, kWgTW = 4, kWgTZ = 32, kWgThreads = 256;
+// The box is 512 voxels whatever the depth: 4 x 4 x 32 for deep tensors, 8 x 8 x 8 and 16 x 16 x 2 for the shallow top levels
+// (a 32-deep box on an 8 x 8 x 2 volume would be 15/16 padding).
+constexpr int kWgThreads = 256;
+template <int TZ> struct WgTile { static constexpr int TH = TZ == 32 ? 4 : (TZ == 8 ? 8 : 16), TW = TH; };
 
-template <int APT>
+template <int APT, int kWgTZ>
 __global__ void __launch_bounds__(kWgThreads)
 conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int cic) {
+    constexpr int kWgTH = WgTile<kWgTZ>::TH, kWgTW = WgTile<kWgTZ>::TW;
     VQ3D_DYN_SMEM(float, smem);
     // blockIdx.y selects a chunk of `cic` input channels (the accumulators of one chunk fit the CTA's registers and its
     // halo tile fits shared memory); Cin below is the chunk's channel count, ci0 its first channel
@@ -375,7 +379,7 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
 #pragma unroll 1
         for (int dw = 0; dw < kWgTW; ++dw) {
             const float *gb = sg + (dh * kWgTW + dw) * kWgTZ, *ub = su + (dh * HW + dw) * HZ;
-#pragma unroll 8
+#pragma unroll(kWgTZ < 8 ? kWgTZ : 8)
             for (int dz = 0; dz < kWgTZ; ++dz)
 #pragma unroll
                 for (int j = 0; j < APT; ++j) acc[j] = __fmaf_rn(gb[gofs[j] + dz], ub[uofs[j] + dz], acc[j]);
@@ -459,22 +463,24 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
     // tiled weight gradient: input channels in chunks whose accumulators (<= 16 per thread) and halo tile (<= 150 KB with the
     // output-gradient tile) fit one CTA
     const int k3 = d->k * d->k * d->k;
-    const size_t wg_halo = (size_t)(kWgTH + d->k - 1) * (kWgTW + d->k - 1) * (kWgTZ + d->k - 1) * sizeof(float);
-    const size_t wg_gtile = (size_t)d->Cout * kWgTH * kWgTW * kWgTZ * sizeof(float);
+    const int wtz = d->Z >= 32 ? 32 : (d->Z >= 8 ? 8 : 2);
+    const int wth = wtz == 32 ? 4 : (wtz == 8 ? 8 : 16);
+    const size_t wg_halo = (size_t)(wth + d->k - 1) * (wth + d->k - 1) * (wtz + d->k - 1) * sizeof(float);
+    const size_t wg_gtile = (size_t)d->Cout * 512 * sizeof(float);
     int cic = d->Cout * k3 <= 16 * kWgThreads ? (16 * kWgThreads) / (d->Cout * k3) : 0;
     if (cic > Cin) cic = Cin;
     while (cic > 0 && wg_gtile + (size_t)cic * wg_halo > 150 * 1024) --cic;
     if (p.gw && cic > 0 && d->stride == 1 && (d->k == 1 || d->k == 3) && d->pad == (d->k - 1) / 2 &&
         (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
-        const int tH = (int)ceil_div(d->H, kWgTH), tW = (int)ceil_div(d->W, kWgTW), tZ = (int)ceil_div(d->Z, kWgTZ);
+        const int tH = (int)ceil_div(d->H, wth), tW = (int)ceil_div(d->W, wth), tZ = (int)ceil_div(d->Z, wtz);
         const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ), (unsigned)ceil_div(Cin, cic));
         const size_t wg_smem = wg_gtile + (size_t)cic * wg_halo;
         const int apt = (int)ceil_div((int64_t)d->Cout * cic * k3, kWgThreads);
-        if (apt <= 1) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<1>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
-        else if (apt <= 2) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<2>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
-        else if (apt <= 4) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<4>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
-        else if (apt <= 9) rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<9>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
-        else rc = launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<16>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic);
+#define VQ3D_WG_LAUNCH(APT, TZ) launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<APT, TZ>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic)
+#define VQ3D_WG_BY_APT(TZ) (apt <= 1 ? VQ3D_WG_LAUNCH(1, TZ) : apt <= 2 ? VQ3D_WG_LAUNCH(2, TZ) : apt <= 4 ? VQ3D_WG_LAUNCH(4, TZ) : apt <= 9 ? VQ3D_WG_LAUNCH(9, TZ) : VQ3D_WG_LAUNCH(16, TZ))
+        rc = wtz == 32 ? VQ3D_WG_BY_APT(32) : (wtz == 8 ? VQ3D_WG_BY_APT(8) : VQ3D_WG_BY_APT(2));
+#undef VQ3D_WG_BY_APT
+#undef VQ3D_WG_LAUNCH
         if (rc) return rc;
     } else if (p.gw) {
         int64_t chunks = ceil_div((int64_t)d->B * So, 128 * 8);
