@@ -305,7 +305,7 @@ adam_amsgrad_dev_kernel(float *__restrict__ p, const float *__restrict__ g, floa
 constexpr int kWgThreads = 256;
 template <int TZ> struct WgTile { static constexpr int TH = TZ == 32 ? 4 : (TZ == 8 ? 8 : 16), TW = TH; };
 
-template <int APT, int kWgTZ>
+template <int APT, int kWgTZ, int ST>          // ST: convolution stride (1 or 2); the box is a box of OUTPUT voxels
 __global__ void __launch_bounds__(kWgThreads)
 conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int cic) {
     constexpr int kWgTH = WgTile<kWgTZ>::TH, kWgTW = WgTile<kWgTZ>::TW;
@@ -314,7 +314,7 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
     // halo tile fits shared memory); Cin below is the chunk's channel count, ci0 its first channel
     const int CinAll = p.C1 + p.C2, ci0 = blockIdx.y * cic;
     const int Cin = min(cic, CinAll - ci0), k = p.k, k3 = k * k * k, pad = p.pad;
-    const int HH = kWgTH + k - 1, HW = kWgTW + k - 1, HZ = kWgTZ + k - 1, HV = HH * HW * HZ, TV = kWgTH * kWgTW * kWgTZ;
+    const int HH = (kWgTH - 1) * ST + k, HW = (kWgTW - 1) * ST + k, HZ = (kWgTZ - 1) * ST + k, HV = HH * HW * HZ, TV = kWgTH * kWgTW * kWgTZ;
     float *su = smem, *sg = smem + (size_t)Cin * HV;
     int tile = blockIdx.x;
     const int tz = tile % tilesZ; tile /= tilesZ;
@@ -322,23 +322,20 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
     const int th = tile % tilesH;
     const int b = tile / tilesH;
     const int h0 = th * kWgTH, w0 = tw * kWgTW, z0 = tz * kWgTZ;
-    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const int64_t S = (int64_t)p.H * p.W * p.Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
     const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
     for (int i = threadIdx.x; i < Cin * HV; i += kWgThreads) {
         const int ci = i / HV;
         int r = i - ci * HV;
         const int hh = r / (HW * HZ); r -= hh * HW * HZ;
         const int ww = r / HZ, zz = r - ww * HZ;
-        int ih = h0 - pad + hh, iw = w0 - pad + ww, iz = z0 - pad + zz;
-        bool ok = true;
-        if (p.circ) {
-            ih = ih < 0 ? ih + p.H : (ih >= p.H ? ih - p.H : ih);
-            iw = iw < 0 ? iw + p.W : (iw >= p.W ? iw - p.W : iw);
-            iz = iz < 0 ? iz + p.Z : (iz >= p.Z ? iz - p.Z : iz);
-            ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;      // boxes past the edge (partial tiles)
-        } else {
-            ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;
+        int ih = h0 * ST - pad + hh, iw = w0 * ST - pad + ww, iz = z0 * ST - pad + zz;
+        if (p.circ) {                      // boxes may reach far past the edge (partial tiles): full modulo
+            ih %= p.H; if (ih < 0) ih += p.H;
+            iw %= p.W; if (iw < 0) iw += p.W;
+            iz %= p.Z; if (iz < 0) iz += p.Z;
         }
+        const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;
         float u = 0.0f;
         if (ok) {
             const int cg = ci0 + ci;
@@ -354,7 +351,7 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
         const int dh = r / (kWgTW * kWgTZ); r -= dh * kWgTW * kWgTZ;
         const int dw = r / kWgTZ, dz = r - dw * kWgTZ;
         const int oh = h0 + dh, ow = w0 + dw, oz = z0 + dz;
-        sg[i] = (oh < p.H && ow < p.W && oz < p.Z) ? p.gy[((size_t)b * p.Cout + co) * S + ((size_t)oh * p.W + ow) * p.Z + oz] * sc : 0.0f;
+        sg[i] = (oh < p.Ho && ow < p.Wo && oz < p.Zo) ? p.gy[((size_t)b * p.Cout + co) * So + ((size_t)oh * p.Wo + ow) * p.Zo + oz] * sc : 0.0f;
     }
     __syncthreads();
     const int naccum = p.Cout * Cin * k3;
@@ -378,11 +375,11 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
     for (int dh = 0; dh < kWgTH; ++dh)
 #pragma unroll 1
         for (int dw = 0; dw < kWgTW; ++dw) {
-            const float *gb = sg + (dh * kWgTW + dw) * kWgTZ, *ub = su + (dh * HW + dw) * HZ;
+            const float *gb = sg + (dh * kWgTW + dw) * kWgTZ, *ub = su + (dh * ST * HW + dw * ST) * HZ;
 #pragma unroll(kWgTZ < 8 ? kWgTZ : 8)
             for (int dz = 0; dz < kWgTZ; ++dz)
 #pragma unroll
-                for (int j = 0; j < APT; ++j) acc[j] = __fmaf_rn(gb[gofs[j] + dz], ub[uofs[j] + dz], acc[j]);
+                for (int j = 0; j < APT; ++j) acc[j] = __fmaf_rn(gb[gofs[j] + dz], ub[uofs[j] + dz * ST], acc[j]);
         }
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
@@ -463,22 +460,24 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
     // tiled weight gradient: input channels in chunks whose accumulators (<= 16 per thread) and halo tile (<= 150 KB with the
     // output-gradient tile) fit one CTA
     const int k3 = d->k * d->k * d->k;
-    const int wtz = d->Z >= 32 ? 32 : (d->Z >= 8 ? 8 : 2);
+    const int wtz = p.Zo >= 32 ? 32 : (p.Zo >= 8 ? 8 : 2);
     const int wth = wtz == 32 ? 4 : (wtz == 8 ? 8 : 16);
-    const size_t wg_halo = (size_t)(wth + d->k - 1) * (wth + d->k - 1) * (wtz + d->k - 1) * sizeof(float);
+    const int st = d->stride;
+    const size_t wg_halo = (size_t)((wth - 1) * st + d->k) * ((wth - 1) * st + d->k) * ((wtz - 1) * st + d->k) * sizeof(float);
     const size_t wg_gtile = (size_t)d->Cout * 512 * sizeof(float);
     int cic = d->Cout * k3 <= 16 * kWgThreads ? (16 * kWgThreads) / (d->Cout * k3) : 0;
     if (cic > Cin) cic = Cin;
     while (cic > 0 && wg_gtile + (size_t)cic * wg_halo > 150 * 1024) --cic;
-    if (p.gw && cic > 0 && d->stride == 1 && (d->k == 1 || d->k == 3) && d->pad == (d->k - 1) / 2 &&
-        (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
-        const int tH = (int)ceil_div(d->H, wth), tW = (int)ceil_div(d->W, wth), tZ = (int)ceil_div(d->Z, wtz);
+    if (p.gw && cic > 0 && (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
+        const int tH = (int)ceil_div(p.Ho, wth), tW = (int)ceil_div(p.Wo, wth), tZ = (int)ceil_div(p.Zo, wtz);
         const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ), (unsigned)ceil_div(Cin, cic));
         const size_t wg_smem = wg_gtile + (size_t)cic * wg_halo;
         const int apt = (int)ceil_div((int64_t)d->Cout * cic * k3, kWgThreads);
-#define VQ3D_WG_LAUNCH(APT, TZ) launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<APT, TZ>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic)
-#define VQ3D_WG_BY_APT(TZ) (apt <= 1 ? VQ3D_WG_LAUNCH(1, TZ) : apt <= 2 ? VQ3D_WG_LAUNCH(2, TZ) : apt <= 4 ? VQ3D_WG_LAUNCH(4, TZ) : apt <= 9 ? VQ3D_WG_LAUNCH(9, TZ) : VQ3D_WG_LAUNCH(16, TZ))
-        rc = wtz == 32 ? VQ3D_WG_BY_APT(32) : (wtz == 8 ? VQ3D_WG_BY_APT(8) : VQ3D_WG_BY_APT(2));
+#define VQ3D_WG_LAUNCH(APT, TZ, ST) launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<APT, TZ, ST>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic)
+#define VQ3D_WG_BY_APT(TZ, ST) (apt <= 1 ? VQ3D_WG_LAUNCH(1, TZ, ST) : apt <= 2 ? VQ3D_WG_LAUNCH(2, TZ, ST) : apt <= 4 ? VQ3D_WG_LAUNCH(4, TZ, ST) : apt <= 9 ? VQ3D_WG_LAUNCH(9, TZ, ST) : VQ3D_WG_LAUNCH(16, TZ, ST))
+#define VQ3D_WG_BY_TZ(ST) (wtz == 32 ? VQ3D_WG_BY_APT(32, ST) : (wtz == 8 ? VQ3D_WG_BY_APT(8, ST) : VQ3D_WG_BY_APT(2, ST)))
+        rc = st == 1 ? VQ3D_WG_BY_TZ(1) : VQ3D_WG_BY_TZ(2);
+#undef VQ3D_WG_BY_TZ
 #undef VQ3D_WG_BY_APT
 #undef VQ3D_WG_LAUNCH
         if (rc) return rc;
