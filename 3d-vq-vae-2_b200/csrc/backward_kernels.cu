@@ -305,7 +305,9 @@ adam_amsgrad_dev_kernel(float *__restrict__ p, const float *__restrict__ g, floa
 constexpr int kWgThreads = 256;
 template <int TZ> struct WgTile { static constexpr int TH = TZ == 32 ? 4 : (TZ == 8 ? 8 : 16), TW = TH; };
 
-template <int APT, int kWgTZ, int ST>          // ST: convolution stride (1 or 2); the box is a box of OUTPUT voxels
+constexpr int kWgCOB = 4, kWgTB = 4;      // accumulator block of a thread: 4 output channels x 4 (input channel, tap) pairs
+
+template <int kWgTZ, int ST>              // ST: convolution stride (1 or 2); the box is a box of OUTPUT voxels
 __global__ void __launch_bounds__(kWgThreads)
 conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int cic) {
     constexpr int kWgTH = WgTile<kWgTZ>::TH, kWgTW = WgTile<kWgTZ>::TW;
@@ -354,39 +356,57 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
         sg[i] = (oh < p.Ho && ow < p.Wo && oz < p.Zo) ? p.gy[((size_t)b * p.Cout + co) * So + ((size_t)oh * p.Wo + ow) * p.Zo + oz] * sc : 0.0f;
     }
     __syncthreads();
-    const int naccum = p.Cout * Cin * k3;
-    int gofs[APT], uofs[APT];
-    float acc[APT];
+    // thread -> (block of kWgCOB output channels, block of kWgTB (input channel, tap) pairs): per voxel kWgCOB + kWgTB shared
+    // loads feed kWgCOB * kWgTB FMAs
+    const int nrt = Cin * k3;                                   // (ci, tap) pairs of this chunk
+    const int nrb = (nrt + kWgTB - 1) / kWgTB;
+    const int cb = threadIdx.x / nrb, rb = threadIdx.x - cb * nrb;
+    const bool worker = cb * kWgCOB < p.Cout;                    // the host sizes the chunk so that every block has a thread
+    int gofs[kWgCOB], uofs[kWgTB];
+    float acc[kWgCOB][kWgTB];
 #pragma unroll
-    for (int j = 0; j < APT; ++j) {
-        int a = threadIdx.x + j * kWgThreads;
-        if (a >= naccum) a = 0;                       // computed, never written
-        const int co = a / (Cin * k3);
-        int rem = a - co * Cin * k3;
-        const int ci = rem / k3;
-        rem -= ci * k3;
+    for (int jc = 0; jc < kWgCOB; ++jc) {
+        const int co = min(cb * kWgCOB + jc, p.Cout - 1);
+        gofs[jc] = co * TV;
+#pragma unroll
+        for (int jt = 0; jt < kWgTB; ++jt) acc[jc][jt] = 0.0f;
+    }
+#pragma unroll
+    for (int jt = 0; jt < kWgTB; ++jt) {
+        const int rt = min(rb * kWgTB + jt, nrt - 1);
+        const int ci = rt / k3;
+        int rem = rt - ci * k3;
         const int kh = rem / (k * k); rem -= kh * k * k;
         const int kw = rem / k, kz = rem - kw * k;
-        gofs[j] = co * TV;
-        uofs[j] = ci * HV + (kh * HW + kw) * HZ + kz;
-        acc[j] = 0.0f;
+        uofs[jt] = ci * HV + (kh * HW + kw) * HZ + kz;
     }
+    if (worker) {
 #pragma unroll 1
-    for (int dh = 0; dh < kWgTH; ++dh)
+        for (int dh = 0; dh < kWgTH; ++dh)
 #pragma unroll 1
-        for (int dw = 0; dw < kWgTW; ++dw) {
-            const float *gb = sg + (dh * kWgTW + dw) * kWgTZ, *ub = su + (dh * ST * HW + dw * ST) * HZ;
-#pragma unroll(kWgTZ < 8 ? kWgTZ : 8)
-            for (int dz = 0; dz < kWgTZ; ++dz)
+            for (int dw = 0; dw < kWgTW; ++dw) {
+                const float *gb = sg + (dh * kWgTW + dw) * kWgTZ, *ub = su + (dh * ST * HW + dw * ST) * HZ;
+#pragma unroll(kWgTZ < 4 ? kWgTZ : 4)
+                for (int dz = 0; dz < kWgTZ; ++dz) {
+                    float gv[kWgCOB], uv[kWgTB];
 #pragma unroll
-                for (int j = 0; j < APT; ++j) acc[j] = __fmaf_rn(gb[gofs[j] + dz], ub[uofs[j] + dz * ST], acc[j]);
-        }
+                    for (int jc = 0; jc < kWgCOB; ++jc) gv[jc] = gb[gofs[jc] + dz];
 #pragma unroll
-    for (int j = 0; j < APT; ++j) {
-        const int a = threadIdx.x + j * kWgThreads;
-        if (a < naccum) {
-            const int co = a / (Cin * k3), rem = a - co * Cin * k3;          // (co, local ci, tap) -> the weight's own layout
-            atomicAdd(p.gw + ((size_t)co * CinAll + ci0) * k3 + rem, acc[j]);
+                    for (int jt = 0; jt < kWgTB; ++jt) uv[jt] = ub[uofs[jt] + dz * ST];
+#pragma unroll
+                    for (int jc = 0; jc < kWgCOB; ++jc)
+#pragma unroll
+                        for (int jt = 0; jt < kWgTB; ++jt) acc[jc][jt] = __fmaf_rn(gv[jc], uv[jt], acc[jc][jt]);
+                }
+            }
+#pragma unroll
+        for (int jc = 0; jc < kWgCOB; ++jc) {
+            const int co = cb * kWgCOB + jc;
+#pragma unroll
+            for (int jt = 0; jt < kWgTB; ++jt) {
+                const int rt = rb * kWgTB + jt;
+                if (co < p.Cout && rt < nrt) atomicAdd(p.gw + ((size_t)co * CinAll + ci0) * k3 + rt, acc[jc][jt]);     // (co, local ci, tap) -> the weight's layout
+            }
         }
     }
 }
@@ -465,20 +485,18 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
     const int st = d->stride;
     const size_t wg_halo = (size_t)((wth - 1) * st + d->k) * ((wth - 1) * st + d->k) * ((wtz - 1) * st + d->k) * sizeof(float);
     const size_t wg_gtile = (size_t)d->Cout * 512 * sizeof(float);
-    int cic = d->Cout * k3 <= 16 * kWgThreads ? (16 * kWgThreads) / (d->Cout * k3) : 0;
+    const int co_blocks = (d->Cout + kWgCOB - 1) / kWgCOB;
+    int cic = co_blocks <= kWgThreads ? ((kWgThreads / co_blocks) * kWgTB) / k3 : 0;     // (ci, tap) blocks per output-channel block
     if (cic > Cin) cic = Cin;
     while (cic > 0 && wg_gtile + (size_t)cic * wg_halo > 150 * 1024) --cic;
     if (p.gw && cic > 0 && (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
         const int tH = (int)ceil_div(p.Ho, wth), tW = (int)ceil_div(p.Wo, wth), tZ = (int)ceil_div(p.Zo, wtz);
         const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ), (unsigned)ceil_div(Cin, cic));
         const size_t wg_smem = wg_gtile + (size_t)cic * wg_halo;
-        const int apt = (int)ceil_div((int64_t)d->Cout * cic * k3, kWgThreads);
-#define VQ3D_WG_LAUNCH(APT, TZ, ST) launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<APT, TZ, ST>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic)
-#define VQ3D_WG_BY_APT(TZ, ST) (apt <= 1 ? VQ3D_WG_LAUNCH(1, TZ, ST) : apt <= 2 ? VQ3D_WG_LAUNCH(2, TZ, ST) : apt <= 4 ? VQ3D_WG_LAUNCH(4, TZ, ST) : apt <= 9 ? VQ3D_WG_LAUNCH(9, TZ, ST) : VQ3D_WG_LAUNCH(16, TZ, ST))
-#define VQ3D_WG_BY_TZ(ST) (wtz == 32 ? VQ3D_WG_BY_APT(32, ST) : (wtz == 8 ? VQ3D_WG_BY_APT(8, ST) : VQ3D_WG_BY_APT(2, ST)))
+#define VQ3D_WG_LAUNCH(TZ, ST) launch("conv3d_wgrad_tiled", conv3d_wgrad_tiled_kernel<TZ, ST>, grid, dim3(kWgThreads), wg_smem, stream, p, tH, tW, tZ, cic)
+#define VQ3D_WG_BY_TZ(ST) (wtz == 32 ? VQ3D_WG_LAUNCH(32, ST) : (wtz == 8 ? VQ3D_WG_LAUNCH(8, ST) : VQ3D_WG_LAUNCH(2, ST)))
         rc = st == 1 ? VQ3D_WG_BY_TZ(1) : VQ3D_WG_BY_TZ(2);
 #undef VQ3D_WG_BY_TZ
-#undef VQ3D_WG_BY_APT
 #undef VQ3D_WG_LAUNCH
         if (rc) return rc;
     } else if (p.gw) {
