@@ -16,6 +16,9 @@
 
 namespace vq3d {
 
+#ifndef VQ3D_ROW_PACK_C8
+#define VQ3D_ROW_PACK_C8 1
+#endif
 template <int C> struct RowThreads { static constexpr int value = C >= 8 ? 256 : 512; };   // wide variants need the registers
 
 struct RowParams {
@@ -43,10 +46,11 @@ struct RowSmem {
 };
 
 template <int C, int CB, bool OUTC>
-__global__ void __launch_bounds__(RowThreads<C>::value)
+__global__ void __launch_bounds__(RowThreads<C>::value, 2)
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
     constexpr int kRowThreads = RowThreads<C>::value;
+    constexpr bool kPackAC = C < 8 || VQ3D_ROW_PACK_C8;   // FFMA2 in conv1 / conv3 too (conv2 always when CB is even)
     VQ3D_DYN_SMEM(float, smem);
     float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_wo = smem + SM::wo, *s_t1 = smem + SM::tile;
     const int tid = threadIdx.x;
@@ -91,6 +95,28 @@ preact_row_kernel(RowParams p) {
             for (int c = 0; c < C; ++c) cur[c] = nxt[c];
             if (rs + nslots < nrows_in) issue(rs + nslots);
             float t[CB][4];
+            if constexpr (CB % 2 == 0 && kPackAC) {
+                float2 t2[CB / 2][4];
+#pragma unroll
+                for (int cp = 0; cp < CB / 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) t2[cp][k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float4 v = cur[c];
+                    const float a[4] = {elu1(v.x + b1a) + b1b, elu1(v.y + b1a) + b1b, elu1(v.z + b1a) + b1b, elu1(v.w + b1a) + b1b};
+#pragma unroll
+                    for (int cp = 0; cp < CB / 2; ++cp) {
+                        const float2 w = *reinterpret_cast<const float2 *>(s_w1 + c * CB + 2 * cp);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) t2[cp][k] = ffma2_bcast(w, a[k], t2[cp][k]);
+                    }
+                }
+#pragma unroll
+                for (int cp = 0; cp < CB / 2; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { t[2 * cp][k] = t2[cp][k].x; t[2 * cp + 1][k] = t2[cp][k].y; }
+            } else {
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
@@ -105,6 +131,7 @@ preact_row_kernel(RowParams p) {
                     t[cb][0] = __fmaf_rn(w, a0, t[cb][0]); t[cb][1] = __fmaf_rn(w, a1, t[cb][1]);
                     t[cb][2] = __fmaf_rn(w, a2, t[cb][2]); t[cb][3] = __fmaf_rn(w, a3, t[cb][3]);
                 }
+            }
             }
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb) {
@@ -127,6 +154,40 @@ preact_row_kernel(RowParams p) {
         const int oh = oh0 + lh, ow = ow0 + lw;
         if (oh >= p.H || ow >= p.W) continue;
         float acc[CB][4];
+        if constexpr (CB % 2 == 0) {
+            // two branch channels per FFMA2 (w pair from shared memory, the window value broadcast)
+            constexpr int CP = CB / 2;
+            float2 acc2[CP][4];
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc2[cp][k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float *row = s_t1 + ((size_t)ci * nrows_in + (lh + kh) * IW + lw + kw) * ZP + 4 * zq;
+                        const float4 m = *reinterpret_cast<const float4 *>(row + 4);
+                        const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                        const float2 *wt = reinterpret_cast<const float2 *>(s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB);
+#pragma unroll
+                        for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                            for (int cp = 0; cp < CP; ++cp) {
+                                const float2 w = wt[kz * CP + cp];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) acc2[cp][k] = ffma2_bcast(w, r[k + kz], acc2[cp][k]);
+                            }
+                    }
+                }
+            }
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc[2 * cp][k] = acc2[cp][k].x; acc[2 * cp + 1][k] = acc2[cp][k].y; }
+        } else {
 #pragma unroll
         for (int co = 0; co < CB; ++co)
 #pragma unroll
@@ -152,6 +213,7 @@ preact_row_kernel(RowParams p) {
                 }
             }
         }
+        }
 #pragma unroll
         for (int co = 0; co < CB; ++co)
 #pragma unroll
@@ -159,14 +221,22 @@ preact_row_kernel(RowParams p) {
         const size_t off = ((size_t)oh * p.W + ow) * Z + 4 * zq;
         float o4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float out[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int cq = 0; cq < C / 2; ++cq) {
+            float2 out2[4];                 // conv3 for the output channel pair (2cq, 2cq+1)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out2[k] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb) {
-                const float w = s_w3[cb * C + c];
+                const float2 w = make_float2(s_w3[cb * C + 2 * cq], s_w3[cb * C + 2 * cq + 1]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+                for (int k = 0; k < 4; ++k) out2[k] = ffma2_bcast_if<kPackAC>(w, acc[cb][k], out2[k]);
             }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int c = 2 * cq + ch;
+            float out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] = ch ? out2[k].y : out2[k].x;
             const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off));
             float4 yv;
             yv.x = __fmaf_rn(out[0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[1], sc, b4) + xv.y;
@@ -178,6 +248,7 @@ preact_row_kernel(RowParams p) {
             } else {
                 *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off) = yv;
             }
+        }
         }
         if (OUTC) {
             const float bo = s_wo[C];
@@ -633,6 +704,39 @@ preact_up_row_kernel(UpParams p) {
         const int oh = oh0 + lho, ow = ow0 + lwo;
         if (oh >= Ho || ow >= Wo) continue;
         float acc[CB][4];
+        if constexpr (CB % 2 == 0) {
+            constexpr int CP = CB / 2;      // two branch channels per FFMA2
+            float2 acc2[CP][4];
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc2[cp][k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float *row = s_hi + ((size_t)ci * HR + (lho + kh) * IW + lwo + kw) * ZPH + 4 * q;
+                        const float4 m = *reinterpret_cast<const float4 *>(row + 4);
+                        const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                        const float2 *wt = reinterpret_cast<const float2 *>(s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB);
+#pragma unroll
+                        for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                            for (int cp = 0; cp < CP; ++cp) {
+                                const float2 w = wt[kz * CP + cp];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) acc2[cp][k] = ffma2_bcast(w, r[k + kz], acc2[cp][k]);
+                            }
+                    }
+                }
+            }
+#pragma unroll
+            for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc[2 * cp][k] = acc2[cp][k].x; acc[2 * cp + 1][k] = acc2[cp][k].y; }
+        } else {
 #pragma unroll
         for (int co = 0; co < CB; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = 0.0f;
 #pragma unroll
@@ -655,6 +759,7 @@ preact_up_row_kernel(UpParams p) {
                         }
                 }
             }
+        }
         }
 #pragma unroll
         for (int co = 0; co < CB; ++co)

@@ -75,6 +75,37 @@ __device__ __forceinline__ float ld_scalar(const float *p, float dflt) { return 
 // ELU(alpha=1), F.elu of layers.py:117 / model.py:120.  exp(x)-1 like ATen's kernel.
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v) - 1.0f); }
 
+// Packed fp32 FMA (sm_100 `fma.rn.f32x2` -> SASS FFMA2 with a scalar-broadcast multiplicand): two independent
+// round-to-nearest FMAs in ONE issue slot, bit-identical to two __fmaf_rn.  The thin-channel SIMT kernels are
+// instruction-issue bound, so pairing two output channels per instruction frees issue slots.
+#ifndef VQ3D_FFMA2
+#define VQ3D_FFMA2 1
+#endif
+__device__ __forceinline__ float2 ffma2_bcast(float2 w, float x, float2 acc) {
+#if defined(VQ3D_EMU) || !VQ3D_FFMA2
+    acc.x = __fmaf_rn(w.x, x, acc.x);
+    acc.y = __fmaf_rn(w.y, x, acc.y);
+    return acc;
+#else
+    unsigned long long rw, rx, ra, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rw) : "f"(w.x), "f"(w.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rx) : "f"(x));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rw), "l"(rx), "l"(ra));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+    return r;
+#endif
+}
+
+template <bool PACKED>
+__device__ __forceinline__ float2 ffma2_bcast_if(float2 w, float x, float2 acc) {
+    if constexpr (PACKED) return ffma2_bcast(w, x, acc);
+    acc.x = __fmaf_rn(w.x, x, acc.x);
+    acc.y = __fmaf_rn(w.y, x, acc.y);
+    return acc;
+}
+
 __host__ __device__ __forceinline__ int wrap(int i, int n) {  // circular index, |i| < 2n
     return i < 0 ? i + n : (i >= n ? i - n : i);
 }
