@@ -286,8 +286,8 @@ static int launch_row(const vq3d_preact_desc *d, void *stream) {
 // ---------------------------------------------------------------------------------------------------
 // 'down' blocks at the big levels (4 -> 4 -> 8 at 512^3, 8 -> 8 -> 16 at 256^3; layers.py:124-126,164-171):
 // conv1 1x1, conv2 k4 s2 circular, conv3 1x1, skip k2 s2.  Same depth-row organisation: stage A computes t1
-// for the (2t+2)^2 input rows of a (t x t) output-row tile over the FULL depth and keeps the raw centre rows
-// for the skip convolution; stage B gives each thread 4 consecutive output z of ONE branch channel (the CB
+// for the (2t+2)^2 input rows of a (t x t) output-row tile over the FULL depth (the skip convolution re-reads its
+// raw centre rows from L1/L2); stage B gives each thread 4 consecutive output z of ONE branch channel (the CB
 // threads of a voxel sit in adjacent lanes and exchange t2 by shuffles for conv3).  Optionally the encoder's
 // parse_input 1x1 convolution (layers.py:535,578) is applied on the fly to a 1-channel input.
 constexpr int kDownThreads = 256;
@@ -311,7 +311,7 @@ struct DownSmem {
     static constexpr int pw = ws + CIN * 8 * COUT;       // [CIN] w, [CIN] b
     static constexpr int tile = (pw + 2 * CIN + 3) & ~3;
     static size_t floats(int tho, int two, int Z) {
-        return tile + (size_t)CB * (2 * tho + 2) * (2 * two + 2) * (Z + 8) + (size_t)CX * 4 * tho * two * Z;
+        return tile + (size_t)CB * (2 * tho + 2) * (2 * two + 2) * (Z + 8);
     }
 };
 
@@ -325,10 +325,8 @@ preact_down_row_kernel(DownParams p) {
     float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_ws = smem + SM::ws, *s_pw = smem + SM::pw;
     const int tid = threadIdx.x;
     const int Z = p.Z, ZQ = Z >> 2, ZQo = Z >> 3, ZP = Z + 8, Zo = Z >> 1;
-    const int IW = 2 * p.two + 2, nrows_in = (2 * p.tho + 2) * IW, nrows_out = p.tho * p.two, ICW = 2 * p.two;
+    const int IW = 2 * p.two + 2, nrows_in = (2 * p.tho + 2) * IW, nrows_out = p.tho * p.two;
     float *s_t1 = smem + SM::tile;
-    float *s_x = s_t1 + (size_t)CB * nrows_in * ZP;       // [CX][4*tho*two centre rows][Z]
-    const int ncentre = 4 * p.tho * p.two;
     const int64_t S = (int64_t)p.H * p.W * Z, So = S >> 3;
     const int Ho = p.H >> 1, Wo = p.W >> 1;
 
@@ -362,12 +360,6 @@ preact_down_row_kernel(DownParams p) {
             float4 raw[CX];
 #pragma unroll
             for (int c = 0; c < CX; ++c) raw[c] = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
-            const bool centre = lh >= 1 && lh <= 2 * p.tho && lw >= 1 && lw <= 2 * p.two;
-            if (centre) {
-                const int ir = (lh - 1) * ICW + (lw - 1);
-#pragma unroll
-                for (int c = 0; c < CX; ++c) *reinterpret_cast<float4 *>(s_x + ((size_t)c * ncentre + ir) * Z + 4 * zq) = raw[c];
-            }
             float t[CB][4];
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
@@ -460,12 +452,14 @@ preact_down_row_kernel(DownParams p) {
                 for (int k = 0; k < 4; ++k) sk[j][k] = 0.0f;
 #pragma unroll
             for (int t2 = 0; t2 < 4; ++t2) {
-                const int ir = (2 * lho + (t2 >> 1)) * ICW + 2 * lwo + (t2 & 1);
+                // the raw centre rows were read by stage A a moment ago: L1/L2 hits (keeping them in shared memory
+                // instead cost a third of the tile and forced 2 x 1 tiles with a 3x halo recompute)
+                const float *rx0 = xb + ((size_t)(2 * oh + (t2 >> 1)) * p.W + 2 * ow + (t2 & 1)) * Z + 8 * lane;
                 float4 r0[CX], r1[CX];
 #pragma unroll
                 for (int c = 0; c < CX; ++c) {
-                    const float *rx = s_x + ((size_t)c * ncentre + ir) * Z + 8 * lane;
-                    r0[c] = *reinterpret_cast<const float4 *>(rx); r1[c] = *reinterpret_cast<const float4 *>(rx + 4);
+                    const float *rx = rx0 + (size_t)c * S;
+                    r0[c] = __ldg(reinterpret_cast<const float4 *>(rx)); r1[c] = __ldg(reinterpret_cast<const float4 *>(rx + 4));
                 }
 #pragma unroll
                 for (int ci = 0; ci < CIN; ++ci) {

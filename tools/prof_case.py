@@ -29,6 +29,9 @@ CASES = {
     "up8_256": ("block", 8, 4, "up", 1, (256, 256, 64)),
     "down4_512": ("block", 4, 8, "down", 1, (512, 512, 128)),
     "down16_128": ("block", 16, 32, "down", 1, (128, 128, 32)),
+    "down8_256": ("block", 8, 16, "down", 1, (256, 256, 64)),
+    "up18_128": ("block", 18, 8, "up", 1, (128, 128, 32)),
+    "up32_64": ("block", 32, 16, "up", 1, (64, 64, 16)),
     "out4_512": ("conv1", 4, 1, None, 1, (512, 512, 128)),
     "in1_512": ("conv1", 1, 4, None, 1, (512, 512, 128)),
     "vq0": ("vq", 2, 128, None, 1, (128, 128, 32)),
