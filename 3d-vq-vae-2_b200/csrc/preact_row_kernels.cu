@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(RowThreads<C>::value, 2)
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
     constexpr int kRowThreads = RowThreads<C>::value;
-    constexpr bool kPackAC = C < 8 || VQ3D_ROW_PACK_C8;   // FFMA2 in conv1 / conv3 too (conv2 always when CB is even)
+    constexpr bool kPackAC = CB % 2 == 0 && (C < 8 || VQ3D_ROW_PACK_C8);   // FFMA2 in conv1 / conv3 too (conv2 always when CB is even)
     VQ3D_DYN_SMEM(float, smem);
     float *s_w1 = smem + SM::w1, *s_w2 = smem + SM::w2, *s_w3 = smem + SM::w3, *s_wo = smem + SM::wo, *s_t1 = smem + SM::tile;
     const int tid = threadIdx.x;
@@ -95,7 +95,7 @@ preact_row_kernel(RowParams p) {
             for (int c = 0; c < C; ++c) cur[c] = nxt[c];
             if (rs + nslots < nrows_in) issue(rs + nslots);
             float t[CB][4];
-            if constexpr (CB % 2 == 0 && kPackAC) {
+            if constexpr (kPackAC) {
                 float2 t2[CB / 2][4];
 #pragma unroll
                 for (int cp = 0; cp < CB / 2; ++cp)
@@ -353,13 +353,24 @@ preact_down_row_kernel(DownParams p) {
     // ---- stage A: t1 on the haloed input rows, raw centre rows for the skip ---------------------------------
     {
         const int zq = tid % ZQ, slot = tid / ZQ, nslots = kDownThreads / ZQ;
-        for (int rs = slot; rs < nrows_in; rs += nslots) {
+        // (as in preact_row_kernel: the loads of the next row slot are issued before the arithmetic of the current
+        //  one, when the registers allow it)
+        constexpr bool kPrefetch = CX <= 4;
+        float4 nxt[CX];
+        auto issue = [&](int rs) {
             const int lh = rs / IW, lw = rs - lh * IW;
             const int gh = rmod(2 * oh0 - 1 + lh, p.H), gw = rmod(2 * ow0 - 1 + lw, p.W);
             const float *px = xb + ((size_t)gh * p.W + gw) * Z + 4 * zq;
+#pragma unroll
+            for (int c = 0; c < CX; ++c) nxt[c] = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
+        };
+        if (kPrefetch && slot < nrows_in) issue(slot);
+        for (int rs = slot; rs < nrows_in; rs += nslots) {
+            if (!kPrefetch) issue(rs);
             float4 raw[CX];
 #pragma unroll
-            for (int c = 0; c < CX; ++c) raw[c] = __ldg(reinterpret_cast<const float4 *>(px + (size_t)c * S));
+            for (int c = 0; c < CX; ++c) raw[c] = nxt[c];
+            if (kPrefetch && rs + nslots < nrows_in) issue(rs + nslots);
             float t[CB][4];
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
