@@ -46,7 +46,7 @@ struct RowSmem {
 };
 
 template <int C, int CB, bool OUTC>
-__global__ void __launch_bounds__(RowThreads<C>::value, 2)
+__global__ void __launch_bounds__(RowThreads<C>::value, C >= 8 ? 2 : 0)
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
     constexpr int kRowThreads = RowThreads<C>::value;
@@ -220,23 +220,7 @@ preact_row_kernel(RowParams p) {
             for (int k = 0; k < 4; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
         const size_t off = ((size_t)oh * p.W + ow) * Z + 4 * zq;
         float o4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int cq = 0; cq < C / 2; ++cq) {
-            float2 out2[4];                 // conv3 for the output channel pair (2cq, 2cq+1)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out2[k] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int cb = 0; cb < CB; ++cb) {
-                const float2 w = make_float2(s_w3[cb * C + 2 * cq], s_w3[cb * C + 2 * cq + 1]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) out2[k] = ffma2_bcast_if<kPackAC>(w, acc[cb][k], out2[k]);
-            }
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const int c = 2 * cq + ch;
-            float out[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = ch ? out2[k].y : out2[k].x;
+        auto finish = [&](int c, const float *out) {      // *scale + b4 + x, then store (or the fused `out` convolution)
             const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off));
             float4 yv;
             yv.x = __fmaf_rn(out[0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[1], sc, b4) + xv.y;
@@ -248,7 +232,35 @@ preact_row_kernel(RowParams p) {
             } else {
                 *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off) = yv;
             }
-        }
+        };
+        if constexpr (kPackAC) {
+#pragma unroll
+            for (int cq = 0; cq < C / 2; ++cq) {
+                float2 out2[4];                 // conv3 for the output channel pair (2cq, 2cq+1)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float2 w = make_float2(s_w3[cb * C + 2 * cq], s_w3[cb * C + 2 * cq + 1]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) out2[k] = ffma2_bcast(w, acc[cb][k], out2[k]);
+                }
+                const float oa[4] = {out2[0].x, out2[1].x, out2[2].x, out2[3].x}, ob[4] = {out2[0].y, out2[1].y, out2[2].y, out2[3].y};
+                finish(2 * cq, oa);
+                finish(2 * cq + 1, ob);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float w = s_w3[cb * C + c];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+                }
+                finish(c, out);
+            }
         }
         if (OUTC) {
             const float bo = s_wo[C];
