@@ -45,8 +45,8 @@ struct RowSmem {
     static size_t floats(int th, int tw, int Z) { return tile + (size_t)CB * (th + 2) * (tw + 2) * (Z + 8); }
 };
 
-template <int C, int CB, bool OUTC>
-__global__ void __launch_bounds__(RowThreads<C>::value, C >= 8 ? 2 : 0)
+template <int C, int CB, bool OUTC, int NZ>
+__global__ void __launch_bounds__(RowThreads<C>::value, (C >= 8 || NZ == 8) ? 2 : 0)
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
     constexpr int kRowThreads = RowThreads<C>::value;
@@ -147,30 +147,41 @@ preact_row_kernel(RowParams p) {
     }
     __syncthreads();
 
-    // ---- stage B + C ------------------------------------------------------------------------------
+    // ---- stage B + C: NZ consecutive z per thread (4; 8 is a measured negative result, see launch_row) ---------
+    constexpr int NV = NZ / 4;
+    const int ZQB = Z / NZ, zqb = tid % ZQB, slotb = tid / ZQB, nslotsb = kRowThreads / ZQB;
     const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
-    for (int ro = slot; ro < nrows_out; ro += nslots) {
+    for (int ro = slotb; ro < nrows_out; ro += nslotsb) {
         const int lh = ro / p.tw, lw = ro - lh * p.tw;
         const int oh = oh0 + lh, ow = ow0 + lw;
         if (oh >= p.H || ow >= p.W) continue;
-        float acc[CB][4];
+        float acc[CB][NZ];
+        auto window = [&](int ci, int kh, int kw, float *r) {       // r[NZ + 2] = t1[z0 - 1 .. z0 + NZ]
+            const float *row = s_t1 + ((size_t)ci * nrows_in + (lh + kh) * IW + lw + kw) * ZP + NZ * zqb;
+            r[0] = row[3];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 m = *reinterpret_cast<const float4 *>(row + 4 + 4 * v);
+                r[1 + 4 * v] = m.x; r[2 + 4 * v] = m.y; r[3 + 4 * v] = m.z; r[4 + 4 * v] = m.w;
+            }
+            r[NZ + 1] = row[4 + NZ];
+        };
         if constexpr (CB % 2 == 0) {
             // two branch channels per FFMA2 (w pair from shared memory, the window value broadcast)
             constexpr int CP = CB / 2;
-            float2 acc2[CP][4];
+            float2 acc2[CP][NZ];
 #pragma unroll
             for (int cp = 0; cp < CP; ++cp)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc2[cp][k] = make_float2(0.0f, 0.0f);
+                for (int k = 0; k < NZ; ++k) acc2[cp][k] = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int ci = 0; ci < CB; ++ci) {
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
-                        const float *row = s_t1 + ((size_t)ci * nrows_in + (lh + kh) * IW + lw + kw) * ZP + 4 * zq;
-                        const float4 m = *reinterpret_cast<const float4 *>(row + 4);
-                        const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                        float r[NZ + 2];
+                        window(ci, kh, kw, r);
                         const float2 *wt = reinterpret_cast<const float2 *>(s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB);
 #pragma unroll
                         for (int kz = 0; kz < 3; ++kz)
@@ -178,7 +189,7 @@ preact_row_kernel(RowParams p) {
                             for (int cp = 0; cp < CP; ++cp) {
                                 const float2 w = wt[kz * CP + cp];
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) acc2[cp][k] = ffma2_bcast(w, r[k + kz], acc2[cp][k]);
+                                for (int k = 0; k < NZ; ++k) acc2[cp][k] = ffma2_bcast(w, r[k + kz], acc2[cp][k]);
                             }
                     }
                 }
@@ -186,93 +197,104 @@ preact_row_kernel(RowParams p) {
 #pragma unroll
             for (int cp = 0; cp < CP; ++cp)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { acc[2 * cp][k] = acc2[cp][k].x; acc[2 * cp + 1][k] = acc2[cp][k].y; }
+                for (int k = 0; k < NZ; ++k) { acc[2 * cp][k] = acc2[cp][k].x; acc[2 * cp + 1][k] = acc2[cp][k].y; }
         } else {
 #pragma unroll
-        for (int co = 0; co < CB; ++co)
+            for (int co = 0; co < CB; ++co)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[co][k] = 0.0f;
+                for (int k = 0; k < NZ; ++k) acc[co][k] = 0.0f;
 #pragma unroll
-        for (int ci = 0; ci < CB; ++ci) {
+            for (int ci = 0; ci < CB; ++ci) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+                for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float *row = s_t1 + ((size_t)ci * nrows_in + (lh + kh) * IW + lw + kw) * ZP + 4 * zq;
-                    const float4 m = *reinterpret_cast<const float4 *>(row + 4);
-                    const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
-                    const float *wt = s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB;
+                    for (int kw = 0; kw < 3; ++kw) {
+                        float r[NZ + 2];
+                        window(ci, kh, kw, r);
+                        const float *wt = s_w2 + ((ci * 9 + kh * 3 + kw) * 3) * CB;
 #pragma unroll
-                    for (int kz = 0; kz < 3; ++kz)
+                        for (int kz = 0; kz < 3; ++kz)
 #pragma unroll
-                        for (int co = 0; co < CB; ++co) {
-                            const float w = wt[kz * CB + co];
+                            for (int co = 0; co < CB; ++co) {
+                                const float w = wt[kz * CB + co];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[co][k] = __fmaf_rn(w, r[k + kz], acc[co][k]);
-                        }
+                                for (int k = 0; k < NZ; ++k) acc[co][k] = __fmaf_rn(w, r[k + kz], acc[co][k]);
+                            }
+                    }
                 }
             }
         }
-        }
 #pragma unroll
         for (int co = 0; co < CB; ++co)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
-        const size_t off = ((size_t)oh * p.W + ow) * Z + 4 * zq;
-        float o4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < NZ; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
+        const size_t off = ((size_t)oh * p.W + ow) * Z + NZ * zqb;
+        float o4[NZ];
+#pragma unroll
+        for (int k = 0; k < NZ; ++k) o4[k] = 0.f;
         auto finish = [&](int c, const float *out) {      // *scale + b4 + x, then store (or the fused `out` convolution)
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off));
-            float4 yv;
-            yv.x = __fmaf_rn(out[0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[1], sc, b4) + xv.y;
-            yv.z = __fmaf_rn(out[2], sc, b4) + xv.z; yv.w = __fmaf_rn(out[3], sc, b4) + xv.w;
-            if (OUTC) {
-                const float w = s_wo[c];
-                o4[0] = __fmaf_rn(w, yv.x, o4[0]); o4[1] = __fmaf_rn(w, yv.y, o4[1]);
-                o4[2] = __fmaf_rn(w, yv.z, o4[2]); o4[3] = __fmaf_rn(w, yv.w, o4[3]);
-            } else {
-                *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off) = yv;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off + 4 * v));
+                float4 yv;
+                yv.x = __fmaf_rn(out[4 * v + 0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[4 * v + 1], sc, b4) + xv.y;
+                yv.z = __fmaf_rn(out[4 * v + 2], sc, b4) + xv.z; yv.w = __fmaf_rn(out[4 * v + 3], sc, b4) + xv.w;
+                if (OUTC) {
+                    const float w = s_wo[c];
+                    o4[4 * v + 0] = __fmaf_rn(w, yv.x, o4[4 * v + 0]); o4[4 * v + 1] = __fmaf_rn(w, yv.y, o4[4 * v + 1]);
+                    o4[4 * v + 2] = __fmaf_rn(w, yv.z, o4[4 * v + 2]); o4[4 * v + 3] = __fmaf_rn(w, yv.w, o4[4 * v + 3]);
+                } else {
+                    *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off + 4 * v) = yv;
+                }
             }
         };
         if constexpr (kPackAC) {
 #pragma unroll
             for (int cq = 0; cq < C / 2; ++cq) {
-                float2 out2[4];                 // conv3 for the output channel pair (2cq, 2cq+1)
+                float2 out2[NZ];                // conv3 for the output channel pair (2cq, 2cq+1)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) out2[k] = make_float2(0.f, 0.f);
+                for (int k = 0; k < NZ; ++k) out2[k] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int cb = 0; cb < CB; ++cb) {
                     const float2 w = make_float2(s_w3[cb * C + 2 * cq], s_w3[cb * C + 2 * cq + 1]);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) out2[k] = ffma2_bcast(w, acc[cb][k], out2[k]);
+                    for (int k = 0; k < NZ; ++k) out2[k] = ffma2_bcast(w, acc[cb][k], out2[k]);
                 }
-                const float oa[4] = {out2[0].x, out2[1].x, out2[2].x, out2[3].x}, ob[4] = {out2[0].y, out2[1].y, out2[2].y, out2[3].y};
+                float oa[NZ], ob[NZ];
+#pragma unroll
+                for (int k = 0; k < NZ; ++k) { oa[k] = out2[k].x; ob[k] = out2[k].y; }
                 finish(2 * cq, oa);
                 finish(2 * cq + 1, ob);
             }
         } else {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float out[4] = {0.f, 0.f, 0.f, 0.f};
+                float out[NZ];
+#pragma unroll
+                for (int k = 0; k < NZ; ++k) out[k] = 0.f;
 #pragma unroll
                 for (int cb = 0; cb < CB; ++cb) {
                     const float w = s_w3[cb * C + c];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+                    for (int k = 0; k < NZ; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
                 }
                 finish(c, out);
             }
         }
         if (OUTC) {
             const float bo = s_wo[C];
-            float4 ov;
-            ov.x = o4[0] + bo; ov.y = o4[1] + bo; ov.z = o4[2] + bo; ov.w = o4[3] + bo;
-            *reinterpret_cast<float4 *>(p.y + (size_t)b * S + off) = ov;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float4 ov;
+                ov.x = o4[4 * v + 0] + bo; ov.y = o4[4 * v + 1] + bo; ov.z = o4[4 * v + 2] + bo; ov.w = o4[4 * v + 3] + bo;
+                *reinterpret_cast<float4 *>(p.y + (size_t)b * S + off + 4 * v) = ov;
+            }
         }
     }
 }
 
-template <int C, int CB, bool OUTC>
-static int launch_row(const vq3d_preact_desc *d, void *stream) {
+template <int C, int CB, bool OUTC, int NZ>
+static int launch_row_nz(const vq3d_preact_desc *d, void *stream) {
     using SM = RowSmem<C, CB>;
     RowParams p;
     p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z;
@@ -292,7 +314,23 @@ static int launch_row(const vq3d_preact_desc *d, void *stream) {
     p.y = OUTC ? d->out_y : d->y;
     const int64_t grid = ntiles();
     if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(row): grid too large");
-    return launch("preact_row", preact_row_kernel<C, CB, OUTC>, dim3((unsigned)grid), dim3(RowThreads<C>::value), SM::floats(th, tw, d->Z) * 4, stream, p);
+    return launch("preact_row", preact_row_kernel<C, CB, OUTC, NZ>, dim3((unsigned)grid), dim3(RowThreads<C>::value), SM::floats(th, tw, d->Z) * 4, stream, p);
+}
+
+// z per thread in stage B/C (VQ3D_ROW_NZ8: 0 = always 4, 1 = 8 for the 4 -> 2 -> 4 variant, 2 = also for 8 -> 4 -> 8).
+// Measured (profiles/r01x_ffma2_ab.txt, variants P / B / N2): 8 z per thread halve the shared-memory instructions per FMA
+// but the 32-byte lane stride makes every LDS.128 of the window a 2-way bank conflict: 4 -> 2 -> 4 at 512^3 gets 13 %
+// SLOWER, 8 -> 4 -> 8 at 256^3 1.6 % slower.  Off by default.
+#ifndef VQ3D_ROW_NZ8
+#define VQ3D_ROW_NZ8 0
+#endif
+template <int C, int CB, bool OUTC>
+static int launch_row(const vq3d_preact_desc *d, void *stream) {
+    constexpr bool kWide = CB % 2 == 0 && ((C < 8 && VQ3D_ROW_NZ8 >= 1) || VQ3D_ROW_NZ8 >= 2);
+    if constexpr (kWide) {
+        if (d->Z % 8 == 0 && RowThreads<C>::value % (d->Z / 8) == 0) return launch_row_nz<C, CB, OUTC, 8>(d, stream);
+    }
+    return launch_row_nz<C, CB, OUTC, 4>(d, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
