@@ -45,8 +45,8 @@ struct RowSmem {
     static size_t floats(int th, int tw, int Z) { return tile + (size_t)CB * (th + 2) * (tw + 2) * (Z + 8); }
 };
 
-template <int C, int CB, bool OUTC, int NZ>
-__global__ void __launch_bounds__(RowThreads<C>::value, (C >= 8 || NZ == 8) ? 2 : 0)
+template <int C, int CB, bool OUTC, int NZ, int NW>
+__global__ void __launch_bounds__(RowThreads<C>::value, (C >= 8 || NZ == 8 || NW == 2) ? 2 : 0)
 preact_row_kernel(RowParams p) {
     using SM = RowSmem<C, CB>;
     constexpr int kRowThreads = RowThreads<C>::value;
@@ -151,6 +151,136 @@ preact_row_kernel(RowParams p) {
     constexpr int NV = NZ / 4;
     const int ZQB = Z / NZ, zqb = tid % ZQB, slotb = tid / ZQB, nslotsb = kRowThreads / ZQB;
     const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
+    auto stage_c = [&](float (&acc)[CB][NZ], const size_t off) {   // ELU, conv3, *scale + b4 + x [, out conv], store
+#pragma unroll
+        for (int co = 0; co < CB; ++co)
+#pragma unroll
+            for (int k = 0; k < NZ; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
+        float o4[NZ];
+#pragma unroll
+        for (int k = 0; k < NZ; ++k) o4[k] = 0.f;
+        auto finish = [&](int c, const float *out) {      // *scale + b4 + x, then store (or the fused `out` convolution)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off + 4 * v));
+                float4 yv;
+                yv.x = __fmaf_rn(out[4 * v + 0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[4 * v + 1], sc, b4) + xv.y;
+                yv.z = __fmaf_rn(out[4 * v + 2], sc, b4) + xv.z; yv.w = __fmaf_rn(out[4 * v + 3], sc, b4) + xv.w;
+                if (OUTC) {
+                    const float w = s_wo[c];
+                    o4[4 * v + 0] = __fmaf_rn(w, yv.x, o4[4 * v + 0]); o4[4 * v + 1] = __fmaf_rn(w, yv.y, o4[4 * v + 1]);
+                    o4[4 * v + 2] = __fmaf_rn(w, yv.z, o4[4 * v + 2]); o4[4 * v + 3] = __fmaf_rn(w, yv.w, o4[4 * v + 3]);
+                } else {
+                    *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off + 4 * v) = yv;
+                }
+            }
+        };
+        if constexpr (kPackAC) {
+#pragma unroll
+            for (int cq = 0; cq < C / 2; ++cq) {
+                float2 out2[NZ];                // conv3 for the output channel pair (2cq, 2cq+1)
+#pragma unroll
+                for (int k = 0; k < NZ; ++k) out2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float2 w = make_float2(s_w3[cb * C + 2 * cq], s_w3[cb * C + 2 * cq + 1]);
+#pragma unroll
+                    for (int k = 0; k < NZ; ++k) out2[k] = ffma2_bcast(w, acc[cb][k], out2[k]);
+                }
+                float oa[NZ], ob[NZ];
+#pragma unroll
+                for (int k = 0; k < NZ; ++k) { oa[k] = out2[k].x; ob[k] = out2[k].y; }
+                finish(2 * cq, oa);
+                finish(2 * cq + 1, ob);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float out[NZ];
+#pragma unroll
+                for (int k = 0; k < NZ; ++k) out[k] = 0.f;
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const float w = s_w3[cb * C + c];
+#pragma unroll
+                    for (int k = 0; k < NZ; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+                }
+                finish(c, out);
+            }
+        }
+        if (OUTC) {
+            const float bo = s_wo[C];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float4 ov;
+                ov.x = o4[4 * v + 0] + bo; ov.y = o4[4 * v + 1] + bo; ov.z = o4[4 * v + 2] + bo; ov.w = o4[4 * v + 3] + bo;
+                *reinterpret_cast<float4 *>(p.y + (size_t)b * S + off + 4 * v) = ov;
+            }
+        }
+    };
+    if constexpr (NW == 2) {
+        // two neighbouring output rows (w, w + 1) per thread: the four windows of a (ci, kh) row pair and every weight
+        // are loaded once for both, 21 instead of 36 shared-memory instructions per 72 FFMA2
+        constexpr int CP = CB / 2;
+        const int tw2 = p.tw >> 1;
+        for (int ro = slotb; ro < p.th * tw2; ro += nslotsb) {
+            const int lh = ro / tw2, lw = 2 * (ro - lh * tw2);
+            const int oh = oh0 + lh, ow = ow0 + lw;
+            if (oh >= p.H || ow >= p.W) continue;
+            float2 acc2[2][CP][4];
+#pragma unroll
+            for (int rw = 0; rw < 2; ++rw)
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc2[rw][cp][k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    float2 wprev[3][CP];
+#pragma unroll
+                    for (int kwi = 0; kwi < 4; ++kwi) {
+                        const float *row = s_t1 + ((size_t)ci * nrows_in + (lh + kh) * IW + lw + kwi) * ZP + 4 * zqb;
+                        const float4 m = *reinterpret_cast<const float4 *>(row + 4);
+                        const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                        float2 wcur[3][CP];
+                        if (kwi < 3) {
+                            const float2 *wt = reinterpret_cast<const float2 *>(s_w2 + ((ci * 9 + kh * 3 + kwi) * 3) * CB);
+#pragma unroll
+                            for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                                for (int cp = 0; cp < CP; ++cp) wcur[kz][cp] = wt[kz * CP + cp];
+                        }
+#pragma unroll
+                        for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                            for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (kwi < 3) acc2[0][cp][k] = ffma2_bcast(wcur[kz][cp], r[k + kz], acc2[0][cp][k]);
+                                    if (kwi > 0) acc2[1][cp][k] = ffma2_bcast(wprev[kz][cp], r[k + kz], acc2[1][cp][k]);
+                                }
+                        if (kwi < 3) {
+#pragma unroll
+                            for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                                for (int cp = 0; cp < CP; ++cp) wprev[kz][cp] = wcur[kz][cp];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int rw = 0; rw < 2; ++rw) {
+                float acc[CB][NZ];
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { acc[2 * cp][k] = acc2[rw][cp][k].x; acc[2 * cp + 1][k] = acc2[rw][cp][k].y; }
+                stage_c(acc, ((size_t)oh * p.W + ow + rw) * Z + 4 * zqb);
+            }
+        }
+    } else
     for (int ro = slotb; ro < nrows_out; ro += nslotsb) {
         const int lh = ro / p.tw, lw = ro - lh * p.tw;
         const int oh = oh0 + lh, ow = ow0 + lw;
@@ -224,76 +354,11 @@ preact_row_kernel(RowParams p) {
                 }
             }
         }
-#pragma unroll
-        for (int co = 0; co < CB; ++co)
-#pragma unroll
-            for (int k = 0; k < NZ; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
-        const size_t off = ((size_t)oh * p.W + ow) * Z + NZ * zqb;
-        float o4[NZ];
-#pragma unroll
-        for (int k = 0; k < NZ; ++k) o4[k] = 0.f;
-        auto finish = [&](int c, const float *out) {      // *scale + b4 + x, then store (or the fused `out` convolution)
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)c * S + off + 4 * v));
-                float4 yv;
-                yv.x = __fmaf_rn(out[4 * v + 0], sc, b4) + xv.x; yv.y = __fmaf_rn(out[4 * v + 1], sc, b4) + xv.y;
-                yv.z = __fmaf_rn(out[4 * v + 2], sc, b4) + xv.z; yv.w = __fmaf_rn(out[4 * v + 3], sc, b4) + xv.w;
-                if (OUTC) {
-                    const float w = s_wo[c];
-                    o4[4 * v + 0] = __fmaf_rn(w, yv.x, o4[4 * v + 0]); o4[4 * v + 1] = __fmaf_rn(w, yv.y, o4[4 * v + 1]);
-                    o4[4 * v + 2] = __fmaf_rn(w, yv.z, o4[4 * v + 2]); o4[4 * v + 3] = __fmaf_rn(w, yv.w, o4[4 * v + 3]);
-                } else {
-                    *reinterpret_cast<float4 *>(p.y + (size_t)b * C * S + (size_t)c * S + off + 4 * v) = yv;
-                }
-            }
-        };
-        if constexpr (kPackAC) {
-#pragma unroll
-            for (int cq = 0; cq < C / 2; ++cq) {
-                float2 out2[NZ];                // conv3 for the output channel pair (2cq, 2cq+1)
-#pragma unroll
-                for (int k = 0; k < NZ; ++k) out2[k] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int cb = 0; cb < CB; ++cb) {
-                    const float2 w = make_float2(s_w3[cb * C + 2 * cq], s_w3[cb * C + 2 * cq + 1]);
-#pragma unroll
-                    for (int k = 0; k < NZ; ++k) out2[k] = ffma2_bcast(w, acc[cb][k], out2[k]);
-                }
-                float oa[NZ], ob[NZ];
-#pragma unroll
-                for (int k = 0; k < NZ; ++k) { oa[k] = out2[k].x; ob[k] = out2[k].y; }
-                finish(2 * cq, oa);
-                finish(2 * cq + 1, ob);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float out[NZ];
-#pragma unroll
-                for (int k = 0; k < NZ; ++k) out[k] = 0.f;
-#pragma unroll
-                for (int cb = 0; cb < CB; ++cb) {
-                    const float w = s_w3[cb * C + c];
-#pragma unroll
-                    for (int k = 0; k < NZ; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
-                }
-                finish(c, out);
-            }
-        }
-        if (OUTC) {
-            const float bo = s_wo[C];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                float4 ov;
-                ov.x = o4[4 * v + 0] + bo; ov.y = o4[4 * v + 1] + bo; ov.z = o4[4 * v + 2] + bo; ov.w = o4[4 * v + 3] + bo;
-                *reinterpret_cast<float4 *>(p.y + (size_t)b * S + off + 4 * v) = ov;
-            }
-        }
+        stage_c(acc, ((size_t)oh * p.W + ow) * Z + NZ * zqb);
     }
 }
 
-template <int C, int CB, bool OUTC, int NZ>
+template <int C, int CB, bool OUTC, int NZ, int NW = 1>
 static int launch_row_nz(const vq3d_preact_desc *d, void *stream) {
     using SM = RowSmem<C, CB>;
     RowParams p;
@@ -314,7 +379,7 @@ static int launch_row_nz(const vq3d_preact_desc *d, void *stream) {
     p.y = OUTC ? d->out_y : d->y;
     const int64_t grid = ntiles();
     if (grid > 0x7fffffff) return fail(VQ3D_ERR_INVALID, "preact_block(row): grid too large");
-    return launch("preact_row", preact_row_kernel<C, CB, OUTC, NZ>, dim3((unsigned)grid), dim3(RowThreads<C>::value), SM::floats(th, tw, d->Z) * 4, stream, p);
+    return launch("preact_row", preact_row_kernel<C, CB, OUTC, NZ, NW>, dim3((unsigned)grid), dim3(RowThreads<C>::value), SM::floats(th, tw, d->Z) * 4, stream, p);
 }
 
 // z per thread in stage B/C (VQ3D_ROW_NZ8: 0 = always 4, 1 = 8 for the 4 -> 2 -> 4 variant, 2 = also for 8 -> 4 -> 8).
@@ -324,11 +389,18 @@ static int launch_row_nz(const vq3d_preact_desc *d, void *stream) {
 #ifndef VQ3D_ROW_NZ8
 #define VQ3D_ROW_NZ8 0
 #endif
+// output rows per thread in stage B (VQ3D_ROW_NW2: 0 = one, 1 = two for 4 -> 2 -> 4, 2 = also for 8 -> 4 -> 8)
+#ifndef VQ3D_ROW_NW2
+#define VQ3D_ROW_NW2 2
+#endif
 template <int C, int CB, bool OUTC>
 static int launch_row(const vq3d_preact_desc *d, void *stream) {
     constexpr bool kWide = CB % 2 == 0 && ((C < 8 && VQ3D_ROW_NZ8 >= 1) || VQ3D_ROW_NZ8 >= 2);
     if constexpr (kWide) {
         if (d->Z % 8 == 0 && RowThreads<C>::value % (d->Z / 8) == 0) return launch_row_nz<C, CB, OUTC, 8>(d, stream);
+    }
+    if constexpr (CB % 2 == 0 && (VQ3D_ROW_NW2 >= 2 || (VQ3D_ROW_NW2 == 1 && C < 8))) {
+        if (d->W % 2 == 0 && d->W >= 8 && d->H >= 8) return launch_row_nz<C, CB, OUTC, 4, 2>(d, stream);
     }
     return launch_row_nz<C, CB, OUTC, 4>(d, stream);
 }

@@ -271,3 +271,16 @@ def test_emu_tiled_conv_matches_torch(cin, cout, circ, shape, pre_act, res):
     with use_emulator():
         got = _ops.default().conv3d(x, w, pad=1, circular=circ, pre_act=pre_act, pre_a=a, pre_b=b, post_scale=s, post_b=pb, residual=r)
     assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("C,shape", [(4, (1, 4, 8, 10, 8)), (8, (2, 8, 9, 8, 8)), (2, (1, 2, 8, 8, 8))])
+def test_emu_row_kernel_two_rows_per_thread(C, shape):
+    """preact_row_kernel with H, W >= 8 (the two-output-rows-per-thread path of the even-width variants, partial
+    tiles included) against the block composed from the generic convolution kernels."""
+    with use_emulator(), torch.no_grad():
+        torch.manual_seed(C)
+        m = L.PreActFixupResBlock(C, C, "same").eval()
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape) * 0.1)
+        x = portable_randn(shape, 11 + C)
+        assert close(m(x).numpy(), m.forward_composed(x).numpy())

@@ -315,6 +315,23 @@ def test_same_block_shift_equivariance_full_size():
         assert torch.allclose(blk.forward_composed(x), y, rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("C,shape", [(4, (2, 4, 24, 20, 128)), (4, (1, 4, 9, 8, 16)), (8, (1, 8, 16, 24, 64)), (8, (2, 8, 8, 10, 32))])
+def test_row_kernel_two_rows_per_thread_vs_composed(C, shape):
+    """preact_row_kernel (packed FMAs, two output rows per thread when H, W >= 8; partial tiles included) against the
+    same block composed from the generic fp32 convolution kernels, and its circular-shift equivariance bit for bit."""
+    torch.manual_seed(C)
+    blk = L.PreActFixupResBlock(C, C, "same")
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn(p.shape) * 0.1)
+        blk.to(DEV).eval()
+        x = torch.randn(*shape, device=DEV)
+        y = blk(x)
+        assert torch.allclose(blk.forward_composed(x), y, rtol=2e-5, atol=2e-6), float((blk.forward_composed(x) - y).abs().max())
+        ys = blk(torch.roll(x, shifts=(3, -1, 5), dims=(2, 3, 4)))
+        assert torch.equal(ys, torch.roll(y, shifts=(3, -1, 5), dims=(2, 3, 4)))
+
+
 def test_full_model_512_runs_and_is_self_consistent():
     """BASELINE.json metric config: Full 3-level model on one 512x512x128 volume.
     The oracle does not finish in seconds here, so use size-independent properties:
