@@ -657,6 +657,9 @@ static int launch_down_row(const vq3d_preact_desc *d, void *stream) {
 // that tile with 4 consecutive hi-res z per thread, the skip is upsampled on the fly in the epilogue.
 // Low-res rows are stored with one clamped element of padding on each side, which turns the depth interpolation of
 // hi z = 4q..4q+3 into fixed-weight blends of padded entries 2q..2q+3 with no edge cases.
+#ifndef VQ3D_UP_NW2
+#define VQ3D_UP_NW2 1
+#endif
 constexpr int kUpThreads = 256;
 
 struct UpParams {
@@ -826,6 +829,102 @@ preact_up_row_kernel(UpParams p) {
     // ---- stage B + C ---------------------------------------------------------------------------------------
     const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
     const float b1d = ld_scalar(p.b1d, 0.f);
+    auto up_epilogue = [&](float (&acc)[CB][4], const int lho, const int lwo, const int oh, const int ow) {
+#pragma unroll
+        for (int co = 0; co < CB; ++co)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
+        // skip: trilinear x2 of the low-res 1x1 skip at this hi row (tile rows lho+1, lwo+1 of the tap tables)
+        const int qh = lho + 1, qw = lwo + 1;
+        const int h0 = (int)s_tab[3 * qh], h1 = (int)s_tab[3 * qh + 1]; const float lh = s_tab[3 * qh + 2];
+        const int w0 = (int)s_tab[3 * (IH + qw)], w1 = (int)s_tab[3 * (IH + qw) + 1]; const float lw = s_tab[3 * (IH + qw) + 2];
+        const int r00 = h0 * LW + w0, r01 = h0 * LW + w1, r10 = h1 * LW + w0, r11 = h1 * LW + w1;
+        const size_t off = ((size_t)oh * Wo + ow) * Zo + 4 * q;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+            float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const float w = s_w3[cb * COUT + c];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
+            }
+            const float *base = s_sk + (size_t)c * LR * ZPL + 2 * q;
+            float a00[4], a01[4], a10[4], a11[4];
+            up_z4(base + (size_t)r00 * ZPL, a00); up_z4(base + (size_t)r01 * ZPL, a01);
+            up_z4(base + (size_t)r10 * ZPL, a10); up_z4(base + (size_t)r11 * ZPL, a11);
+            float yv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float c0 = a00[k] * (1.f - lw) + a01[k] * lw, c1 = a10[k] * (1.f - lw) + a11[k] * lw;
+                yv[k] = __fmaf_rn(out[k], sc, b4) + (c0 * (1.f - lh) + c1 * lh + b1d);
+            }
+            *reinterpret_cast<float4 *>(p.y + ((size_t)b * COUT + c) * So + off) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+        }
+    };
+    if constexpr (CB % 2 == 0 && VQ3D_UP_NW2) {
+        // two neighbouring hi-res output rows (w, w + 1) per thread, as in preact_row_kernel: windows and weights are
+        // loaded once for both
+        constexpr int CP = CB / 2;
+        const int two2 = p.two >> 1;
+        for (int ro = slot; ro < p.tho * two2; ro += nslots) {
+            const int lho = ro / two2, lwo = 2 * (ro - lho * two2);
+            const int oh = oh0 + lho, ow = ow0 + lwo;
+            if (oh >= Ho || ow >= Wo) continue;
+            float2 acc2[2][CP][4];
+#pragma unroll
+            for (int rw = 0; rw < 2; ++rw)
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc2[rw][cp][k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int ci = 0; ci < CB; ++ci) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    float2 wprev[3][CP];
+#pragma unroll
+                    for (int kwi = 0; kwi < 4; ++kwi) {
+                        const float *row = s_hi + ((size_t)ci * HR + (lho + kh) * IW + lwo + kwi) * ZPH + 4 * q;
+                        const float4 m = *reinterpret_cast<const float4 *>(row + 4);
+                        const float r[6] = {row[3], m.x, m.y, m.z, m.w, row[8]};
+                        float2 wcur[3][CP];
+                        if (kwi < 3) {
+                            const float2 *wt = reinterpret_cast<const float2 *>(s_w2 + ((ci * 9 + kh * 3 + kwi) * 3) * CB);
+#pragma unroll
+                            for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                                for (int cp = 0; cp < CP; ++cp) wcur[kz][cp] = wt[kz * CP + cp];
+                        }
+#pragma unroll
+                        for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                            for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (kwi < 3) acc2[0][cp][k] = ffma2_bcast(wcur[kz][cp], r[k + kz], acc2[0][cp][k]);
+                                    if (kwi > 0) acc2[1][cp][k] = ffma2_bcast(wprev[kz][cp], r[k + kz], acc2[1][cp][k]);
+                                }
+                        if (kwi < 3) {
+#pragma unroll
+                            for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+                                for (int cp = 0; cp < CP; ++cp) wprev[kz][cp] = wcur[kz][cp];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int rw = 0; rw < 2; ++rw) {
+                float acc[CB][4];
+#pragma unroll
+                for (int cp = 0; cp < CP; ++cp)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { acc[2 * cp][k] = acc2[rw][cp][k].x; acc[2 * cp + 1][k] = acc2[rw][cp][k].y; }
+                up_epilogue(acc, lho, lwo + rw, oh, ow + rw);
+            }
+        }
+    } else
     for (int ro = slot; ro < p.tho * p.two; ro += nslots) {
         const int lho = ro / p.two, lwo = ro - lho * p.two;
         const int oh = oh0 + lho, ow = ow0 + lwo;
@@ -888,37 +987,7 @@ preact_up_row_kernel(UpParams p) {
             }
         }
         }
-#pragma unroll
-        for (int co = 0; co < CB; ++co)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[co][k] = elu1(acc[co][k] + b3a) + b3b;
-        // skip: trilinear x2 of the low-res 1x1 skip at this hi row (tile rows lho+1, lwo+1 of the tap tables)
-        const int qh = lho + 1, qw = lwo + 1;
-        const int h0 = (int)s_tab[3 * qh], h1 = (int)s_tab[3 * qh + 1]; const float lh = s_tab[3 * qh + 2];
-        const int w0 = (int)s_tab[3 * (IH + qw)], w1 = (int)s_tab[3 * (IH + qw) + 1]; const float lw = s_tab[3 * (IH + qw) + 2];
-        const int r00 = h0 * LW + w0, r01 = h0 * LW + w1, r10 = h1 * LW + w0, r11 = h1 * LW + w1;
-        const size_t off = ((size_t)oh * Wo + ow) * Zo + 4 * q;
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-            float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int cb = 0; cb < CB; ++cb) {
-                const float w = s_w3[cb * COUT + c];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) out[k] = __fmaf_rn(w, acc[cb][k], out[k]);
-            }
-            const float *base = s_sk + (size_t)c * LR * ZPL + 2 * q;
-            float a00[4], a01[4], a10[4], a11[4];
-            up_z4(base + (size_t)r00 * ZPL, a00); up_z4(base + (size_t)r01 * ZPL, a01);
-            up_z4(base + (size_t)r10 * ZPL, a10); up_z4(base + (size_t)r11 * ZPL, a11);
-            float yv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float c0 = a00[k] * (1.f - lw) + a01[k] * lw, c1 = a10[k] * (1.f - lw) + a11[k] * lw;
-                yv[k] = __fmaf_rn(out[k], sc, b4) + (c0 * (1.f - lh) + c1 * lh + b1d);
-            }
-            *reinterpret_cast<float4 *>(p.y + ((size_t)b * COUT + c) * So + off) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-        }
+        up_epilogue(acc, lho, lwo, oh, ow);
     }
 }
 
