@@ -57,6 +57,9 @@ template <int MODE> struct Geo {
     static constexpr int ST = MODE == 1 ? 2 : 1;
 };
 
+#ifndef VQ3D_FUSED_FFMA2
+#define VQ3D_FUSED_FFMA2 1
+#endif
 template <int CIN, int CB, int COUT, int MODE, bool SKIP, int VX>
 struct PreactSmem {
     static constexpr int K = Geo<MODE>::K, K3 = K * K * K;
@@ -219,12 +222,51 @@ preact_fused_kernel(PreactParams p) {
     if (in_tile) {
         const int n_in = IH * IW * IZ;
         float acc[VX][CB];
+        constexpr int NW = (VX - 1) * ST + K;       // register window along W
+        const int bh = ly * ST, bw = lxv * VX * ST, bz = lz * ST;
+        if constexpr (VQ3D_FUSED_FFMA2 && CB >= 4) {
+            // two branch channels per packed FMA (weight pair x broadcast window value); an odd CB pads the last pair
+            // with the (ignored) lane of the padded weight column CB < CBP
+            constexpr int CP = (CB + 1) / 2;
+            static_assert(2 * CP <= CBP, "padded weight column");
+            float2 acc2[VX][CP];
+#pragma unroll
+            for (int v = 0; v < VX; ++v)
+#pragma unroll
+                for (int c = 0; c < CP; ++c) acc2[v][c] = make_float2(0.0f, 0.0f);
+            for (int ci = 0; ci < CB; ++ci) {
+                const float *t1c = s_t1 + (size_t)ci * n_in;
+                const float *wc = s_w2 + (size_t)ci * K3 * CBP;
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+                    for (int kz = 0; kz < K; ++kz) {
+                        float win[NW];
+                        const float *row = t1c + ((size_t)(bh + kh) * IW + bw) * IZ + bz + kz;
+#pragma unroll
+                        for (int j = 0; j < NW; ++j) win[j] = row[(size_t)j * IZ];
+#pragma unroll
+                        for (int kw = 0; kw < K; ++kw) {
+                            const float2 *wt = reinterpret_cast<const float2 *>(wc + ((kh * K + kw) * K + kz) * CBP);
+#pragma unroll
+                            for (int c = 0; c < CP; ++c) {
+                                const float2 wv = wt[c];
+#pragma unroll
+                                for (int v = 0; v < VX; ++v) acc2[v][c] = ffma2_bcast(wv, win[v * ST + kw], acc2[v][c]);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VX; ++v)
+#pragma unroll
+                for (int c = 0; c < CB; ++c) acc[v][c] = (c & 1) ? acc2[v][c >> 1].y : acc2[v][c >> 1].x;
+        } else {
 #pragma unroll
         for (int v = 0; v < VX; ++v)
 #pragma unroll
             for (int c = 0; c < CB; ++c) acc[v][c] = 0.0f;
-        constexpr int NW = (VX - 1) * ST + K;       // register window along W
-        const int bh = ly * ST, bw = lxv * VX * ST, bz = lz * ST;
         for (int ci = 0; ci < CB; ++ci) {
             const float *t1c = s_t1 + (size_t)ci * n_in;
             const float *wc = s_w2 + (size_t)ci * K3 * CBP;
@@ -248,6 +290,7 @@ preact_fused_kernel(PreactParams p) {
                     }
                 }
             }
+        }
         }
         // stage C
         const float b3a = ld_scalar(p.b3a, 0.f), b3b = ld_scalar(p.b3b, 0.f), b4 = ld_scalar(p.b4, 0.f), sc = ld_scalar(p.scale, 1.f);
