@@ -569,11 +569,20 @@ preact_down_row_kernel(DownParams p) {
             float tv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) tv[k] = __shfl_sync(0xffffffffu, acc[k], cb, CB);
+            if constexpr (NPC == 2) {               // the lane's two output channels in one packed FMA
+                const float2 w = *reinterpret_cast<const float2 *>(s_w3 + cb * COUT + co * NPC);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 o = ffma2_bcast(w, tv[k], make_float2(out[0][k], out[1][k]));
+                    out[0][k] = o.x; out[1][k] = o.y;
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < NPC; ++j) {
                 const float w = s_w3[cb * COUT + co * NPC + j];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) out[j][k] = __fmaf_rn(w, tv[k], out[j][k]);
+            }
             }
         }
         if (live && oh < Ho && ow < Wo) {
@@ -606,11 +615,21 @@ preact_down_row_kernel(DownParams p) {
                     }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) xv[e] += b1c;
+                    if constexpr (NPC == 2) {
+                        const float2 w0 = *reinterpret_cast<const float2 *>(s_ws + (ci * 8 + t2 * 2 + 0) * COUT + co * NPC);
+                        const float2 w1 = *reinterpret_cast<const float2 *>(s_ws + (ci * 8 + t2 * 2 + 1) * COUT + co * NPC);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 o = ffma2_bcast(w1, xv[2 * k + 1], ffma2_bcast(w0, xv[2 * k], make_float2(sk[0][k], sk[1][k])));
+                            sk[0][k] = o.x; sk[1][k] = o.y;
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < NPC; ++j) {
                         const float w0 = s_ws[(ci * 8 + t2 * 2 + 0) * COUT + co * NPC + j], w1 = s_ws[(ci * 8 + t2 * 2 + 1) * COUT + co * NPC + j];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) sk[j][k] = __fmaf_rn(w1, xv[2 * k + 1], __fmaf_rn(w0, xv[2 * k], sk[j][k]));
+                    }
                     }
                 }
             }
