@@ -367,7 +367,68 @@ elu_hu_rint_kernel(const float *__restrict__ x, int64_t n, float scale, float of
         out[i] = (int64_t)rintf(v);
     }
 }
+
+// the same epilogue with a 16-bit result (CT Hounsfield units fit int16: the reference clips its inputs to [-1500, 3000],
+// utils/load_nrrd_dataset.py:73-81); values outside int16 saturate.  Four voxels per thread: one 16-byte load, one 8-byte store.
+__global__ void __launch_bounds__(256)
+elu_hu_rint_i16_kernel(const float *__restrict__ x, int64_t n, float scale, float offset, int16_t *__restrict__ out) {
+    auto one = [&](float d) -> int {
+        const float v = __fsub_rn(__fmul_rn(elu1(d), scale), offset);
+        return (int)fminf(fmaxf(rintf(v), -32768.0f), 32767.0f);
+    };
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(x) + i);
+        const int a = one(v.x), b = one(v.y), c = one(v.z), d = one(v.w);
+        uint2 pk;
+        pk.x = (uint32_t)(a & 0xffff) | ((uint32_t)(b & 0xffff) << 16);
+        pk.y = (uint32_t)(c & 0xffff) | ((uint32_t)(d & 0xffff) << 16);
+        __stcs(reinterpret_cast<uint2 *>(out) + i, pk);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(n4 << 2) + threadIdx.x] = (int16_t)one(x[(n4 << 2) + threadIdx.x]);
+}
+
+// CT front end, utils/load_nrrd_dataset.py:73-81 (monai ThresholdIntensity x2, ScaleIntensity(factor = -1 + 1/1000),
+// ShiftIntensity(1)) on raw int16 Hounsfield units: out = clip(hu, lo, hi) * mul + add in fp32, two roundings like the
+// reference's separate transforms.
+__global__ void __launch_bounds__(256)
+hu_to_network_kernel(const int16_t *__restrict__ hu, int64_t n, float lo, float hi, float mul, float add, float *__restrict__ out) {
+    auto one = [&](int h) -> float { return __fadd_rn(__fmul_rn(fminf(fmaxf((float)h, lo), hi), mul), add); };
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 pk = __ldcs(reinterpret_cast<const uint2 *>(hu) + i);
+        float4 v;
+        v.x = one((int16_t)(pk.x & 0xffff)); v.y = one((int16_t)(pk.x >> 16));
+        v.z = one((int16_t)(pk.y & 0xffff)); v.w = one((int16_t)(pk.y >> 16));
+        reinterpret_cast<float4 *>(out)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(n4 << 2) + threadIdx.x] = one(hu[(n4 << 2) + threadIdx.x]);
+}
 }  // namespace vq3d
+
+extern "C" int vq3d_elu_hu_rint_i16(const float *decoded, int64_t n, double scale, double offset, int16_t *out, void *stream) {
+    if (!decoded || !out || n < 0) return vq3d::fail(VQ3D_ERR_INVALID, "elu_hu_rint_i16: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(decoded) & 15) || (reinterpret_cast<uintptr_t>(out) & 7))
+        return vq3d::fail(VQ3D_ERR_INVALID, "elu_hu_rint_i16: decoded must be 16-byte and out 8-byte aligned");
+    if (n == 0) return VQ3D_OK;
+    int64_t blocks = vq3d::ceil_div(n, 256 * 4 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    return vq3d::launch("elu_hu_rint_i16", vq3d::elu_hu_rint_i16_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, n,
+                        (float)scale, (float)offset, out);
+}
+
+extern "C" int vq3d_hu_to_network(const int16_t *hu, int64_t n, double min_hu, double max_hu, double mul, double add, float *out, void *stream) {
+    if (!hu || !out || n < 0 || !(min_hu <= max_hu)) return vq3d::fail(VQ3D_ERR_INVALID, "hu_to_network: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(hu) & 7) || (reinterpret_cast<uintptr_t>(out) & 15))
+        return vq3d::fail(VQ3D_ERR_INVALID, "hu_to_network: hu must be 8-byte and out 16-byte aligned");
+    if (n == 0) return VQ3D_OK;
+    int64_t blocks = vq3d::ceil_div(n, 256 * 4 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    return vq3d::launch("hu_to_network", vq3d::hu_to_network_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, hu, n, (float)min_hu,
+                        (float)max_hu, (float)mul, (float)add, out);
+}
 
 extern "C" int vq3d_elu_hu_rint(const float *decoded, int64_t n, double scale, double offset, int64_t *out, void *stream) {
     if (!decoded || !out || n < 0) return vq3d::fail(VQ3D_ERR_INVALID, "elu_hu_rint: bad arguments");

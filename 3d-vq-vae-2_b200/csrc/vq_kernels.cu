@@ -293,6 +293,10 @@ extern "C" int vq3d_vq_assign(const float *x, const float *embed, int64_t B, int
     if (!x || !embed || !quant || !idx) return fail(VQ3D_ERR_INVALID, "vq_assign: null pointer");
     if (B < 0 || S < 0 || D < 1 || K < 1 || D > 4096) return fail(VQ3D_ERR_INVALID, "vq_assign: bad sizes B=%lld D=%d S=%lld K=%d", (long long)B, D, (long long)S, K);
     if ((counts == nullptr) != (dw == nullptr)) return fail(VQ3D_ERR_INVALID, "vq_assign: counts and dw must both be given or both NULL");
+    if (sqerr != nullptr) {      // the accumulator is zeroed here (a memset node on the stream), not by the caller
+        const int rc = check_cuda(cudaMemsetAsync(sqerr, 0, sizeof(double), static_cast<cudaStream_t>(stream)), "vq_assign(memset)");
+        if (rc != VQ3D_OK) return rc;
+    }
     if (B == 0 || S == 0) return VQ3D_OK;
     switch (D) {
         case 1: return launch_assign<1>(x, embed, B, D, S, K, quant, idx, sqerr, counts, dw, stream);

@@ -746,6 +746,7 @@ static int launch_vqt(const float *x, const float *embed, int64_t B, int64_t S, 
     p.quant = quant; p.idx = idx; p.sqerr = sqerr; p.counts = counts; p.dw = dw;
     p.tmem_cols = 512;                                                   // NG groups x 2 accumulators x NT columns
     cudaError_t e = cudaMemsetAsync(wsb, 0, 256, st);
+    if (e == cudaSuccess && sqerr != nullptr) e = cudaMemsetAsync(sqerr, 0, sizeof(double), st);
     if (e != cudaSuccess) return check_cuda(e, "vq_assign_tc(memset)");
     vqt_norm_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(embed, K, D, cnorm);
     vqt_rank_kernel<<<(unsigned)ceil_div(p.Kpad, 256), 256, 0, st>>>(cnorm, K, p.Kpad, perm);

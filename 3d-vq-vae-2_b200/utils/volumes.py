@@ -19,8 +19,9 @@ MIN_HU, MAX_HU, SCALE = -1500.0, 3000.0, 1000.0          # utils/load_nrrd_datas
 
 
 def preprocess_hu(vol: np.ndarray) -> np.ndarray:
-    """HU -> network range: clip, / 1000, + 1 (air -> 0); utils/load_nrrd_dataset.py:73-81."""
-    return (np.clip(vol.astype(np.float32), MIN_HU, MAX_HU) / SCALE + 1.0).astype(np.float32)
+    """HU -> network range: clip, * (1 + (-1 + 1/1000)) in fp32, + 1 (air -> 0); utils/load_nrrd_dataset.py:73-81 (monai
+    ScaleIntensity multiplies by 1 + factor; same arithmetic as the device kernel vq3d_hu_to_network)."""
+    return (np.clip(vol.astype(np.float32), MIN_HU, MAX_HU) * np.float32(1 + (-1 + 1 / SCALE)) + np.float32(1.0)).astype(np.float32)
 
 
 class SyntheticVolumeDataset(torch.utils.data.Dataset):

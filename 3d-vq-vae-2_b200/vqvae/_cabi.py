@@ -36,7 +36,7 @@ class ConvBwd(C.Structure):
     _fields_ = [(n, _fp) for n in ("gy", "raw", "gx1", "gx2", "gw", "gbias", "gscalars")] + [("skip_input_grads", C.c_int32)]
 
 
-# name -> (restype, argtypes); the single source of truth for tests/test_cabi_symbols.py
+# name -> (restype, argtypes); the single source of truth for tests/test_host_logic.py::test_cabi_header_and_binding_agree
 SIGNATURES = {
     "vq3d_abi_version": (C.c_int, []),
     "vq3d_last_error": (C.c_char_p, []),
@@ -71,6 +71,8 @@ SIGNATURES = {
     "vq3d_evonorm_s0_stats": (C.c_int, [_fp, C.c_int, C.c_int64, C.c_int, C.c_double, _fp, _fp, _fp]),
     "vq3d_evonorm_s0_apply": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int64, _fp, _fp]),
     "vq3d_elu_hu_rint": (C.c_int, [_fp, C.c_int64, C.c_double, C.c_double, _fp, _fp]),
+    "vq3d_elu_hu_rint_i16": (C.c_int, [_fp, C.c_int64, C.c_double, C.c_double, _fp, _fp]),
+    "vq3d_hu_to_network": (C.c_int, [_fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _fp, _fp]),
     "vq3d_huber_elu_mask": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
 }
 

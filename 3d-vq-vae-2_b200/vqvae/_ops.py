@@ -101,7 +101,7 @@ class Ops:
         K = embed.shape[0]
         quant = torch.empty_like(x)
         idx = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.int64, device=x.device)
-        sqerr = torch.zeros(1, dtype=torch.float64, device=x.device)
+        sqerr = torch.empty(1, dtype=torch.float64, device=x.device)        # zeroed by the C call
         counts = dw = stats = None
         if want_stats:
             stats = torch.zeros(K * (D + 1), dtype=torch.float32, device=x.device)   # one flat all-reduce buffer
@@ -342,9 +342,12 @@ class Ops:
         to fuse into the last block's epilogue (the decoder's `out` conv); the result is then its output."""
         x = self._t(x)
         n = len(blocks)
+        B, Cc, H, W, Z = x.shape
+        # the fused tail is a C -> 1 pointwise convolution (out_w is read as one C-vector); anything else runs on its own
+        if tail is not None and (tuple(tail.weight.shape[:2]) != (1, Cc) or tuple(tail.weight.shape[2:]) != (1, 1, 1)):
+            return None
         y = torch.empty_like(x)
         tmp = torch.empty_like(x) if n > 1 else None
-        B, Cc, H, W, Z = x.shape
         out_y = torch.empty((B, 1, H, W, Z), dtype=torch.float32, device=x.device) if tail is not None else None
         arr = (_cabi.PreactDesc * n)()
         for i, blk in enumerate(blocks):
@@ -439,12 +442,28 @@ class Ops:
                     self.stream()), nbytes=12 * x.numel())
         return gx, g_v.float().view_as(v), g_gamma.float().view_as(gamma), g_beta.float().view_as(gamma)
 
-    def elu_hu_rint(self, decoded: Tensor, scale: float = 1000.0, offset: float = 1000.0) -> Tensor:
-        """rint(ELU(decoded) * scale - offset) as int64: the Hounsfield-unit output of decode_embeddings.py:43-47."""
+    def elu_hu_rint(self, decoded: Tensor, scale: float = 1000.0, offset: float = 1000.0, dtype=torch.int64) -> Tensor:
+        """rint(ELU(decoded) * scale - offset): the Hounsfield-unit output of decode_embeddings.py:43-47, as int64 (the
+        reference's `astype(int)`) or saturating int16 (2 bytes per voxel over PCIe instead of 8)."""
         decoded = self._t(decoded.detach())
-        out = torch.empty(decoded.shape, dtype=torch.int64, device=decoded.device)
-        self._call("elu_hu_rint", self.lib.vq3d_elu_hu_rint,
-                   (self._p(decoded), decoded.numel(), float(scale), float(offset), self._p(out), self.stream()), nbytes=12 * decoded.numel())
+        out = torch.empty(decoded.shape, dtype=dtype, device=decoded.device)
+        if dtype == torch.int16:
+            self._call("elu_hu_rint_i16", self.lib.vq3d_elu_hu_rint_i16,
+                       (self._p(decoded), decoded.numel(), float(scale), float(offset), self._p(out), self.stream()), nbytes=6 * decoded.numel())
+        elif dtype == torch.int64:
+            self._call("elu_hu_rint", self.lib.vq3d_elu_hu_rint,
+                       (self._p(decoded), decoded.numel(), float(scale), float(offset), self._p(out), self.stream()), nbytes=12 * decoded.numel())
+        else:
+            raise RuntimeError("elu_hu_rint: dtype must be torch.int64 or torch.int16")
+        return out
+
+    def hu_to_network(self, hu: Tensor, min_hu: float = -1500.0, max_hu: float = 3000.0, mul: float = 0.001, add: float = 1.0) -> Tensor:
+        """Raw int16 Hounsfield units -> the network's fp32 input range on the device: clip, * 0.001f, + 1
+        (utils/load_nrrd_dataset.py:73-81)."""
+        hu = self._t(hu, torch.int16)
+        out = torch.empty(hu.shape, dtype=torch.float32, device=hu.device)
+        self._call("hu_to_network", self.lib.vq3d_hu_to_network,
+                   (self._p(hu), hu.numel(), float(min_hu), float(max_hu), float(mul), float(add), self._p(out), self.stream()), nbytes=6 * hu.numel())
         return out
 
     def huber_loss(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]) -> Tensor:
@@ -456,7 +475,7 @@ class Ops:
 
     def huber_backward(self, decoded, x, num_valid, mask_hw, count, gloss) -> Tensor:
         decoded, x = self._t(decoded.detach()), self._t(x.detach())
-        B, _, H, W, Z = x.shape
+        B, H, W, Z, num_valid = self._huber_extent(decoded, x, num_valid)
         gdec = torch.empty_like(decoded)
         self._call("huber_elu_mask_backward", self.lib.vq3d_huber_elu_mask_backward,
                    (self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)), self._p(self._t(mask_hw, torch.uint8)), B, H, W, Z,
@@ -479,9 +498,23 @@ class Ops:
                    (self._p(p), self._p(g), self._p(m), self._p(v), self._p(vmax), p.numel(), float(lr), float(b1), float(b2), float(eps),
                     self._p(step_state), self.stream()), kernels=2, nbytes=28 * p.numel())
 
+    @staticmethod
+    def _huber_extent(decoded: Tensor, x: Tensor, num_valid: Optional[Tensor]):
+        """smooth_l1 runs over every channel (model.py:163): the kernels index (b, hw, z), so channels fold into the batch
+        extent and each volume's num_valid_slices entry is repeated per channel."""
+        if decoded.shape != x.shape:
+            raise RuntimeError(f"huber: decoded {tuple(decoded.shape)} vs target {tuple(x.shape)}")
+        B, Cc, H, W, Z = x.shape
+        if num_valid is not None:
+            if num_valid.numel() != B:
+                raise RuntimeError(f"huber: num_valid_slices has {num_valid.numel()} entries for a batch of {B}")
+            if Cc > 1:
+                num_valid = num_valid.repeat_interleave(Cc)
+        return B * Cc, H, W, Z, num_valid
+
     def huber_elu_mask(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor]):
         decoded, x = self._t(decoded.detach()), self._t(x.detach())
-        B, _, H, W, Z = x.shape
+        B, H, W, Z, num_valid = self._huber_extent(decoded, x, num_valid)
         acc = torch.zeros(2, dtype=torch.float64, device=x.device)
         self._call("huber_elu_mask", self.lib.vq3d_huber_elu_mask,
                    (self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)), self._p(self._t(mask_hw, torch.uint8)),

@@ -20,8 +20,9 @@ MIN_VAL, MAX_VAL, SCALE_VAL = -1500, 3000, 1000          # decode_embeddings.py:
 
 
 @torch.no_grad()
-def decode_codes(model: VQVAE, codes) -> torch.Tensor:
-    """codes: per level (bottom -> top) a LongTensor (h, w, d) or (B, h, w, d) -> Hounsfield units, int64 (B, 1, H, W, D)."""
+def decode_codes(model: VQVAE, codes, dtype=torch.int64) -> torch.Tensor:
+    """codes: per level (bottom -> top) a LongTensor (h, w, d) or (B, h, w, d) -> Hounsfield units (B, 1, H, W, D), int64 like
+    the reference's `astype(int)` or int16 (what the NRRD writer needs for CT: a quarter of the device -> host bytes)."""
     embeddings = []
     for idx, quantizer in zip(codes, model.encoder.quantize):
         idx = idx.cuda()
@@ -29,7 +30,7 @@ def decode_codes(model: VQVAE, codes) -> torch.Tensor:
             idx = idx.unsqueeze(dim=0)
         embeddings.append(quantizer.embed_code(idx).permute(0, 4, 1, 2, 3).contiguous())       # decode_embeddings.py:36-40
     res = model.decode(embeddings)
-    return _ops.default().elu_hu_rint(res, SCALE_VAL, SCALE_VAL)
+    return _ops.default().elu_hu_rint(res, SCALE_VAL, SCALE_VAL, dtype=dtype)
 
 
 def iter_samples(db):

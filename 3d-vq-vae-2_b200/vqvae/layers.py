@@ -7,9 +7,10 @@ this module instead.  The modules are parameter containers + launch logic only: 
 number is produced by the sm_100a kernels of libvqvae3d_b200.so through `_ops` (C ABI,
 include/vqvae3d_b200.h).  There is no PyTorch/CPU fallback; tensors must live on CUDA.
 
-Scope this round: forward (inference, extraction, EMA codebook training statistics) and
-the quantizer's straight-through backward.  Convolution backward kernels are not built
-yet; calling a block with autograd enabled on parameters that require grad raises.
+Inference (autograd off) runs each block / stack of blocks as one fused launch.  When autograd is
+recording, the blocks are composed from the differentiable generic ops of `_ops` whose backward runs
+the library's dgrad / wgrad / scalar-gradient kernels (csrc/backward_kernels.cu), so `loss.backward()`
+works on every module here.
 """
 from __future__ import annotations
 

@@ -120,6 +120,23 @@ class VQVAE(_Base):
     def decode(self, quantizations):
         return self.decoder(quantizations)
 
+    # ---- CT volumes in, CT volumes out (the data module's front end + decode_embeddings' epilogue on the device) ----
+    @torch.no_grad()
+    def reconstruct_hu(self, hu: torch.Tensor):
+        """hu: raw Hounsfield units, int16 (B, 1, H, W, D) on the device -> (reconstruction in Hounsfield units, int16, same
+        shape; code indices bottom -> top).  The clip / scale / shift of utils/load_nrrd_dataset.py:73-81 and the
+        ELU * 1000 - 1000 + rint of decode_embeddings.py:43-47 run on the device, so a volume crosses PCIe in 2 bytes per
+        voxel each way (fp32 forward API: 4 in, 4 + indices out)."""
+        o = _ops.default()
+        x = o.hu_to_network(hu)
+        decoded, (_, _, idx) = self(x)
+        return o.elu_hu_rint(decoded, 1000.0, 1000.0, dtype=torch.int16), idx
+
+    @torch.no_grad()
+    def encode_hu(self, hu: torch.Tensor):
+        """extract_embeddings.py:62-70 from raw int16 Hounsfield units: the hierarchical code indices, bottom -> top."""
+        return tuple(t[2] for t in self.encode(_ops.default().hu_to_network(hu)))
+
     def configure_optimizers(self):
         """model.py:91-93: Adam(lr, amsgrad=True).  CUDA parameters get the library's fused step kernel."""
         if all(p.is_cuda for p in self.parameters()):

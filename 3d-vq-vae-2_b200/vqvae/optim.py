@@ -48,6 +48,50 @@ class FusedAdamAMSGrad(torch.optim.Optimizer):
             self._slices.append((p, off, k, gv))
             off += k
 
+    def current_step(self) -> int:
+        """Optimisation steps applied so far.  In flat mode the authoritative counter is the device-side one (a CUDA-graph
+        replay advances it without the host seeing it)."""
+        if self.flat_grad is None:
+            return max((int(st.get("step", 0)) for st in self.state.values()), default=0)
+        return int(round(float(self._step_state[0])))
+
+    def state_dict(self):
+        """torch.optim.Adam's layout (per-parameter `step`, `exp_avg`, `exp_avg_sq`, `max_exp_avg_sq`), with the step
+        counters brought up to date first (in flat mode they are refreshed lazily)."""
+        if self.flat_grad is not None:
+            self._step = self.current_step()
+            for p, _, _, _ in self._slices:
+                self.state[p]["step"] = self._step
+        return super().state_dict()
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Restore a `state_dict()` (or a torch.optim.Adam(amsgrad=True) one of the same parameters).  In flat mode the
+        loaded moments are copied INTO the flat buffers and the per-parameter entries become views of them again, and the
+        step counter / bias corrections on the device are rebuilt, so the next step continues the saved trajectory."""
+        super().load_state_dict(state_dict)
+        if self.flat_grad is None:
+            return
+        step = 0
+        for p, off, k, _ in self._slices:
+            st = self.state[p]
+            for name, flat in (("exp_avg", self._m), ("exp_avg_sq", self._v), ("max_exp_avg_sq", self._vmax)):
+                view = flat[off:off + k].view(p.shape)
+                loaded = st.get(name)
+                if loaded is None:
+                    view.zero_()
+                elif loaded.data_ptr() != view.data_ptr():
+                    view.copy_(loaded.to(view.device, torch.float32))
+                st[name] = view
+            s = st.get("step", 0)
+            step = max(step, int(s.item() if torch.is_tensor(s) else s))
+            st["step"] = step
+        b1, b2 = self.param_groups[0]["betas"]
+        self._step = step
+        self._step_state.copy_(torch.tensor([float(step), 1.0 - b1 ** step, 1.0 - b2 ** step], dtype=torch.float64))
+        for p, _, _, _ in self._slices:
+            self.state[p]["step"] = step
+
     def zero_grad(self, set_to_none: bool = True):
         if self.flat_grad is None:
             return super().zero_grad(set_to_none=set_to_none)

@@ -29,7 +29,9 @@ WORKLOADS = {
     "downscaled_256x256x128": ("down", (1, 1, 256, 256, 128)),
     "downscaled_128x128x64": ("down", (1, 1, 128, 128, 64)),
 }
-CPU_SAMPLE_SHAPE = (1, 1, 128, 128, 64)     # bounded sample for the CPU arm: 1/32 of a 512x512x128 volume
+# bounded samples for the CPU arm (the Full model needs extents divisible by 64): the whole volume, a quarter, 1/32 of it
+CPU_SAMPLES = [(512, 512, 128), (256, 256, 128), (128, 128, 64)]
+DTYPE = "bf16 operands / fp32 accumulate (GEMM-shaped convolutions, tcgen05) + fp32 (thin convolutions, quantizer)"
 
 
 def peaks():
@@ -168,21 +170,36 @@ def quantizer_point(dev, pk, N=1 << 20, D=32, K=512, reps=10):
     return {"value": gc, "unit": "Gcodes/s", "config": {"N": N, "D": D, "K": K, "mode": "eval", "path": "tcgen05 bf16 candidate pass + exact fp32 re-rank"},
             "ms": t * 1e3, "roofline": {"bound": "hbm" if hbm < tens else "tensor", "peak": min(hbm, tens), "unit": "Gcodes/s", "frac": gc / min(hbm, tens),
                                         "tmem_read_ceiling": tmem, "frac_of_tmem_read_ceiling": gc / tmem},
-            "sweep": "profiles/r01_final_quantizer_sweep_tc_v2.tsv (tools/bench_quantizer.py)"}
+            "sweep": "profiles/r02_quantizer_sweep.tsv (tools/bench_quantizer.py, N up to 64 M)"}
 
 
-def train_point(dev, steps=3):
+def train_point(dev, workload, steps=3, world=1, rank=0):
+    """One optimisation step (forward in training mode with EMA codebook updates, Huber + commitment loss, backward, gradient
+    all-reduce, fused Adam(amsgrad)) of `workload`, batch 1 per GPU like the reference (train_vqvae_3d.job:76), captured as
+    ONE CUDA graph.  With world > 1 every rank calls this: the flat gradient all-reduce and the three flat [counts | dw] EMA
+    all-reduces (layers.py:645-647) are NCCL calls inside the captured step; the step time is the max over ranks."""
+    import torch.distributed as dist
     from vqvae.parallel import GraphedTrainingStep, training_step
-    kind, shape = WORKLOADS["downscaled_256x256x128"]
+    kind, shape = WORKLOADS[workload]
     torch.cuda.empty_cache()
     m = build_model(kind).to(dev).train()
     for q in m.encoder.quantize:
         q.first_pass.fill_(1)
-    x = synthetic_volume(shape, 42).to(dev)
+    x = synthetic_volume(shape, volume_seed(rank)).to(dev)
     opt = m.configure_optimizers()
     batch = (x, [shape[4]])
+    torch.cuda.reset_peak_memory_stats()
     training_step(m, opt, batch)                      # data-dependent codebook init (layers.py:665-683)
-    step = GraphedTrainingStep(m, opt, batch, warmup=2)
+    graphed = True
+    try:
+        step = GraphedTrainingStep(m, opt, batch, warmup=2)
+    except Exception as ex:                           # pragma: no cover - capture refused (e.g. NCCL build without graph support)
+        graphed = repr(ex)[:200]
+        step = lambda b: training_step(m, opt, b)
+        step(batch)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -191,17 +208,45 @@ def train_point(dev, steps=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    out = {"workload": "downscaled_256x256x128 (BASELINE.json configs[1])", "ms_per_step": ms, "volumes_per_s": 1e3 / ms, "batch": 1,
-           "loss": float(loss), "cuda_graph": True, "steps": steps,
-           "what": "forward (training mode, EMA codebook update) + backward + fused Adam(amsgrad); fp32 master weights, bf16 tcgen05 convolutions where GEMM-shaped"}
+    grad_bytes = opt.flat_grad.numel() * 4
+    ema_bytes = sum(4 * q.num_embeddings * (q.embedding_dim + 1) for q in m.encoder.quantize)
+    ar = None
+    if world > 1:                                     # the two exchanges on their own (same buffers, NCCL over NVLink)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        g = torch.zeros_like(opt.flat_grad)
+        stats = [torch.zeros(q.num_embeddings * (q.embedding_dim + 1), device=dev) for q in m.encoder.quantize]
+        for _ in range(3):
+            dist.all_reduce(g)
+        torch.cuda.synchronize()
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(g)
+        a1.record()
+        for _ in range(10):
+            for st in stats:
+                dist.all_reduce(st)
+        a2.record()
+        torch.cuda.synchronize()
+        ar = {"gradient_allreduce_us": 100.0 * a0.elapsed_time(a1), "gradient_bytes": grad_bytes,
+              "gradient_busbw_GBps": grad_bytes * 2 * (world - 1) / world / (a0.elapsed_time(a1) * 1e-4) / 1e9,
+              "ema_allreduce_us": 100.0 * a1.elapsed_time(a2), "ema_bytes": ema_bytes, "ema_calls_per_step": len(stats),
+              "backend": "nccl", "inside_timed_step": True}
+    out = {"workload": workload, "ms_per_step": ms, "volumes_per_s": world * 1e3 / ms, "batch_per_gpu": 1, "n_gpus": world,
+           "loss": float(loss), "cuda_graph": graphed, "steps": steps, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+           "parameters": opt.flat_grad.numel(), "collectives": ar,
+           "what": "forward (training mode, EMA codebook update) + backward + gradient/EMA all-reduce + fused Adam(amsgrad); fp32 master "
+                   "weights, bf16 tcgen05 convolutions where GEMM-shaped"}
     del step, m, opt
     torch.cuda.empty_cache()
     return out
 
 
 def ncu_traffic(kernel_tag):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
-    --set full capture (profiles/ncu_traffic.json, written by hand from profiles/*.summary.txt)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of that very launch (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the capture's raw page)."""
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
@@ -213,8 +258,9 @@ def ncu_traffic(kernel_tag):
 
 
 # ---------------------------------------------------------------------------------------
-def cpu_arm(kind, steps, warmup):
-    """The reference's CPU path (oracle port, ATen fp32, all host cores) on a bounded sample."""
+def cpu_forward_fn(kind):
+    """The reference's CPU path for this workload: the oracle port (ATen fp32 kernels, the same F.* calls in the same order as
+    the reference modules) on all host cores.  Returns run(sample_hwd) -> (seconds, outputs)."""
     from oracle import vqvae_oracle as O
     if _ORIGINAL_AFFINITY is not None:          # the CPU arm uses every host core, not only the GPU-local ones
         os.sched_setaffinity(0, _ORIGINAL_AFFINITY)
@@ -223,40 +269,108 @@ def cpu_arm(kind, steps, warmup):
     m = build_model(kind)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     cfg = O.FULL if kind == "full" else O.DOWNSCALED
-    x = synthetic_volume(CPU_SAMPLE_SHAPE, 42)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
+
+    def run(hwd, seed=42):
+        x = synthetic_volume((1, 1) + tuple(hwd), seed)
+        with torch.no_grad():
             t0 = time.perf_counter()
-            O.vqvae_forward(sd, cfg, x)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    return times, cores
+            out = O.vqvae_forward(sd, cfg, x)
+            return time.perf_counter() - t0, out
+    return run, cores
 
 
 def run_reference(args):
+    """`--impl reference`: every step is ONE oracle forward of a bounded sample of the workload's volume -- the whole volume if
+    K + W of them fit the budget, else a quarter or 1/32 of it (picked from one untimed probe).  `ms_per_step` is the measured
+    time of a step as run; `value` converts sample forwards to whole volumes by the voxel ratio, named in `config`."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     kind, shape = WORKLOADS[args.workload]
-    frac = (shape[2] * shape[3] * shape[4]) / (CPU_SAMPLE_SHAPE[2] * CPU_SAMPLE_SHAPE[3] * CPU_SAMPLE_SHAPE[4])
-    steps = min(args.steps, 5)
-    times, cores = cpu_arm(kind, steps, min(args.warmup, 1))
+    run, cores = cpu_forward_fn(kind)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    full_vox = shape[2] * shape[3] * shape[4]
+    samples = [hwd for hwd in CPU_SAMPLES if hwd[0] * hwd[1] * hwd[2] <= full_vox] or [tuple(shape[2:])]
+    probe_hwd = samples[-1]
+    probe_s, _ = run(probe_hwd)                                    # untimed probe (also warms the allocator / thread pool)
+    probe_s, _ = run(probe_hwd)
+    budget_s = float(os.environ.get("VQ3D_REFERENCE_BUDGET_S", "150"))
+    pick = probe_hwd
+    for hwd in samples:                                            # largest first
+        est = probe_s * (hwd[0] * hwd[1] * hwd[2]) / (probe_hwd[0] * probe_hwd[1] * probe_hwd[2])
+        if est * (steps + warmup) <= budget_s:
+            pick = hwd
+            break
+    frac = full_vox / (pick[0] * pick[1] * pick[2])
+    for _ in range(warmup):
+        run(pick)
+    times = [run(pick)[0] for _ in range(steps)]
     total = sum(times)
     value = steps / (total * frac)
-    sample = (f"{kind} model forward on a {CPU_SAMPLE_SHAPE[2]}x{CPU_SAMPLE_SHAPE[3]}x{CPU_SAMPLE_SHAPE[4]} crop "
-              f"(1/{frac:g} of the volume's voxels) per step; volumes/s = crops/s / {frac:g}")
+    sample = (f"{kind} model forward (oracle port, ATen fp32, {cores} threads) on a {pick[0]}x{pick[1]}x{pick[2]} "
+              + ("volume (the whole workload volume)" if frac == 1 else f"crop = 1/{frac:g} of the volume's voxels; volumes/s = crops/s / {frac:g}")
+              + " per step")
     print(json.dumps({
         "impl": "reference", "metric": "volumes_per_s_encode_vq_decode", "value": value, "unit": "volumes/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps * frac,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "volume": list(shape), "batch_per_gpu": args.batch},
+        "extrapolated": frac != 1, "sample_fraction_of_volume": 1.0 / frac,
+        "config": {"workload": args.workload, "volume": list(shape), "batch_per_gpu": args.batch,
+                   "workload_sample": list(pick), "volumes_per_step": 1.0 / frac},
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 # ---------------------------------------------------------------------------------------
+def pipelined(fwd, host_in, n_steps, barrier, dev, check=None):
+    """End-to-end loop with HOST buffers: every step copies `host_in` (pinned) to the device, runs fwd(device input) -> list
+    of device tensors, and copies those to pinned host buffers.  Copies ride on their own streams (double-buffered input, staged
+    outputs) so that the H2D of step i+1 and the D2H of step i-1 overlap the compute of step i; the clock (host wall clock
+    between barriers, the copies are part of it) runs until the last result is in host memory.  Returns (seconds for n_steps,
+    h2d bytes per step, d2h bytes per step, host outputs)."""
+    main = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    x_bufs = [torch.empty(host_in.shape, dtype=host_in.dtype, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_fwd_read = [torch.cuda.Event(), torch.cuda.Event()]     # fwd has consumed x_bufs[i]
+    ev_staged, ev_out = torch.cuda.Event(), torch.cuda.Event()
+    stage = host_out = None
+    t0 = None
+    for it in range(2 + n_steps):
+        if it == 2:
+            barrier()
+            t0 = time.perf_counter()
+        b = it & 1
+        with torch.cuda.stream(s_in):
+            if it >= 2:
+                s_in.wait_event(ev_fwd_read[b])
+            x_bufs[b].copy_(host_in, non_blocking=True)
+            ev_in[b].record(s_in)
+        main.wait_event(ev_in[b])
+        outs = fwd(x_bufs[b])
+        ev_fwd_read[b].record(main)
+        if stage is None:
+            stage = [torch.empty_like(o) for o in outs]
+            host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+        if it > 0:
+            main.wait_event(ev_out)              # the previous result has left the staging buffers
+        for st, o in zip(stage, outs):
+            st.copy_(o, non_blocking=True)
+        ev_staged.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_staged)
+            for h, st in zip(host_out, stage):
+                h.copy_(st, non_blocking=True)
+            ev_out.record(s_out)
+    torch.cuda.synchronize()
+    barrier()
+    secs = time.perf_counter() - t0
+    h2d = host_in.numel() * host_in.element_size()
+    d2h = sum(h.numel() * h.element_size() for h in host_out)
+    return secs, h2d, d2h, host_out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from vqvae import _ops
@@ -323,103 +437,141 @@ def run_b200(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
-        # dominant kernel, timed live in isolation on the launching stream (L2-cold: the workload's
-        # working set is far larger than the 126 MB L2 and a 256 MB scratch is rewritten between repeats)
         dom_key = max(groups, key=lambda k: groups[k][1])
         dom = groups[dom_key]
 
-        # end to end through the public API with HOST buffers: every step copies its volume from pinned host
-        # memory, runs the forward and copies the reconstruction + the three code-index tensors back to pinned host
-        # memory.  Copies ride on their own streams (double-buffered input, staged outputs) so that the H2D of
-        # volume i+1 and the D2H of result i-1 overlap the forward of volume i; the clock runs until the last
-        # result is in host memory.
-        dec_host = torch.empty(bshape, dtype=torch.float32).pin_memory()
+        # ---- end to end through the public API with HOST buffers (pinned): H2D + forward + D2H inside the clock ----
         e2e_steps = max(3, min(steps, 10))
-        main = torch.cuda.current_stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        x_bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_fwd_read = [torch.cuda.Event(), torch.cuda.Event()]     # forward has consumed x_bufs[i]
-        ev_staged, ev_out = torch.cuda.Event(), torch.cuda.Event()
-        dec_stage = idx_stage = idx_host = None
-        for it in range(2 + e2e_steps):
-            if it == 2:
-                barrier()
-                t0 = time.perf_counter()
-            b = it & 1
-            with torch.cuda.stream(s_in):
-                if it >= 2:
-                    s_in.wait_event(ev_fwd_read[b])
-                x_bufs[b].copy_(x_host, non_blocking=True)
-                ev_in[b].record(s_in)
-            main.wait_event(ev_in[b])
-            dec, (_, _, idxs) = model(x_bufs[b])
-            ev_fwd_read[b].record(main)
-            if dec_stage is None:
-                dec_stage = torch.empty_like(dec)
-                idx_stage = [torch.empty_like(i) for i in idxs]
-                idx_host = [torch.empty(i.shape, dtype=i.dtype).pin_memory() for i in idxs]
-            if it > 0:
-                main.wait_event(ev_out)              # the previous result has left the staging buffers
-            dec_stage.copy_(dec, non_blocking=True)
-            for st, d in zip(idx_stage, idxs):
-                st.copy_(d, non_blocking=True)
-            ev_staged.record(main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_staged)
-                dec_host.copy_(dec_stage, non_blocking=True)
-                for h, d in zip(idx_host, idx_stage):
-                    h.copy_(d, non_blocking=True)
-                ev_out.record(s_out)
-        torch.cuda.synchronize()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        # the pipelined loop returned the same bits as a plain call on the same volume
-        chk, (_, _, chk_idx) = model(x_dev)
-        # (split-K layers reduce with fp32 atomics, so two runs agree to rounding, not bit for bit; a latent that sits on a
-        # near-tie can then pick the other code, which changes the reconstruction around it -- allow a small fraction)
-        bad = float(((chk.cpu() - dec_host).abs() > 1e-3 + 1e-3 * dec_host.abs()).float().mean())
-        assert bad < 1e-2, f"e2e pipeline result mismatch ({bad:.2e} of the voxels)"
-        assert all(float((a.cpu() != h).float().mean()) < 1e-2 for a, h in zip(chk_idx, idx_host)), "e2e pipeline index mismatch"
-    h2d = x_host.numel() * 4
-    d2h = dec_host.numel() * 4 + sum(h.numel() * 8 for h in idx_host)
 
-    t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
+        def fwd_api(xb):                     # VQVAE.forward: fp32 volume in, fp32 reconstruction + int64 code indices out
+            dec, (_, _, idxs) = model(xb)
+            return [dec] + list(idxs)
+        e2e_s, h2d, d2h, host_out = pipelined(fwd_api, x_host, e2e_steps, barrier, dev)
+        # the pipelined loop returned the same results as a plain call on the same volumes (the forward has no atomics, so
+        # it is bit-reproducible; the tolerance only covers a change of the split-K plan between captures)
+        chk, (_, _, chk_idx) = model(x_dev)
+        bad = float(((chk.cpu() - host_out[0]).abs() > 1e-3 + 1e-3 * host_out[0].abs()).float().mean())
+        assert bad < 1e-2, f"e2e pipeline result mismatch ({bad:.2e} of the voxels)"
+        assert all(float((a.cpu() != h).float().mean()) < 1e-2 for a, h in zip(chk_idx, host_out[1:])), "e2e pipeline index mismatch"
+        del host_out, chk
+
+        # the same volumes as raw int16 Hounsfield units in, int16 Hounsfield units + code indices out (VQVAE.reconstruct_hu:
+        # the data module's clip/scale/shift and decode_embeddings' ELU*1000-1000+rint run on the device): 2 bytes per voxel
+        # each way instead of 4
+        hu_host = torch.clamp(torch.round((x_host - 1.0) * 1000.0), -32768, 32767).to(torch.int16).pin_memory()
+
+        def fwd_hu(hb):
+            hu, idxs = model.reconstruct_hu(hb)
+            return [hu] + list(idxs)
+        hu_s, hu_h2d, hu_d2h, hu_out = pipelined(fwd_hu, hu_host, e2e_steps, barrier, dev)
+        del hu_out
+
+        # BASELINE.json configs[3]: extract_embeddings end to end -- fp32 volume in, ONLY the hierarchical code indices out
+        def fwd_extract(xb):
+            return [t[2] for t in model.encode(xb)]
+        ex_s, ex_h2d, ex_d2h, _ = pipelined(fwd_extract, x_host, e2e_steps, barrier, dev)
+
+        # the box's ceiling for the fp32 API's traffic: the same buffers and streams with NO forward between the copies
+        copy_outs = [torch.empty(bshape, dtype=torch.float32, device=dev)] + [torch.empty_like(i) for i in chk_idx]
+        cp_s, _, _, _ = pipelined(lambda xb: copy_outs, x_host, e2e_steps, barrier, dev)
+        del copy_outs
+
+        # batch 1 (the reference's own operating point, train_vqvae_3d.job:76): latency of one volume, CUDA-graph replay
+        x1 = x_dev[:1].contiguous()
+        for _ in range(3):
+            model(x1)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(max(5, steps)):
+            model(x1)
+        b1.record()
+        torch.cuda.synchronize()
+        batch1_ms = b0.elapsed_time(b1) / max(5, steps)
+
+        # encode + quantize only (extract_embeddings), inputs resident in HBM
+        for _ in range(3):
+            list(model.encode(x_dev))
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(steps):
+            list(model.encode(x_dev))
+        a1.record()
+        torch.cuda.synchronize()
+        enc_ms = a0.elapsed_time(a1) / steps
+
+    t = torch.tensor([elapsed_ms, e2e_s, hu_s, ex_s, cp_s, enc_ms, batch1_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_s = float(t[0]), float(t[1])
+    elapsed_ms, e2e_s, hu_s, ex_s, cp_s, enc_ms, batch1_ms = (float(v) for v in t)
+
+    # BASELINE.json configs[1] / configs[2]: training steps.  configs[2] (Full model, 512x512x128, data parallel) runs on EVERY
+    # rank with the NCCL gradient + EMA all-reduces inside the captured step; configs[1] (downscaled, 1 GPU) on rank 0 at N = 1
+    train = {}
+    if not args.no_train:
+        model.enable_cuda_graphs(False)          # drop the inference graphs' static pools before the training steps allocate
+        del out
+        torch.cuda.empty_cache()
+        try:
+            train["full_512x512x128_dp"] = train_point(dev, "full_512x512x128", steps=3, world=world, rank=rank)
+        except Exception as ex:  # pragma: no cover
+            train["full_512x512x128_dp"] = {"error": repr(ex)[:300]}
+        if world == 1:
+            try:
+                train["downscaled_256x256x128"] = train_point(dev, "downscaled_256x256x128", steps=3)
+            except Exception as ex:  # pragma: no cover
+                train["downscaled_256x256x128"] = {"error": repr(ex)[:300]}
+        model.enable_cuda_graphs()
 
     if rank == 0:
         pk, pk_src = peaks()
         n_dom, t_dom, b_dom, f_dom = dom
         achieved = b_dom / (t_dom * 1e-3) / 1e9            # GB/s, algorithmic bytes / event time
         intensity = f_dom / max(b_dom, 1)
+        vps = lambda secs: world * e2e_steps * batch / secs
         line = {
             "metric": "volumes_per_s_encode_vq_decode", "value": aggregate(world, steps, elapsed_ms, batch), "unit": "volumes/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / steps,
             "ms_per_volume": elapsed_ms / steps / batch,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": args.workload, "volume": list(shape), "batch_per_gpu": batch,
                        "model": "3-level Full (train_vqvae_3d.job flags)" if kind == "full" else "2-level downscaled",
                        "weights": "reference ctor RNG seed 42 + Fixup init + N(0,0.02) perturbation",
                        "l2": f"inputs larger than L2 ({134 * batch} MB of volumes, GBs of activations per step)",
-                       "cuda_graph": True, "parallelism": f"dp{world} (independent volumes, no collective)",
+                       "cuda_graph": True, "parallelism": f"dp{world} (independent volumes, no collective on the inference path)",
                        "e2e": "pinned H2D / forward / D2H on three streams, double-buffered",
                        "host_cpus_bound": numa_cpus},
-            "e2e": {"value": world * e2e_steps * batch / e2e_s, "unit": "volumes/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+            "e2e": {"value": vps(e2e_s), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "VQVAE.forward (fp32 volume in; fp32 reconstruction + int64 code indices out)",
+                    "copy_only": {"value": vps(cp_s), "unit": "volumes/s", "GBps_each_way_per_gpu": (h2d + d2h) / 2 * e2e_steps / cp_s / 1e9,
+                                  "what": "the same pinned buffers, streams and bytes with no forward in between: the host<->device ceiling of this box at this N"}},
+            "e2e_hu_int16": {"value": vps(hu_s), "unit": "volumes/s", "h2d_bytes_per_step": hu_h2d, "d2h_bytes_per_step": hu_d2h,
+                             "ms_per_step": 1e3 * hu_s / e2e_steps,
+                             "api": "VQVAE.reconstruct_hu (int16 Hounsfield units in; int16 Hounsfield units + int64 code indices out; "
+                                    "clip/scale/shift and ELU*1000-1000+rint on the device)"},
+            "batch1": {"value": 1e3 / batch1_ms, "unit": "volumes/s", "ms_per_volume": batch1_ms,
+                       "what": "one 512x512x128 volume per step (the reference's batch size), CUDA-graph replay, per GPU"},
             "gpu_launches": launches_per_step * steps,
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm" if intensity < 210 else "tensor", "achieved": achieved, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
                          "kernel": f"{dom_key[0]} [{dom_key[1]}]", "launches_per_step": n_dom,
                          "avg_launch_us": 1e3 * t_dom / n_dom, "share_of_step": t_dom / prof_total,
-                         "algorithmic_bytes_per_launch": b_dom / n_dom, "flop_per_byte": intensity},
+                         "algorithmic_bytes_per_launch": b_dom / n_dom, "flop_per_byte": intensity,
+                         "whole_step": {"algorithmic_GB": 12.77 * batch if kind == "full" else None,
+                                        "achieved_GBps": (12.77 * batch / (elapsed_ms / steps * 1e-3)) if kind == "full" else None,
+                                        "frac_of_hbm": (12.77 * batch / (elapsed_ms / steps * 1e-3) / pk["hbm_gbs"]) if kind == "full" else None,
+                                        "what": "SURVEY 8d block-fused fp32 byte count (12.77 GB per volume) / step time"}},
             "kernel_shares": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / prof_total, 4)}
                               for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])},
             "top_ops": [{"op": f"{k[0]} [{k[1]}]", "n": g[0], "ms": round(g[1], 3),
                          "GBps": round(g[2] / max(g[1], 1e-9) / 1e6, 1), "TFLOPs": round(g[3] / max(g[1], 1e-9) / 1e9, 2)}
                         for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:12]],
+            "extract": {"value": world * batch * 1e3 / enc_ms, "unit": "volumes/s", "ms_per_step": enc_ms,
+                        "what": "VQVAE.encode (Encoder2 + 3 quantizers -> code indices), CUDA-graph replay, inputs resident in HBM, max over ranks",
+                        "e2e": {"value": vps(ex_s), "unit": "volumes/s", "h2d_bytes_per_step": ex_h2d, "d2h_bytes_per_step": ex_d2h,
+                                "what": "fp32 volume from pinned host memory in, only the three int64 code-index tensors out (extract_embeddings.py:62-76)"}},
         }
         if args.profile_out:
             with open(args.profile_out, "w") as f:
@@ -427,49 +579,41 @@ def run_b200(args):
                 for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1]):
                     f.write(f"{k[0]}\t{k[1]}\t{g[0]}\t{g[1]:.3f}\t{g[1] / prof_total:.4f}\t{g[2] / max(g[1], 1e-9) / 1e6:.1f}\t{g[3] / max(g[1], 1e-9) / 1e9:.2f}\n")
                 f.write(f"TOTAL\t\t{sum(g[0] for g in groups.values())}\t{prof_total:.3f}\n")
-        # second half of BASELINE.json's metric: quantizer Gcodes/s on a sweep point (configs[4]), inputs resident in HBM
+        # second half of BASELINE.json's metric: quantizer Gcodes/s on two sweep points (configs[4]), inputs resident in HBM
         try:
             line["quantizer"] = quantizer_point(dev, pk)
+            line["quantizer"]["second_point"] = quantizer_point(dev, pk, N=1 << 22, D=128, K=4096, reps=3)
         except Exception as ex:  # pragma: no cover
             line["quantizer"] = {"error": repr(ex)}
-        # BASELINE.json configs[3]: extract_embeddings = encode + quantize only (hierarchical code indices), same volume
-        try:
-            with torch.no_grad():
-                for _ in range(3):
-                    list(model.encode(x_dev))
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(steps):
-                    list(model.encode(x_dev))
-                a1.record()
-                torch.cuda.synchronize()
-            enc_ms = a0.elapsed_time(a1) / steps
-            line["extract"] = {"value": world * batch * 1e3 / enc_ms, "unit": "volumes/s", "ms_per_step": enc_ms,
-                               "what": "VQVAE.encode (Encoder2 + 3 quantizers -> code indices), CUDA-graph replay, per-rank time of rank 0"}
-        except Exception as ex:  # pragma: no cover
-            line["extract"] = {"error": repr(ex)}
-        # BASELINE.json configs[1]: one training step of the 2-level downscaled model on a 256x256x128 volume (forward in training
-        # mode with EMA updates, backward, fused Adam), captured as one CUDA graph; reported next to the headline, not part of it
-        if not args.no_train and world == 1:
-            try:
-                line["train_step"] = train_point(dev)
-            except Exception as ex:  # pragma: no cover
-                line["train_step"] = {"error": repr(ex)}
+        if train:
+            line["train_step"] = train
         traffic = ncu_traffic(f"{dom_key[0]} [{dom_key[1]}]")
         if traffic is not None:
             line["roofline"]["traffic"] = traffic["dram_bytes_per_launch"]
             line["roofline"]["traffic_source"] = traffic["source"]
         if not args.no_cpu_baseline and world == 1:
-            frac = (shape[2] * shape[3] * shape[4]) / (CPU_SAMPLE_SHAPE[2] * CPU_SAMPLE_SHAPE[3] * CPU_SAMPLE_SHAPE[4])
-            times, cores = cpu_arm(kind, 3, 1)
-            line["cpu_baseline"] = {
-                "value": 1.0 / (min(times) * frac), "unit": "volumes/s", "cores": cores, "kind": "port",
-                "median_value": 1.0 / (sorted(times)[len(times) // 2] * frac),
-                "sample": f"oracle (ATen fp32) forward of the same model on a {CPU_SAMPLE_SHAPE[2]}x{CPU_SAMPLE_SHAPE[3]}x"
-                          f"{CPU_SAMPLE_SHAPE[4]} crop = 1/{frac:g} of the voxels; best of 3, scaled by 1/{frac:g}"}
+            # the oracle on ONE whole volume of this workload (volume 0 of rank 0) on all host cores: the CPU baseline, and the
+            # checker for the GPU's code indices on the benchmarked configuration (both precision modes)
+            run_cpu, cores = cpu_forward_fn(kind)
+            secs, (ref_dec, (_, _, ref_idx)) = run_cpu(tuple(shape[2:]), seed=volume_seed(rank, 0, batch))
+            line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "volumes/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle (ATen fp32, {cores} threads) forward of the same model on ONE whole "
+                                              f"{shape[2]}x{shape[3]}x{shape[4]} volume (volume 0 of the batch), {secs:.1f} s, no extrapolation"}
+            mism = {}
+            model.enable_cuda_graphs(False)
+            with torch.no_grad():
+                for mode in ("bf16", "fp32"):
+                    prev, ops.precision = ops.precision, mode
+                    try:
+                        dec1, (_, _, idx1) = model(x_dev[:1].contiguous())
+                        mism[mode] = {"index_mismatch_bottom_to_top": [float((a.cpu() != b).float().mean()) for a, b in zip(idx1, ref_idx)],
+                                      "decoded_mean_abs_err_rel_to_range": float((dec1.cpu() - ref_dec).abs().mean() / ref_dec.abs().max())}
+                    finally:
+                        ops.precision = prev
+            line["extract"]["index_mismatch_vs_oracle"] = mism
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -482,7 +626,7 @@ def main():
     ap.add_argument("--workload", default="full_512x512x128", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=8, help="independent volumes per step and GPU (stacked along B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the training-step point (configs[1])")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step points (configs[1], configs[2])")
     ap.add_argument("--profile-out", default=None, help="write the per-op CUDA-event table of one eager step here")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -47,7 +47,7 @@ int vq3d_is_cuda_build(void);
  *                summation order of torch.cdist(compute_mode='donot_use_mm_for_euclid_dist')
  *   quant[b,d,s] = x + (embed[idx[b,s], d] - x) (straight-through value, layers.py:720, same two
  *                roundings; the codebook BEFORE this step's EMA update)
- *   *sqerr    += sum (embed[idx] - x)^2             (double accumulator; caller zeroes it)
+ *   *sqerr     = sum (embed[idx] - x)^2             (double accumulator; zeroed by the call itself)
  *   counts[k] += #{idx == k};  dw[k,d] += sum_{idx==k} x[.,d,.]   (fp32; caller zeroes)
  * x, quant: [B, D, S]; idx: [B, S] int64; embed: [K, D]; counts/dw may both be NULL (eval).
  */
@@ -140,9 +140,10 @@ int vq3d_conv3d(const vq3d_conv_desc *desc, void *stream);
  * VQ3D_ERR_UNSUPPORTED when C_in*k^3 < 32, C_out < 8 or C_out > 256 (callers fall back to
  * vq3d_conv3d).  Results agree with the fp32 kernel to bf16 operand rounding (~1e-2 relative).
  * Layers with few output voxels and a long reduction (128 -> 128 k3 at 8x8x2 ...) are split along K
- * across CTAs and reduced through `ws` (fp32 atomics, so their summation order varies run to run):
- * pass a 16-byte aligned device buffer of vq3d_conv3d_tc_workspace(desc) bytes (0 = no split wanted
- * for this shape); with ws == NULL the layer runs unsplit.  The call zeroes what it uses.
+ * across CTAs: every K slice stores its partial tile into its own slab of `ws` and a second kernel adds
+ * the slabs in slice order and applies the epilogue (no atomics: bit-reproducible run to run).
+ * Pass a 16-byte aligned device buffer of vq3d_conv3d_tc_workspace(desc) bytes (0 = no split wanted
+ * for this shape); with ws == NULL the layer runs unsplit.
  */
 size_t vq3d_conv3d_tc_workspace(const vq3d_conv_desc *desc);
 int vq3d_conv3d_tc(const vq3d_conv_desc *desc, void *ws, size_t ws_bytes, void *stream);
@@ -311,6 +312,22 @@ int vq3d_huber_elu_mask(const float *decoded, const float *x, const int32_t *num
  * (the reference: F.elu, then numpy `res * 1000 - 1000`, np.rint, astype(int)); n elements.
  */
 int vq3d_elu_hu_rint(const float *decoded, int64_t n, double scale, double offset, int64_t *out, void *stream);
+
+/*
+ * The same epilogue with an int16 result (saturating): Hounsfield units of CT volumes fit 16 bits (the reference clips its
+ * inputs to [-1500, 3000], utils/load_nrrd_dataset.py:73-81), so a volume leaves the device in 2 bytes per voxel instead of
+ * the 8 of `astype(int)` (decode_embeddings.py:47).  decoded 16-byte aligned, out 8-byte aligned.
+ */
+int vq3d_elu_hu_rint_i16(const float *decoded, int64_t n, double scale, double offset, int16_t *out, void *stream);
+
+/*
+ * CT front end of the reference's data module, utils/load_nrrd_dataset.py:73-81, on raw int16 Hounsfield units:
+ *   out[i] = clip(hu[i], min_hu, max_hu) * mul + add        (fp32, product and sum rounded separately)
+ * = ThresholdIntensity(3000) / ThresholdIntensity(-1500) / ScaleIntensity(factor = -1 + 1/1000) / ShiftIntensity(1) with
+ * (min_hu, max_hu, mul, add) = (-1500, 3000, 0.001f, 1).  A volume enters the device in 2 bytes per voxel and becomes the
+ * network's fp32 (B, 1, H, W, D) input there.  hu 8-byte aligned, out 16-byte aligned; n elements.
+ */
+int vq3d_hu_to_network(const int16_t *hu, int64_t n, double min_hu, double max_hu, double mul, double add, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ struct dim3 {
 };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 inline float2 make_float2(float a, float b) { return float2{a, b}; }
 
@@ -175,6 +176,8 @@ inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __expf(float a) { return expf(a); }
 inline float __fdividef(float a, float b) { return a / b; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcs(const T *p) { return *p; }
+template <typename T> inline void __stcs(T *p, T v) { *p = v; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }

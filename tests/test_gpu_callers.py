@@ -86,3 +86,37 @@ def test_train_loop_two_steps_and_checkpoint(tmp_path):
     assert all(torch.isfinite(p).all() for p in m.parameters())
     assert int(m.encoder.quantize[0].first_pass) == 0                 # the EMA init ran (layers.py:665-683)
     assert abs(float(m.encoder.quantize[0].cluster_size.sum()) - float(m.encoder.quantize[0].cluster_size.numel())) > 1e-3
+
+
+def test_train_resume_from_checkpoint(tmp_path):
+    """`--resume-from-checkpoint` (train_vqvae_3d.job:87): weights, EMA codebooks, Adam moments and the step counter come
+    back (checked tensor by tensor on a fresh model + optimizer), a resumed run continues the step count, and the
+    validation monitor writes best.ckpt (ModelCheckpoint(monitor='val_recon_loss_mean'), train.py:56)."""
+    from vqvae import train
+    from vqvae.model import VQVAE
+    base = ["synthetic:4:16x16x8", "--batch-size", "1", "--n-bottleneck-blocks", "2", "--n-downscales-per-bottleneck", "1",
+            "--num-embeddings", "16", "24", "--n-pre-quantization-blocks", "1", "--n-post-quantization-blocks", "1",
+            "--extract-center-cylinder", "False", "--base_lr", "1e-3", "--num-workers", "0", "--log-every-n-steps", "1",
+            "--default-root-dir", str(tmp_path)]
+    args = train.parse_arguments(base + ["--max-steps", "2", "--val-dataset-path", "synthetic:2:16x16x8"])
+    train.main(args)
+    ck_path = tmp_path / "checkpoints" / "last.ckpt"
+    assert (tmp_path / "checkpoints" / "best.ckpt").exists()
+    half = torch.load(ck_path, weights_only=False)
+    assert half["global_step"] == 2
+    osd = half["optimizer_states"][0]
+    assert all(int(st["step"]) == 2 for st in osd["state"].values())
+    m = VQVAE(args).to(DEV).train()
+    opt = m.configure_optimizers()
+    train.load_checkpoint(m, opt, ck_path)
+    assert opt.current_step() == 2
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), half["state_dict"][k]), k
+    for i, p in enumerate(opt.param_groups[0]["params"]):
+        for name in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+            assert torch.equal(opt.state[p][name].cpu(), osd["state"][i][name]), (i, name)
+    assert float(opt._m.abs().sum()) > 0
+    train.main(train.parse_arguments(base + ["--max-steps", "4", "--resume-from-checkpoint", str(ck_path)]))
+    done = torch.load(ck_path, weights_only=False)
+    assert done["global_step"] == 4
+    assert all(int(st["step"]) == 4 for st in done["optimizer_states"][0]["state"].values())

@@ -1,0 +1,188 @@
+"""The BENCHMARKED configuration pinned to the oracle (run on the B200 box: pytest -m gpu).
+
+bench.py's headline workload is the Full 3-level model (train_vqvae_3d.job:77-86 flags, bench.build_model) on synthetic
+512x512x128 volumes, batch 8, in the product's default bf16 tensor-core mode.  The oracle (ATen fp32 on the host cores,
+oracle/vqvae_oracle.py) runs ONE such volume in tens of seconds, so it is computed once per session and every test here
+compares against it:
+
+  * teacher-forced index exactness on the oracle's real latents at all three levels (524 288 x 2 x 128, 8 192 x 8 x 256,
+    128 x 32 x 512; layers.py:700-703) -- bit-exact, both precision modes share the fp32 quantizer;
+  * teacher-forced decoder (the oracle's quantised tensors through the product decoder, model.py:85-89):
+    fp32 mode within 1e-4 of the volume's dynamic range... stated below per assertion; bf16 mode within 1e-2 of it
+    (north_star's max-abs tolerances);
+  * free-running forward: per-level index mismatch rate against the oracle, asserted and printed (the same numbers go into
+    bench.py's `extract.index_mismatch_vs_oracle`);
+  * batch 8 == 8 single-volume forwards in bf16 mode (bench.py stacks volumes along B);
+  * quantizer sweep sizes of BASELINE.json configs[4] up to 64 M vectors: index-exact against the C oracle on 65 536-row
+    slabs spread over the tensor, and against the exact fp32 scan kernel on every row.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import vqvae_oracle as O
+from vqvae import layers as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SHAPE = (1, 1, 512, 512, 128)
+
+
+@pytest.fixture(scope="module")
+def full():
+    """(model on the GPU, oracle results for volume seed 42) -- the oracle forward runs once (tens of seconds)."""
+    import bench
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = bench.build_model("full")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = bench.synthetic_volume(SHAPE, bench.volume_seed(0))
+    lat = {}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref_dec, (ref_loss, ref_q, ref_idx) = O.vqvae_forward(sd, O.FULL, x, collect=lat)
+    print(f"\noracle forward of one 512x512x128 volume: {time.perf_counter() - t0:.1f} s on {os.cpu_count()} cores")
+    return dict(model=m.to(DEV), x=x, dec=ref_dec, loss=ref_loss, q=ref_q, idx=ref_idx, lat=lat)
+
+
+def _mode(precision):
+    from vqvae import _ops
+    o = _ops.default()
+    prev, o.precision = o.precision, precision
+    return o, prev
+
+
+def test_full_512_teacher_forced_indices_are_exact(full):
+    """The oracle's real latents through the CUDA quantizers: bit-exact indices and straight-through values."""
+    m = full["model"]
+    sizes = []
+    with torch.no_grad():
+        for i, qz in enumerate(m.encoder.quantize):
+            lat = full["lat"][f"latent_{i}"]
+            loss, quant, got = qz(lat.to(DEV))
+            sizes.append((lat.numel() // lat.shape[1], lat.shape[1], qz.num_embeddings))
+            assert torch.equal(got.cpu(), full["idx"][i]), (i, int((got.cpu() != full["idx"][i]).sum()))
+            assert torch.equal(quant.cpu(), full["q"][i].contiguous()), i
+            assert abs(float(loss) - float(full["loss"][i])) <= 1e-5 * abs(float(full["loss"][i])) + 1e-9
+    assert sizes == [(524288, 2, 128), (8192, 8, 256), (128, 32, 512)]
+
+
+@pytest.mark.parametrize("precision,tol_max,tol_mean", [("fp32", 1e-4, 1e-5), ("bf16", 1e-2, 1.5e-3)])
+def test_full_512_teacher_forced_decoder(full, precision, tol_max, tol_mean):
+    """Oracle quantised tensors -> product decoder (361 blocks) vs the oracle's reconstruction.  Tolerances are max-abs /
+    mean-abs errors relative to the reconstruction's dynamic range (max |decoded|)."""
+    m = full["model"]
+    o, prev = _mode(precision)
+    try:
+        with torch.no_grad():
+            dec = m.decoder([t.contiguous().to(DEV) for t in full["q"]]).cpu()
+    finally:
+        o.precision = prev
+    ref = full["dec"]
+    scale = float(ref.abs().max())
+    emax, emean = float((dec - ref).abs().max()), float((dec - ref).abs().mean())
+    print(f"\nteacher-forced decoder [{precision}]: max-abs {emax:.3e}, mean-abs {emean:.3e}, range {scale:.3f} "
+          f"-> {emax / scale:.2e} / {emean / scale:.2e} relative")
+    assert emax <= tol_max * scale, (precision, emax, scale)
+    assert emean <= tol_mean * scale, (precision, emean, scale)
+
+
+@pytest.mark.parametrize("precision,max_mismatch", [("fp32", 0.01), ("bf16", 0.03)])
+def test_full_512_free_running_vs_oracle(full, precision, max_mismatch):
+    """The whole forward from the volume: per-level code-index mismatch rate against the oracle (a latent on a near-tie may
+    pick the other code once the convolutions sum in a different order / round operands to bf16) and the reconstruction."""
+    m = full["model"]
+    o, prev = _mode(precision)
+    try:
+        with torch.no_grad():
+            dec, (losses, quants, idxs) = m(full["x"].to(DEV))
+            dec = dec.cpu()
+    finally:
+        o.precision = prev
+    mism = [float((a.cpu() != b).float().mean()) for a, b in zip(idxs, full["idx"])]
+    ref = full["dec"]
+    scale = float(ref.abs().max())
+    emean = float((dec - ref).abs().mean())
+    print(f"\nfree-running [{precision}]: index mismatch vs oracle bottom->top {['%.5f' % v for v in mism]}, "
+          f"decoded mean-abs err {emean:.3e} (range {scale:.3f})")
+    assert max(mism) <= max_mismatch, (precision, mism)
+    assert emean <= (2e-3 if precision == "fp32" else 1e-2) * scale
+    for a, b in zip(losses, full["loss"]):
+        assert abs(float(a) - float(b)) <= 0.05 * abs(float(b)) + 1e-6
+
+
+def test_full_512_batch8_equals_singles_bf16(full):
+    """bench.py's step: 8 volumes stacked along B in bf16 mode against the same 8 volumes one at a time."""
+    import bench
+    m = full["model"]
+    o, prev = _mode("bf16")
+    try:
+        with torch.no_grad():
+            xs = [bench.synthetic_volume(SHAPE, bench.volume_seed(0, i, 8)).to(DEV) for i in range(8)]
+            dec_b, (_, _, idx_b) = m(torch.cat(xs))
+            worst_idx, worst_dec = 0.0, 0.0
+            for i, x in enumerate(xs):
+                dec, (_, _, idx) = m(x)
+                for lvl in range(3):
+                    worst_idx = max(worst_idx, float((idx_b[lvl][i:i + 1] != idx[lvl]).float().mean()))
+                worst_dec = max(worst_dec, float((dec_b[i:i + 1] - dec).abs().mean() / dec.abs().mean()))
+                del dec, idx
+    finally:
+        o.precision = prev
+    print(f"\nbatch 8 vs singles [bf16]: worst per-level index mismatch {worst_idx:.5f}, worst relative mean-abs decoded diff {worst_dec:.3e}")
+    assert worst_idx <= 0.01 and worst_dec <= 5e-3, (worst_idx, worst_dec)
+
+
+# ---- BASELINE.json configs[4]: the quantizer sweep's large sizes -------------------------------------------------------
+@pytest.mark.parametrize("N,D,K,slabs", [(1 << 24, 32, 512, 24), (1 << 26, 32, 512, 32), (1 << 24, 64, 1024, 8),
+                                         (1 << 24, 128, 4096, 3), (1 << 25, 128, 512, 6)])
+def test_quantizer_sweep_sizes_index_exact(N, D, K, slabs):
+    """N up to 64 M latent vectors: (a) the tensor-core path equals the exact fp32 scan kernel on EVERY row, (b) both equal
+    the C oracle (cdist + argmin in the reference's arithmetic, oracle chunked in 65 536-row slabs as BASELINE.md 4 says) on
+    `slabs` slabs spread over the tensor including the first and the last one, (c) codewords are fixed points."""
+    from vqvae import _ops
+    o = _ops.default()
+    g = torch.Generator(device=DEV).manual_seed(N % 1000 + D + K)
+    x = torch.randn(1, D, N // 4096, 64, 64, generator=g, device=DEV)
+    e = torch.randn(K, D, generator=torch.Generator().manual_seed(K + D))
+    q = L.Quantizer(K, D, 0.1)
+    q.embed.copy_(e); q.first_pass.fill_(0)
+    q = q.eval().to(DEV)
+    o.profile = []
+    try:
+        with torch.no_grad():
+            _, quant, idx = q(x)
+            torch.cuda.synchronize()
+            assert [p[0] for p in o.profile][0] == "vq_assign_tc"
+            o.vq_tensor_cores = False
+            _, quant_s, idx_s = q(x)
+            torch.cuda.synchronize()
+            assert [p[0] for p in o.profile][-2] == "vq_assign"
+    finally:
+        o.profile = None
+        o.vq_tensor_cores = True
+    assert torch.equal(idx, idx_s), int((idx != idx_s).sum())
+    assert torch.equal(quant, quant_s)
+    del quant_s, idx_s
+    flat_idx = idx.reshape(-1)
+    xs = x.reshape(D, N)
+    rows = 65536
+    nslab = N // rows
+    picks = sorted(set([0, nslab - 1] + [int(v) for v in np.random.RandomState(N % 97).randint(0, nslab, size=max(slabs - 2, 0))]))
+    en = e.numpy()
+    for s in picks:
+        xh = xs[:, s * rows:(s + 1) * rows].t().contiguous().cpu().numpy()
+        ref, _ = O.vq_assign_c(xh, en)
+        got = flat_idx[s * rows:(s + 1) * rows].cpu().numpy()
+        assert np.array_equal(got, ref), (s, int((got != ref).sum()))
+    # idempotence on a slice (size-independent property)
+    with torch.no_grad():
+        _, _, idx2 = q(quant[:, :, :16].contiguous())
+    assert torch.equal(q.embed[idx2], q.embed[idx[:, :16]])

@@ -41,17 +41,17 @@ def main():
     if a.simt:
         _ops.default().vq_tensor_cores = False
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
-    Ns = [1 << 20] if a.quick else [1 << 20, 1 << 22, 1 << 24]
+    Ns = [1 << 20] if a.quick else [1 << 20, 1 << 22, 1 << 24, 1 << 26]      # BASELINE.json configs[4]: 1 M ... 64 M
     rows = []
     for N in Ns:
         for K in (512, 1024, 4096):
             for D in (32, 64, 128):
-                if N * D * 4 * 2 > 40e9:
+                if N * D * 4 * 2 > 80e9:            # x + quantized (fp32) must fit comfortably: 64 M x D128 = 69 GB
                     continue
                 for training in (False, True):
                     if training and (a.quick or N > (1 << 22)):
                         continue
-                    t = run(N, D, K, training, reps=3 if N >= (1 << 24) else 5)
+                    t = run(N, D, K, training, reps=2 if N >= (1 << 26) else 3 if N >= (1 << 24) else 5)
                     gc = N / t / 1e9
                     hbm = pk["hbm_gbs"] * 1e9 / (8 * D + 8) / 1e9
                     tens = pk["bf16_tflops_sustained"] * 1e12 / (2.0 * K * D) / 1e9
