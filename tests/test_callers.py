@@ -143,6 +143,28 @@ def test_elu_hu_rint_kernel_on_the_emulator():
     assert got.dtype == torch.int64 and np.array_equal(got.numpy(), ref)
 
 
+def test_int16_hounsfield_kernels_on_the_emulator():
+    """vq3d_hu_to_network (clip / * 0.001f / + 1: utils/load_nrrd_dataset.py:73-81) against the numpy front end, and
+    vq3d_elu_hu_rint_i16 against the int64 epilogue incl. saturation and the n % 4 tail."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu.emu_ops import use_emulator
+    from utils.volumes import preprocess_hu
+    from vqvae import _ops
+    rs = np.random.RandomState(0)
+    hu = rs.randint(-4000, 6000, size=(1, 1, 5, 7, 9)).astype(np.int16)          # 315 elements: exercises the scalar tail
+    hu.reshape(-1)[:4] = [-32768, 32767, -1500, 3000]
+    with use_emulator():
+        got = _ops.default().hu_to_network(torch.from_numpy(hu))
+        assert got.dtype == torch.float32 and np.array_equal(got.numpy(), preprocess_hu(hu))
+        assert abs(float(got.min()) + 0.5) < 1e-6 and abs(float(got.max()) - 4.0) < 1e-6      # the reference's value range
+        x = torch.from_numpy(rs.standard_normal((1, 1, 5, 7, 9)).astype(np.float32) * 2)
+        x.reshape(-1)[:3] = torch.tensor([40.0, -50.0, 0.0005])                    # 39 000 HU saturates to 32 767
+        a = _ops.default().elu_hu_rint(x)
+        b = _ops.default().elu_hu_rint(x, dtype=torch.int16)
+    assert b.dtype == torch.int16 and np.array_equal(b.numpy(), np.clip(a.numpy(), -32768, 32767).astype(np.int16))
+    assert int(b.reshape(-1)[0]) == 32767 and int(b.reshape(-1)[1]) == -2000
+
+
 def test_decode_database_iteration_and_names():
     from vqvae.decode_embeddings import iter_samples, output_name
     db = {0: {"a": {"data": torch.ones(2, 2, 2, dtype=torch.long), "condition": "t1"},

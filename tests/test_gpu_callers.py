@@ -120,3 +120,56 @@ def test_train_resume_from_checkpoint(tmp_path):
     done = torch.load(ck_path, weights_only=False)
     assert done["global_step"] == 4
     assert all(int(st["step"]) == 4 for st in done["optimizer_states"][0]["state"].values())
+
+
+def test_hounsfield_int16_in_and_out_against_the_oracle():
+    """VQVAE.reconstruct_hu / encode_hu: raw int16 HU -> (device) clip, * 0.001f, + 1 (utils/load_nrrd_dataset.py:73-81) ->
+    forward -> ELU * 1000 - 1000, rint (decode_embeddings.py:43-47) -> int16 HU, against the numpy front end + oracle forward."""
+    from utils.volumes import preprocess_hu
+    m = _model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    rs = np.random.RandomState(5)
+    hu = rs.randint(-2500, 4000, size=(2, 1, 16, 16, 8)).astype(np.int16)
+    x = torch.from_numpy(preprocess_hu(hu))
+    ref_dec, (_, _, ref_idx) = O.vqvae_forward(sd, O.ModelConfig(**CFG), x)
+    ref_hu = np.clip(np.rint(torch.nn.functional.elu(ref_dec).numpy() * 1000 - 1000), -32768, 32767).astype(np.int16)
+    m = m.to(DEV)
+    got_hu, idx = m.reconstruct_hu(torch.from_numpy(hu).to(DEV))
+    assert got_hu.dtype == torch.int16 and got_hu.shape == hu.shape
+    for a, b in zip(idx, ref_idx):
+        assert torch.equal(a.cpu(), b)
+    diff = np.abs(got_hu.cpu().numpy().astype(np.int32) - ref_hu.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-2            # fp32 conv rounding can move a value across a .5 boundary
+    for a, b in zip(m.encode_hu(torch.from_numpy(hu).to(DEV)), ref_idx):
+        assert torch.equal(a.cpu(), b)
+    from vqvae import _ops
+    assert torch.equal(_ops.default().hu_to_network(torch.from_numpy(hu).to(DEV)).cpu(), x)
+
+
+def test_decoder_tail_with_two_output_channels_falls_back():
+    """input_channels = 2: the fused `out` tail only covers C -> 1; with two output channels the decoder must run
+    the 1x1 on its own and return both channels, equal to the oracle."""
+    from vqvae.model import VQVAE
+    cfg = dict(CFG, input_channels=2)
+    torch.manual_seed(3)
+    m = VQVAE(VQVAE.default_args(extract_center_cylinder=False, **cfg))
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.05)
+        for q in m.encoder.quantize:
+            q.first_pass.fill_(0)
+    m.eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.rand(1, 2, 16, 16, 8, generator=torch.Generator().manual_seed(9)) * 4.5 - 0.5
+    ref_dec, (ref_loss, _, ref_idx) = O.vqvae_forward(sd, O.ModelConfig(**cfg), x)
+    m = m.to(DEV)
+    with torch.no_grad():
+        dec, (_, _, idx) = m(x.to(DEV))
+    assert dec.shape == (1, 2, 16, 16, 8)
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(idx, ref_idx))
+    assert torch.allclose(dec.cpu(), ref_dec, rtol=1e-4, atol=1e-5)
+    # the Huber epilogue covers both channels (model.py:163)
+    loss, log = m.huber((x.to(DEV), [6]))
+    ref_total, ref_recon = O.huber_epilogue(ref_dec, x, [6], list(ref_loss), cylinder=False)
+    assert abs(float(log["recon_loss_mean"]) - float(ref_recon)) <= 1e-5 * abs(float(ref_recon)) + 1e-7
