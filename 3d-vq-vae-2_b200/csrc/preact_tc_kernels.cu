@@ -60,6 +60,8 @@ struct TcsParams {
     int IH, IW, IZ, NL;
     int L0, NMB, NLA;
     int ntiles, nblocks;
+    int t1_ready;                          // 1: t1[0] was written by an earlier kernel and the residual of block 0 is already in y
+                                           //    (the 'up' block: vq3d_preact_up_tc); no prologue, no leading grid barrier
     uint32_t tmem_cols;
     unsigned int *sync;                    // grid barrier counter (zeroed by the host before the launch)
     unsigned long long *trace;             // debug timeline or NULL
@@ -121,7 +123,7 @@ struct TcsCfg {
     static constexpr uint32_t WIMG = W2BYTES + 2 * WPBYTES;      // per block image [W1 | W2 | W3]
     static constexpr uint32_t LBO_B2 = (uint32_t)CBP * 16;       // conv2 and conv1 images: CBP rows per k-chunk
     static constexpr uint32_t LBO_B3 = (uint32_t)CP * 16;        // conv3 image: CP rows per k-chunk
-    static constexpr uint32_t SAP = (uint32_t)CP * 256;          // per consumer group staging: 128 rows x CP bf16 (A3 aliases A1)
+    static constexpr uint32_t SAP = (uint32_t)(CP > CBP ? CP : CBP) * 256;   // per consumer group staging: 128 rows x max(CP, CBP) bf16 (A3 aliases A1)
     static size_t smem_bytes(int NLA, int nbuf, int ng) {
         return 128 + WIMG + (size_t)nbuf * NCH * NLA * 16 + (size_t)ng * SAP;
     }
@@ -155,7 +157,7 @@ tcs_prep_kernel(const __grid_constant__ TcsParams p, unsigned char *wimg) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int c = kc * 8 + e;
-                wv[e] = (real && n < CB && c < C) ? __ldg(bp.w1 + n * C + c) : 0.0f;
+                wv[e] = (real && bp.w1 != nullptr && n < CB && c < C) ? __ldg(bp.w1 + n * C + c) : 0.0f;
             }
             dst = img + (size_t)kc * Cfg::LBO_B2 + (size_t)n * 16;
         } else if (i < n1 + n2) {                       // W2: per tap, rows n = co, K = ci
@@ -236,7 +238,7 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
     const int IW = p.IW, IZ = p.IZ, IWZ = p.IW * p.IZ;
 
     // ---- prologue: t1 of block 0 from x (pointwise SIMT, grid-stride over voxels; fp32 weights in the A area) ----
-    {
+    if (!p.t1_ready) {
         const TcsBlock &b0 = p.blk[0];
         float *sw1 = reinterpret_cast<float *>(sA);          // [C][CB4]
         for (int i = tid; i < C * CB4; i += NT) {
@@ -294,7 +296,7 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
         if (tid == 0) tc_trace(p.trace, blk, 0);
         const uint4 *t1src = p.t1[blk & 1];
         uint4 *t1dst = p.t1[(blk + 1) & 1];
-        const float *resid = blk == 0 ? p.x : p.y;
+        const float *resid = (blk == 0 && !p.t1_ready) ? p.x : p.y;
 
         if (warp == 0) {
             // ================= weights (one image copy) + MMA issue for conv2 (warp 0, one elected lane) ==========
@@ -702,6 +704,246 @@ static const TcsEntry *find_tcs(const vq3d_preact_desc *d) {
     return nullptr;
 }
 
+// =====================================================================================================================
+// 'up' blocks (mode 2, layers.py:124-132,176-195,591-597) on the same tensor-core kernel.
+//
+//   t1_lo = ELU(conv1x1(ELU(x+b1a)+b1b) + b2a) + b2b                  low resolution, fp32        (up_lo_kernel, SIMT)
+//   s_lo  = conv1x1(x + b1c; w_skip) + b1d                            low resolution, fp32        (the same kernel)
+//   t1_hi = bf16(trilinear_x2(t1_lo))   -> the stack kernel's haloed workspace layout             (up_expand_kernel, SIMT)
+//   y     = trilinear_x2(s_lo)          (the 1x1 skip convolution commutes with the interpolation, whose weights sum to 1)
+//   y    += conv1x1(ELU(conv3x3x3_circular(t1_hi) + b3a) + b3b) * scale + b4     preact_tc_kernel<Cout, Cb>, one block,
+//                                                                                t1_ready: no prologue, residual = y
+// The low-resolution work is 1/8 of the voxels; the expansion is write bound (32 B of bf16 t1 + 4 Cout B per output voxel).
+template <int T>
+__global__ void __launch_bounds__(T)
+up_lo_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float *__restrict__ wskip, const float *b1a_p, const float *b1b_p,
+             const float *b2a_p, const float *b2b_p, const float *b1c_p, const float *b1d_p, float *__restrict__ t1_lo, float *__restrict__ s_lo,
+             int64_t total, int64_t S, int Cin, int Cb, int Cout) {
+    VQ3D_DYN_SMEM(float, sm);
+    const int Cb4 = (Cb + 3) & ~3, Co4 = (Cout + 3) & ~3;
+    float *sw1 = sm;                                   // [Cin][Cb4]
+    float *swk = sw1 + (size_t)Cin * Cb4;              // [Cin][Co4]
+    float *sx = swk + (size_t)Cin * Co4;               // [Cin][T] activated input
+    float *sr = sx + (size_t)Cin * T;                  // [Cin][T] raw input + b1c
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cin * Cb4; i += T) { const int cb = i % Cb4, ci = i / Cb4; sw1[i] = cb < Cb ? __ldg(w1 + (size_t)cb * Cin + ci) : 0.0f; }
+    for (int i = tid; i < Cin * Co4; i += T) { const int co = i % Co4, ci = i / Co4; swk[i] = co < Cout ? __ldg(wskip + (size_t)co * Cin + ci) : 0.0f; }
+    const float b1a = ld_scalar(b1a_p, 0.f), b1b = ld_scalar(b1b_p, 0.f), b2a = ld_scalar(b2a_p, 0.f), b2b = ld_scalar(b2b_p, 0.f);
+    const float b1c = ld_scalar(b1c_p, 0.f), b1d = ld_scalar(b1d_p, 0.f);
+    __syncthreads();
+    for (int64_t v = (int64_t)blockIdx.x * T + tid; v < total; v += (int64_t)gridDim.x * T) {
+        const int64_t b = v / S, r = v - b * S;
+        const float *px = x + (size_t)b * Cin * S + r;
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float xv = __ldcs(px + (size_t)ci * S);
+            sx[ci * T + tid] = elu1(xv + b1a) + b1b;
+            sr[ci * T + tid] = xv + b1c;
+        }
+        float *pt = t1_lo + (size_t)b * Cb * S + r;
+        for (int c0 = 0; c0 < Cb; c0 += 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float a = sx[ci * T + tid];
+                const float4 w = *reinterpret_cast<const float4 *>(sw1 + ci * Cb4 + c0);
+                a0 = __fmaf_rn(w.x, a, a0); a1 = __fmaf_rn(w.y, a, a1); a2 = __fmaf_rn(w.z, a, a2); a3 = __fmaf_rn(w.w, a, a3);
+            }
+            const float o[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < Cb) pt[(size_t)(c0 + j) * S] = elu1(o[j] + b2a) + b2b;
+        }
+        float *ps = s_lo + (size_t)b * Cout * S + r;
+        for (int c0 = 0; c0 < Cout; c0 += 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float a = sr[ci * T + tid];
+                const float4 w = *reinterpret_cast<const float4 *>(swk + ci * Co4 + c0);
+                a0 = __fmaf_rn(w.x, a, a0); a1 = __fmaf_rn(w.y, a, a1); a2 = __fmaf_rn(w.z, a, a2); a3 = __fmaf_rn(w.w, a, a3);
+            }
+            const float o[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < Cout) ps[(size_t)(c0 + j) * S] = o[j] + b1d;
+        }
+    }
+}
+
+// nn.Upsample(scale_factor=2, 'trilinear', align_corners=False) (layers.py:594): out[2i] = .25 in[max(i-1,0)] + .75 in[i],
+// out[2i+1] = .75 in[i] + .25 in[min(i+1,n-1)] per axis.  One work item = one low-resolution depth index of one output (h2, w2)
+// column = two output voxels of 8 channels; a CTA owns a compact 4 x 8 patch of output columns so that the 12 low-resolution
+// values an item reads per channel are L1 hits for all but the first toucher (a row-major item order made every load an L2
+// access: 13.7 GB of L2 traffic for the 18 -> 9 -> 8 block at batch 8).  blockIdx.y selects the 8-channel job: the bf16 t1 chunks
+// first (written in the tensor-core operand layout, depth halo included), then the fp32 skip chunks (written into y).
+constexpr int kUpPH = 4, kUpPW = 8;
+__global__ void __launch_bounds__(256)
+up_expand_kernel(const float *__restrict__ t1_lo, const float *__restrict__ s_lo, uint4 *__restrict__ t1_hi, float *__restrict__ y,
+                 int B, int Cb, int Cout, int H, int W, int Z, int NCH) {
+    const int H2 = 2 * H, W2 = 2 * W, Z2 = 2 * Z;
+    const int nph = (H2 + kUpPH - 1) / kUpPH, npw = (W2 + kUpPW - 1) / kUpPW;
+    int t = blockIdx.x;
+    const int pwi = t % npw; t /= npw;
+    const int phi = t % nph;
+    const int b = t / nph;
+    const int job = blockIdx.y;
+    const bool is_t1 = job < NCH;
+    const float *src = is_t1 ? t1_lo : s_lo;
+    const int Cs = is_t1 ? Cb : Cout, c0 = (is_t1 ? job : job - NCH) * 8;
+    const int nc = min(8, Cs - c0);                     // real channels of this job (uniform over the CTA)
+    const size_t S = (size_t)H * W * Z;
+    for (int item = threadIdx.x; item < kUpPH * kUpPW * Z; item += blockDim.x) {
+        const int zl = item % Z, col = item / Z;
+        const int h2 = phi * kUpPH + col / kUpPW, w2 = pwi * kUpPW + col % kUpPW;
+        if (h2 >= H2 || w2 >= W2) continue;
+        int h0, h1, w0, w1;
+        float fh0, fh1, fw0, fw1;
+        if (h2 & 1) { h0 = h2 >> 1; h1 = min(h0 + 1, H - 1); fh0 = 0.75f; fh1 = 0.25f; } else { h1 = h2 >> 1; h0 = max(h1 - 1, 0); fh0 = 0.25f; fh1 = 0.75f; }
+        if (w2 & 1) { w0 = w2 >> 1; w1 = min(w0 + 1, W - 1); fw0 = 0.75f; fw1 = 0.25f; } else { w1 = w2 >> 1; w0 = max(w1 - 1, 0); fw0 = 0.25f; fw1 = 0.75f; }
+        const int zm = max(zl - 1, 0), zp = min(zl + 1, Z - 1);
+        // 32-bit element offsets inside one channel volume (H * W * Z < 2^31 is checked by the host): one IMAD.WIDE per load
+        const int o00 = (h0 * W + w0) * Z, o01 = (h0 * W + w1) * Z, o10 = (h1 * W + w0) * Z, o11 = (h1 * W + w1) * Z;
+        const int i00m = o00 + zm, i01m = o01 + zm, i10m = o10 + zm, i11m = o11 + zm;
+        const int i00c = o00 + zl, i01c = o01 + zl, i10c = o10 + zl, i11c = o11 + zl;
+        const int i00p = o00 + zp, i01p = o01 + zp, i10p = o10 + zp, i11p = o11 + zp;
+        const float f00 = fh0 * fw0, f01 = fh0 * fw1, f10 = fh1 * fw0, f11 = fh1 * fw1;
+        float e[8], o[8];                               // even / odd output depth
+        const float *pc = src + ((size_t)b * Cs + c0) * S;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            e[j] = 0.0f; o[j] = 0.0f;
+            if (j < nc) {
+                const float vm = f00 * __ldg(pc + i00m) + f01 * __ldg(pc + i01m) + f10 * __ldg(pc + i10m) + f11 * __ldg(pc + i11m);
+                const float vc = f00 * __ldg(pc + i00c) + f01 * __ldg(pc + i01c) + f10 * __ldg(pc + i10c) + f11 * __ldg(pc + i11c);
+                const float vp = f00 * __ldg(pc + i00p) + f01 * __ldg(pc + i01p) + f10 * __ldg(pc + i10p) + f11 * __ldg(pc + i11p);
+                e[j] = 0.25f * vm + 0.75f * vc;
+                o[j] = 0.75f * vc + 0.25f * vp;
+                pc += S;
+            }
+        }
+        if (is_t1) {
+            uint4 ue, uo;
+            ue.x = bf16x2(e[0], e[1]); ue.y = bf16x2(e[2], e[3]); ue.z = bf16x2(e[4], e[5]); ue.w = bf16x2(e[6], e[7]);
+            uo.x = bf16x2(o[0], o[1]); uo.y = bf16x2(o[2], o[3]); uo.z = bf16x2(o[4], o[5]); uo.w = bf16x2(o[6], o[7]);
+            uint4 *row = t1_hi + ((((size_t)b * NCH + job) * H2 + h2) * W2 + w2) * (size_t)(Z2 + 2);
+            row[1 + 2 * zl] = ue;
+            row[2 + 2 * zl] = uo;
+            if (zl == 0) row[Z2 + 1] = ue;              // circular depth halo (the padding is applied AFTER the upsampling)
+            if (zl == Z - 1) row[0] = uo;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nc)
+                    __stcs(reinterpret_cast<float2 *>(y + ((((size_t)b * Cout + c0 + j) * H2 + h2) * W2 + w2) * (size_t)Z2 + 2 * zl), make_float2(e[j], o[j]));
+        }
+    }
+}
+
+static vq3d_preact_desc up_hi_desc(const vq3d_preact_desc *d) {      // the one-block 'same' problem the tensor-core kernel sees
+    vq3d_preact_desc h = *d;
+    h.H = 2 * d->H; h.W = 2 * d->W; h.Z = 2 * d->Z;
+    h.Cin = d->Cout;
+    return h;
+}
+
+// [256 B: barrier counter, trace] [t1_hi] [weight images: 2 slots] [t1_lo fp32] [s_lo fp32]
+template <int C, int CB>
+static size_t up_ws_bytes(const vq3d_preact_desc *d) {
+    const vq3d_preact_desc h = up_hi_desc(d);
+    const size_t lo = (size_t)d->B * d->H * d->W * d->Z;
+    return 256 + t1_units<C, CB>(&h) * 16 + 2 * (size_t)TcsCfg<C, CB>::WIMG + 256 + lo * (size_t)(d->Cb + d->Cout) * 4;
+}
+
+template <int C, int CB, int NCW, int NBUF>
+static int launch_up_tc(const vq3d_preact_desc *d, void *ws, size_t ws_size, void *stream) {
+    using Cfg = TcsCfg<C, CB>;
+    constexpr int NT = (kTcsAuxWarps + NCW) * 32;
+    if (ws_size < up_ws_bytes<C, CB>(d)) return fail(VQ3D_ERR_INVALID, "preact_up_tc: workspace too small (%zu < %zu bytes)", ws_size, up_ws_bytes<C, CB>(d));
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(VQ3D_ERR_INVALID, "preact_up_tc: workspace must be 256-byte aligned");
+    const vq3d_preact_desc h = up_hi_desc(d);
+    TcsPlan pl;
+    if (!plan_tile<C, CB, NCW, NBUF>(&h, pl)) return fail(VQ3D_ERR_UNSUPPORTED, "preact_up_tc: no tile fits shared memory / TMEM");
+    auto kernel = preact_tc_kernel<C, CB, NCW, NBUF>;
+    size_t smem = pl.smem < 120 * 1024 ? 120 * 1024 : pl.smem;
+    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "preact_up_tc(attr)");
+    int grid = sm_count();
+    if (grid > pl.ntiles) grid = pl.ntiles;
+    if (getenv("VQ3D_TC_DEBUG"))
+        fprintf(stderr, "preact_up_tc<%d,%d>: lo %dx%dx%d Cin=%d tile %dx%dx%d NL=%d NMB=%d ntiles=%d grid=%d smem=%zu tmem=%u\n", C, CB, d->H, d->W, d->Z,
+                d->Cin, pl.th, pl.tw, h.Z, pl.NL, pl.NMB, pl.ntiles, grid, smem, pl.tmem_cols);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char *wsb = static_cast<unsigned char *>(ws);
+    const size_t t1u = t1_units<C, CB>(&h);
+    uint4 *t1_hi = reinterpret_cast<uint4 *>(wsb + 256);
+    unsigned char *wimg = reinterpret_cast<unsigned char *>(t1_hi + t1u);
+    const size_t lo = (size_t)d->B * d->H * d->W * d->Z;
+    float *t1_lo = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(wimg + 2 * (size_t)Cfg::WIMG) + 255) & ~(uintptr_t)255);
+    float *s_lo = t1_lo + lo * d->Cb;
+
+    // low-resolution pointwise stage
+    {
+        constexpr int T = 128;
+        const int Cb4 = (d->Cb + 3) & ~3, Co4 = (d->Cout + 3) & ~3;
+        const size_t sm = ((size_t)d->Cin * (Cb4 + Co4) + 2 * (size_t)d->Cin * T) * 4;
+        if (sm > 200 * 1024) return fail(VQ3D_ERR_UNSUPPORTED, "preact_up_tc: Cin = %d too wide for the low-resolution stage", d->Cin);
+        int64_t blocks = ceil_div((int64_t)lo, T);
+        if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+        int rc = launch("up_lo", up_lo_kernel<T>, dim3((unsigned)blocks), dim3(T), sm, stream, d->x, d->w1, d->wskip, d->b1a, d->b1b, d->b2a, d->b2b,
+                        d->b1c, d->b1d, t1_lo, s_lo, (int64_t)lo, (int64_t)d->H * d->W * d->Z, (int)d->Cin, (int)d->Cb, (int)d->Cout);
+        if (rc != VQ3D_OK) return rc;
+    }
+    // expansion: bf16 t1 in the tensor-core layout + the interpolated skip path into y
+    {
+        const unsigned jobs = (unsigned)(Cfg::NCH + (d->Cout + 7) / 8);
+        const unsigned patches = (unsigned)(d->B * ceil_div(h.H, kUpPH) * ceil_div(h.W, kUpPW));
+        int rc = launch("up_expand", up_expand_kernel, dim3(patches, jobs), dim3(256), 0, stream, (const float *)t1_lo, (const float *)s_lo,
+                        t1_hi, d->y, (int)d->B, (int)d->Cb, (int)d->Cout, (int)d->H, (int)d->W, (int)d->Z, (int)Cfg::NCH);
+        if (rc != VQ3D_OK) return rc;
+    }
+    TcsParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = h.B; p.H = h.H; p.W = h.W; p.Z = h.Z;
+    p.th = pl.th; p.tw = pl.tw;
+    p.nth = (int)ceil_div(h.H, pl.th); p.ntw = (int)ceil_div(h.W, pl.tw);
+    p.IH = pl.IH; p.IW = pl.IW; p.IZ = pl.IZ; p.NL = pl.NL; p.L0 = pl.L0; p.NMB = pl.NMB; p.NLA = pl.NLA;
+    p.ntiles = pl.ntiles; p.tmem_cols = pl.tmem_cols;
+    p.nblocks = 1;
+    p.t1_ready = 1;
+    p.sync = reinterpret_cast<unsigned int *>(wsb);
+    p.trace = nullptr;
+    p.t1[0] = t1_hi; p.t1[1] = t1_hi;
+    p.wimg = wimg;
+    p.x = d->y; p.y = d->y;
+    TcsBlock &t = p.blk[0];
+    t.w1 = nullptr; t.w2 = d->w2; t.w3 = d->w3;
+    t.b3a = d->b3a; t.b3b = d->b3b; t.b4 = d->b4; t.scale = d->scale;
+    e = cudaMemsetAsync(p.sync, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return check_cuda(e, "preact_up_tc(memset)");
+    const int items = Cfg::CPCH * Cfg::CBP + 27 * Cfg::NCH * Cfg::CBP + Cfg::NCH * Cfg::CP;
+    tcs_prep_kernel<C, CB><<<dim3((unsigned)ceil_div(items, 256), 2u), 256, 0, st>>>(p, wimg);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return check_cuda(e, "preact_up_tc(prep)");
+    void *args[] = {&p};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kernel), dim3((unsigned)grid), dim3(NT), args, smem, st);
+    if (e != cudaSuccess) return check_cuda(e, "preact_up_tc(cooperative launch)");
+    return VQ3D_OK;
+}
+
+struct UpEntry {
+    int cout, cb;
+    int (*fn)(const vq3d_preact_desc *, void *, size_t, void *);
+    size_t (*ws)(const vq3d_preact_desc *);
+};
+#define VQ3D_UP(C, CB, NCW, NBUF) {C, CB, launch_up_tc<C, CB, NCW, NBUF>, up_ws_bytes<C, CB>}
+// (Cout, Cb) of the Full / downscaled models' wide 'up' blocks: 18->9->8, 32->16->16, 16->8->8, 72->36->32
+static const UpEntry kUp[] = {VQ3D_UP(8, 9, 20, 2), VQ3D_UP(16, 16, 20, 2), VQ3D_UP(8, 8, 20, 2), VQ3D_UP(32, 36, 8, 1)};
+
+static const UpEntry *find_up(const vq3d_preact_desc *d) {
+    if (d->mode != 2 || !d->wskip) return nullptr;
+    for (const UpEntry &e : kUp)
+        if (e.cout == d->Cout && e.cb == d->Cb) return &e;
+    return nullptr;
+}
+
 }  // namespace vq3d
 #endif  // !VQ3D_EMU
 
@@ -738,5 +980,35 @@ extern "C" int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void 
     if (!e) return fail(VQ3D_ERR_UNSUPPORTED, "preact_stack_tc: no tensor-core instantiation for C=%d Cb=%d", d->Cin, d->Cb);
     if (!ws) return fail(VQ3D_ERR_INVALID, "preact_stack_tc: null workspace (see vq3d_preact_stack_tc_workspace)");
     return e->fn(blocks, n, ws, ws_size, stream);
+#endif
+}
+
+extern "C" size_t vq3d_preact_up_tc_workspace(const vq3d_preact_desc *d) {
+#ifdef VQ3D_EMU
+    (void)d;
+    return 0;
+#else
+    if (!d || d->B < 1 || d->H < 1 || d->W < 1 || d->Z < 1 || d->Cin < 1) return 0;
+    const UpEntry *e = find_up(d);
+    return e ? e->ws(d) : 0;
+#endif
+}
+
+extern "C" int vq3d_preact_up_tc(const vq3d_preact_desc *d, void *ws, size_t ws_size, void *stream) {
+#ifdef VQ3D_EMU
+    (void)d; (void)ws; (void)ws_size; (void)stream;
+    return fail(VQ3D_ERR_UNSUPPORTED, "preact_up_tc: tensor-core kernels cannot run in the host emulator");
+#else
+    if (!d) return fail(VQ3D_ERR_INVALID, "preact_up_tc: null descriptor");
+    if (d->mode != 2) return fail(VQ3D_ERR_INVALID, "preact_up_tc: mode must be 2 (up)");
+    if (!d->x || !d->y || !d->w1 || !d->w2 || !d->w3 || !d->wskip) return fail(VQ3D_ERR_INVALID, "preact_up_tc: null tensor");
+    if (d->B < 1 || d->H < 1 || d->W < 1 || d->Z < 1 || d->Cin < 1) return fail(VQ3D_ERR_INVALID, "preact_up_tc: bad sizes");
+    if (d->out_w || d->pre_w) return fail(VQ3D_ERR_UNSUPPORTED, "preact_up_tc: fused leading / trailing 1x1 convolutions are not supported here");
+    if ((int64_t)d->B * d->Cout * d->H * d->W * d->Z * 8 > ((int64_t)1 << 40) || (int64_t)d->H * d->W * d->Z >= ((int64_t)1 << 31))
+        return fail(VQ3D_ERR_INVALID, "preact_up_tc: tensor too large");
+    const UpEntry *e = find_up(d);
+    if (!e) return fail(VQ3D_ERR_UNSUPPORTED, "preact_up_tc: no tensor-core instantiation for Cout=%d Cb=%d", d->Cout, d->Cb);
+    if (!ws) return fail(VQ3D_ERR_INVALID, "preact_up_tc: null workspace (see vq3d_preact_up_tc_workspace)");
+    return e->fn(d, ws, ws_size, stream);
 #endif
 }

@@ -31,6 +31,7 @@ class Ops:
         # merged-tap tensor-core kernel for the thin 512^3 / 256^3 blocks: correct, but measured SLOWER than the SIMT row kernel
         # (0.72 vs 0.52 ms per 4->2->4 block and volume: the im2col copy saturates the shared-memory pipe), so off by default
         self.thin_tc = os.environ.get("VQ3D_THIN_TC", "0") == "1"
+        self.up_tc = os.environ.get("VQ3D_UP_TC", "1") == "1"      # wide 'up' blocks on the tensor-core kernel (bf16 mode)
         self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
@@ -327,11 +328,22 @@ class Ops:
         si, so = H * W * Z, sp[0] * sp[1] * sp[2]
         Cb = blk.branch_conv1.weight.shape[0]
         k3 = blk.branch_conv2.weight.shape[2] ** 3
-        ok = self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()), allow_unsupported=True,
-                        nbytes=4 * B * ((1 if pre is not None else Cin) * si + Cout * so),
-                        flops=2 * B * (Cin * Cb * si + Cb * Cb * k3 * so + Cb * Cout * so + (Cin * Cout * so * (8 if mode == 1 else 1) if blk.skip_conv is not None else 0)),
-                        tag=f"{'in+' if pre is not None else ''}{('same', 'down', 'up')[mode]} {Cin}->{Cb}->{Cout} @{H}x{W}x{Z}")
+        meta = dict(nbytes=4 * B * ((1 if pre is not None else Cin) * si + Cout * so),
+                    flops=2 * B * (Cin * Cb * si + Cb * Cb * k3 * so + Cb * Cout * so + (Cin * Cout * so * (8 if mode == 1 else 1) if blk.skip_conv is not None else 0)),
+                    tag=f"{'in+' if pre is not None else ''}{('same', 'down', 'up')[mode]} {Cin}->{Cb}->{Cout} @{H}x{W}x{Z}")
+        # wide 'up' blocks: low-resolution pointwise stage + trilinear expansion (fp32 SIMT) feeding the tcgen05 stack kernel
+        if mode == 2 and self.precision == "bf16" and self.up_tc and pre is None and blk.skip_conv is not None and (Cout, Cb) in self.TC_UP_SHAPES:
+            need = self.lib.vq3d_preact_up_tc_workspace(C.byref(d))
+            if need:
+                ws = self._workspace(need, x.device)
+                if self._call("preact_up_tc", self.lib.vq3d_preact_up_tc, (C.byref(d), self._p(ws), ws.numel(), self.stream()),
+                              allow_unsupported=True, kernels=4, **meta):
+                    return y
+        ok = self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()), allow_unsupported=True, **meta)
         return y if ok else None
+
+    # (Cout, Cb) pairs whose 'up' blocks run on the tensor-core kernel in bf16 mode (vq3d_preact_up_tc)
+    TC_UP_SHAPES = {(8, 9), (16, 16), (8, 8), (32, 36)}
 
     # (C, Cb) pairs whose 'same' blocks run on the tensor-core stack kernel in bf16 mode
     TC_STACK_SHAPES = {(8, 4), (16, 8), (18, 9), (32, 16), (64, 32), (72, 36)}

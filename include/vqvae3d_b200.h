@@ -271,6 +271,19 @@ size_t vq3d_preact_stack_tc_workspace(const vq3d_preact_desc *first_block);
 int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_bytes, void *stream);
 
 /*
+ * One 'up' PreActFixupResBlock (mode 2: trilinear x2 + k3 circular convolution, skip = ResizeConv3D k1; layers.py:124-132,
+ * 176-195,591-597) with the k3 convolution on the tensor cores.  Same descriptor as vq3d_preact_block (mode must be 2).
+ * The pointwise low-resolution stage (conv1 and the 1x1 skip convolution, which commutes with the interpolation) and the
+ * trilinear expansion run as two small fp32 kernels; the expansion writes the bf16 branch activation straight into the
+ * tensor-core operand layout and the interpolated skip path into y, and the k3 convolution + conv3 + residual run on the
+ * persistent tcgen05 kernel of vq3d_preact_stack_tc.  ws: 256-byte aligned device buffer of vq3d_preact_up_tc_workspace(desc)
+ * bytes (0 = no instantiation for (Cout, Cb): callers fall back to vq3d_preact_block).  Results agree with the fp32 kernels to
+ * bf16 operand rounding of the branch; the skip path stays fp32.
+ */
+size_t vq3d_preact_up_tc_workspace(const vq3d_preact_desc *desc);
+int vq3d_preact_up_tc(const vq3d_preact_desc *desc, void *ws, size_t ws_bytes, void *stream);
+
+/*
  * The thin 'same' blocks (4 -> 2 -> 4, 8 -> 4 -> 8; full-depth tiles: Z in {32, 64, 128}, H and W multiples of 8) with
  * conv2 as ONE merged-tap GEMM per 128 voxels on the tensor cores (K = 27 * C_b; bf16 operands, fp32 accumulation).
  * Same arguments and ping-pong convention as vq3d_preact_stack (tmp may be NULL for n == 1); a last block that carries

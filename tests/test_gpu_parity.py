@@ -512,6 +512,65 @@ def test_tensor_core_stack_matches_fp32(C, n, shape):
     assert float((got - ref).abs().mean()) <= 5e-3 * float(branch.abs().mean() + 1e-6)
 
 
+@pytest.mark.parametrize("cin,cout,shape", [
+    (18, 8, (1, 16, 16, 8)),       # the Full decoder's 18 -> 9 -> 8 block (K 9 -> 16 padded), several tiles
+    (18, 8, (2, 24, 20, 16)),      # batch 2, non-square, partial tiles
+    (32, 16, (1, 8, 8, 2)),        # 32 -> 16 -> 16 at the top level's size: wrap on a size-4 axis after the upsampling
+    (32, 16, (1, 16, 12, 8)),
+    (16, 8, (1, 6, 5, 3)),         # odd low-resolution extents
+    (72, 32, (1, 8, 8, 4)),        # 72 -> 36 -> 32: C_b padded 36 -> 48, staging wider than the output channels
+    (18, 8, (1, 64, 64, 32)),      # a quarter of the Full model's tensor
+])
+def test_tensor_core_up_block_matches_fp32(cin, cout, shape):
+    """vq3d_preact_up_tc (low-resolution stage + trilinear expansion + tcgen05 k3 convolution) against the fp32 kernels:
+    the branch within bf16 operand rounding, the interpolated skip path to fp32 rounding."""
+    from vqvae import _ops
+    o = _ops.default()
+    torch.manual_seed(cin + cout)
+    blk = L.PreActFixupResBlock(cin, cout, "up")
+    with torch.no_grad():
+        blk.initialize_weights(num_layers=4)
+        for p in blk.parameters():
+            p.add_(torch.randn(p.shape) * 0.1)
+    blk = blk.to(DEV).eval()
+    B, H, W, Z = shape
+    x = torch.randn(B, cin, H, W, Z, generator=torch.Generator().manual_seed(1)).to(DEV)
+    prev = o.precision
+    try:
+        with torch.no_grad():
+            o.precision = "fp32"
+            ref = blk(x)
+            skip = o.conv3d(o.upsample2x(x, pre_b=blk.bias1c), blk.skip_conv.weight, post_b=blk.bias1d)
+            o.precision = "bf16"
+            o.profile = []
+            got = blk(x)
+            torch.cuda.synchronize()
+            assert [e[0] for e in o.profile] == ["preact_up_tc"], [e[0] for e in o.profile]
+            assert torch.equal(got, blk(x))             # deterministic
+    finally:
+        o.precision = prev
+        o.profile = None
+    branch = ref - skip
+    err, scale = float((got - ref).abs().max()), float(branch.abs().max())
+    assert err <= 2e-2 * scale, (err, scale)
+    assert float((got - ref).abs().mean()) <= 5e-3 * float(branch.abs().mean() + 1e-6)
+
+
+@pytest.mark.bf16
+@pytest.mark.parametrize("name", by_kind("block", lambda c: c.get("mode") == "up" and c.get("cls") == "PreActFixupResBlock"))
+def test_up_block_golden_bf16_tensor_core_mode(name):
+    """The reference's own outputs for the 'up' blocks (tests/golden) in the product's default bf16 mode."""
+    c, g = CASES[name], load(name)
+    with torch.no_grad():
+        m = getattr(L, c["cls"])(c["cin"], c["cout"], c["mode"]).eval()
+        m.load_state_dict(golden_state_dict(c["spec"], c["seed"]))
+        m.to(DEV)
+        x = portable_randn(c["shape"], c["seed"] + 7).to(DEV)
+        y = m(x).cpu().numpy()
+    err = np.abs(y - g["y"]).max()
+    assert err <= 1e-2 * np.abs(g["y"]).max(), (name, err, np.abs(g["y"]).max())
+
+
 @pytest.mark.bf16
 def test_tensor_core_stack_shift_equivariance():
     """Circular padding => the block commutes with circular shifts; with tile-aligned shifts the

@@ -41,7 +41,9 @@ def rep(path, out):
                     i = hdr.index(k)
                     f.write(f"{k:95s} {r[i]:>18s} {units[i]}\n")
             for i, h in enumerate(hdr):
-                if "tensor" in h and h not in KEYS and r[i] not in ("", "0", "0.000000"):
+                if ("pipe_tensor" in h or "l1tex__t_sector_hit_rate" in h or "lts__t_bytes.sum" == h or "l1tex__t_bytes.sum" == h
+                        or h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")) and h not in KEYS \
+                        and r[i] not in ("", "0", "0.000000"):
                     f.write(f"{h:95s} {r[i]:>18s} {units[i]}\n")
     print(open(out).read())
 
