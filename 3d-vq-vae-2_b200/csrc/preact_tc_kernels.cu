@@ -118,7 +118,16 @@ struct TcsCfg {
     static constexpr int NCH = CBP / 8, CPCH = CP / 8; // 8-channel (16 B) chunks per voxel
     static constexpr int CB4 = rup(CB, 4);
     static constexpr uint32_t W2TAP = (uint32_t)CBP * CBP * 2;   // bytes of one tap's B operand
-    static constexpr uint32_t W2BYTES = 27u * W2TAP;
+    // C_b = 9 (the 18-channel stack, the 18 -> 9 -> 8 'up' block): the ninth channel would double the reduction length of
+    // every tap (K 9 -> 16).  Instead its three depth neighbours ride in the spare slots of the second 16-byte chunk
+    // ([c8(z), c8(z-1), c8(z+1), 0 x 5]) and two taps share one K16 MMA through the descriptor's K-chunk stride (LBO):
+    //   MMA a of (kh, kw):  channels 0..7 at depth tap -1  |  channels 0..7 at depth tap 0     (LBO = one row = 16 B)
+    //   MMA b of (kh, kw):  channels 0..7 at depth tap +1  |  channel 8 at all three depth taps (LBO = chunk stride - 16 B)
+    // 18 MMAs instead of 27 for the same products (an M128 x N16 x K16 MMA costs ~43 clk whatever it multiplies: its A operand
+    // is fetched from shared memory at 128 B/clk, profiles/r02_tc_microbench.txt).
+    static constexpr bool K9 = CB == 9;
+    static constexpr int NMMA2 = K9 ? 18 : 27 * (CBP / 16);      // conv2 MMAs per M-block
+    static constexpr uint32_t W2BYTES = K9 ? 18u * 512u : 27u * W2TAP;
     static constexpr uint32_t WPBYTES = (uint32_t)CP * CBP * 2;  // bytes of a pointwise (conv1 or conv3) B operand
     static constexpr uint32_t WIMG = W2BYTES + 2 * WPBYTES;      // per block image [W1 | W2 | W3]
     static constexpr uint32_t LBO_B2 = (uint32_t)CBP * 16;       // conv2 and conv1 images: CBP rows per k-chunk
@@ -138,6 +147,18 @@ __device__ __forceinline__ void elu_pack16(const float *v, float a, float b, int
     hi.x = bf16x2(t[8], t[9]); hi.y = bf16x2(t[10], t[11]); hi.z = bf16x2(t[12], t[13]); hi.w = bf16x2(t[14], t[15]);
 }
 
+// C_b = 9: channel 8 of voxel z goes into slot 0 of its own second chunk, slot 1 of voxel z+1's and slot 2 of voxel z-1's
+// (circular in depth; three disjoint 2-byte stores, slots 3..7 stay zero from the launch's memset).  row1 = the (b, h, w) row of
+// chunk 1 ([Z+2] 16-byte units, unit u = depth u - 1).
+__device__ __forceinline__ void store_c8(uint4 *row1, int oz, int Z, float v8) {
+    const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(v8));
+    unsigned short *r = reinterpret_cast<unsigned short *>(row1);
+    const int zn = oz + 1 == Z ? 0 : oz + 1, zp = oz == 0 ? Z - 1 : oz - 1;
+    r[(oz + 1) * 8 + 0] = h;
+    r[(zn + 1) * 8 + 1] = h;
+    r[(zp + 1) * 8 + 2] = h;
+}
+
 // weights -> bf16 B-operand images (K-major, no swizzle: [k-chunk of 8][row n][16 B]), once per call
 template <int C, int CB>
 __global__ void __launch_bounds__(256)
@@ -148,7 +169,7 @@ tcs_prep_kernel(const __grid_constant__ TcsParams p, unsigned char *wimg) {
     unsigned char *img = wimg + (size_t)blk * Cfg::WIMG;
     const bool real = blk < p.nblocks;
     const TcsBlock &bp = p.blk[real ? blk : 0];
-    const int n1 = CPCH * CBP, n2 = 27 * NCH * CBP, n3 = NCH * CP;
+    const int n1 = CPCH * CBP, n2 = (Cfg::K9 ? 18 * 2 : 27 * NCH) * CBP, n3 = NCH * CP;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + (real ? n2 + n3 : 0); i += gridDim.x * blockDim.x) {
         float wv[8];
         unsigned char *dst;
@@ -162,6 +183,25 @@ tcs_prep_kernel(const __grid_constant__ TcsParams p, unsigned char *wimg) {
             dst = img + (size_t)kc * Cfg::LBO_B2 + (size_t)n * 16;
         } else if (i < n1 + n2) {                       // W2: per tap, rows n = co, K = ci
             const int j = i - n1;
+            if (Cfg::K9) {                              // per MMA m = 2 * (kh * 3 + kw) + {a, b}: [k-chunk 2][n 16][16 B]
+                const int n = j % CBP, kc = (j / CBP) % 2, m = j / (CBP * 2);
+                const int hw = m >> 1;
+                const float *wr = bp.w2 + (size_t)n * CB * 27;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) wv[e] = 0.0f;
+                if (n < CB) {
+                    if ((m & 1) == 0 || kc == 0) {      // channels 0..7 of depth tap -1 / 0 (MMA a) or +1 (MMA b, first chunk)
+                        const int kz = (m & 1) ? 2 : kc;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) wv[e] = __ldg(wr + e * 27 + hw * 3 + kz);
+                    } else {                            // channel 8: slots = depth taps 0, -1, +1
+                        wv[0] = __ldg(wr + 8 * 27 + hw * 3 + 1);
+                        wv[1] = __ldg(wr + 8 * 27 + hw * 3 + 0);
+                        wv[2] = __ldg(wr + 8 * 27 + hw * 3 + 2);
+                    }
+                }
+                dst = img + Cfg::WPBYTES + (size_t)m * 512 + (size_t)kc * 256 + (size_t)n * 16;
+            } else {
             const int n = j % CBP, kc = (j / CBP) % NCH, t = j / (CBP * NCH);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -169,6 +209,7 @@ tcs_prep_kernel(const __grid_constant__ TcsParams p, unsigned char *wimg) {
                 wv[e] = (n < CB && ci < CB) ? __ldg(bp.w2 + ((size_t)n * CB + ci) * 27 + t) : 0.0f;
             }
             dst = img + Cfg::WPBYTES + (size_t)t * Cfg::W2TAP + (size_t)kc * Cfg::LBO_B2 + (size_t)n * 16;
+            }
         } else {                                        // W3: rows n = c, K = cb
             const int j = i - n1 - n2;
             const int n = j % CP, kc = j / CP;
@@ -277,9 +318,16 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                 elu_pack16(acc + 16 * ks, b2a, b2b, CB - 16 * ks, lo, hi);
                 uint4 *r0 = p.t1[0] + ((((size_t)b * NCH + 2 * ks) * H + oh) * W + ow) * (size_t)(Z + 2);
                 uint4 *r1 = r0 + (size_t)H * W * (Z + 2);
-                r0[oz + 1] = lo; r1[oz + 1] = hi;
-                if (oz == 0) { r0[Z + 1] = lo; r1[Z + 1] = hi; }
-                if (oz == Z - 1) { r0[0] = lo; r1[0] = hi; }
+                r0[oz + 1] = lo;
+                if (oz == 0) r0[Z + 1] = lo;
+                if (oz == Z - 1) r0[0] = lo;
+                if (Cfg::K9) {
+                    store_c8(r1, oz, Z, elu_bl(acc[8] + b2a) + b2b);
+                } else {
+                    r1[oz + 1] = hi;
+                    if (oz == 0) r1[Z + 1] = hi;
+                    if (oz == Z - 1) r1[0] = hi;
+                }
             }
         }
         grid_barrier(p.sync, gridDim.x);
@@ -331,6 +379,19 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                     if (elect_one()) {
                         const uint32_t row0 = (uint32_t)(p.L0 + mb * 128);
                         const uint32_t d_addr = tmem_d + (uint32_t)((s * p.NMB + mb) * CBP);
+                        if constexpr (Cfg::K9) {
+#pragma unroll
+                            for (int hw = 0; hw < 9; ++hw) {
+                                const int kh = hw / 3, kw = hw % 3;
+                                const uint32_t arow = row0 + (uint32_t)((kh - 1) * IWZ + (kw - 1) * IZ);       // depth tap 0
+                                // a: channels 0..7 at depth taps -1 | 0 (the second K chunk starts one row further)
+                                umma_f16(d_addr, umma_desc(a_base + (arow - 1u) * 16u, 16, 128),
+                                         umma_desc(sW2_addr + (uint32_t)(2 * hw) * 512u, 256, 128), idesc_b, hw > 0 ? 1u : 0u);
+                                // b: channels 0..7 at depth tap +1 | channel 8's three depth taps (chunk 1 of the row itself)
+                                umma_f16(d_addr, umma_desc(a_base + (arow + 1u) * 16u, lbo_a - 16u, 128),
+                                         umma_desc(sW2_addr + (uint32_t)(2 * hw + 1) * 512u, 256, 128), idesc_b, 1u);
+                            }
+                        } else {
 #pragma unroll
                         for (int tp = 0; tp < 27; ++tp) {
                             const int kh = tp / 9, kw = (tp / 3) % 3, kz = tp % 3;
@@ -341,6 +402,7 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                                 const uint64_t bdesc = umma_desc(sW2_addr + (uint32_t)tp * Cfg::W2TAP + (uint32_t)(2 * ks) * Cfg::LBO_B2, Cfg::LBO_B2, 128);
                                 umma_f16(d_addr, adesc, bdesc, idesc_b, (tp > 0 || ks > 0) ? 1u : 0u);
                             }
+                        }
                         }
                         umma_commit_to(&bar_mb[s][mb]);                      // this M-block's accumulator is complete
                         if (mb + 1 == p.NMB) umma_commit_to(&bar_sa_empty[s]);  // ... and the A buffer has been read
@@ -505,9 +567,16 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                             if (valid) {
                                 uint4 *r0 = t1dst + ((((size_t)b * NCH + 2 * ks) * H + oh) * W + ow) * (size_t)(Z + 2);
                                 uint4 *r1 = r0 + (size_t)H * W * (Z + 2);
-                                r0[oz + 1] = lo; r1[oz + 1] = hi;
-                                if (oz == 0) { r0[Z + 1] = lo; r1[Z + 1] = hi; }
-                                if (oz == Z - 1) { r0[0] = lo; r1[0] = hi; }
+                                r0[oz + 1] = lo;
+                                if (oz == 0) r0[Z + 1] = lo;
+                                if (oz == Z - 1) r0[0] = lo;
+                                if (Cfg::K9) {
+                                    store_c8(r1, oz, Z, elu_bl(v[8] + n2a) + n2b);
+                                } else {
+                                    r1[oz + 1] = hi;
+                                    if (oz == 0) r1[Z + 1] = hi;
+                                    if (oz == Z - 1) r1[0] = hi;
+                                }
                             }
                         }
                         if (tr0) tc_trace(p.trace, blk, 13);
@@ -613,6 +682,14 @@ static size_t ws_bytes(const vq3d_preact_desc *d) {
     return 256 + 2 * t1_units<C, CB>(d) * 16 + (size_t)(kTcsMaxBlocks + 1) * TcsCfg<C, CB>::WIMG;
 }
 
+// C_b = 9: slots 3..7 of every second-chunk unit must read as zero (they meet zero weights, but 0 x NaN would poison the sum)
+template <int C, int CB>
+static cudaError_t zero_c8_planes(uint4 *t1, const vq3d_preact_desc *d, cudaStream_t st) {
+    if (!TcsCfg<C, CB>::K9) return cudaSuccess;
+    const size_t plane = (size_t)d->H * d->W * (size_t)(d->Z + 2) * 16;
+    return cudaMemset2DAsync(reinterpret_cast<unsigned char *>(t1) + plane, 2 * plane, 0, plane, (size_t)d->B, st);
+}
+
 template <int C, int CB, int NCW, int NBUF>
 static int launch_tcs(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_size, void *stream) {
     using Cfg = TcsCfg<C, CB>;
@@ -653,6 +730,9 @@ static int launch_tcs(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws
     p.wimg = wimg;
     p.y = blocks[n - 1].y;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e = zero_c8_planes<C, CB>(p.t1[0], d, st);
+    if (e == cudaSuccess) e = zero_c8_planes<C, CB>(p.t1[1], d, st);
+    if (e != cudaSuccess) return check_cuda(e, "preact_stack_tc(memset chunk 1)");
     for (int i0 = 0; i0 < n; i0 += kTcsMaxBlocks) {
         const int nb = n - i0 < kTcsMaxBlocks ? n - i0 : kTcsMaxBlocks;
         p.nblocks = nb;
@@ -777,7 +857,7 @@ up_lo_kernel(const float *__restrict__ x, const float *__restrict__ w1, const fl
 constexpr int kUpPH = 4, kUpPW = 8;
 __global__ void __launch_bounds__(256)
 up_expand_kernel(const float *__restrict__ t1_lo, const float *__restrict__ s_lo, uint4 *__restrict__ t1_hi, float *__restrict__ y,
-                 int B, int Cb, int Cout, int H, int W, int Z, int NCH) {
+                 int B, int Cb, int Cout, int H, int W, int Z, int NCH, int k9) {
     const int H2 = 2 * H, W2 = 2 * W, Z2 = 2 * Z;
     const int nph = (H2 + kUpPH - 1) / kUpPH, npw = (W2 + kUpPW - 1) / kUpPW;
     int t = blockIdx.x;
@@ -819,7 +899,11 @@ up_expand_kernel(const float *__restrict__ t1_lo, const float *__restrict__ s_lo
                 pc += S;
             }
         }
-        if (is_t1) {
+        if (is_t1 && k9 && job == 1) {                 // C_b = 9: the ninth channel and its depth neighbours (TcsCfg::K9)
+            uint4 *row = t1_hi + ((((size_t)b * NCH + 1) * H2 + h2) * W2 + w2) * (size_t)(Z2 + 2);
+            store_c8(row, 2 * zl, Z2, e[0]);
+            store_c8(row, 2 * zl + 1, Z2, o[0]);
+        } else if (is_t1) {
             uint4 ue, uo;
             ue.x = bf16x2(e[0], e[1]); ue.y = bf16x2(e[2], e[3]); ue.z = bf16x2(e[4], e[5]); ue.w = bf16x2(e[6], e[7]);
             uo.x = bf16x2(o[0], o[1]); uo.y = bf16x2(o[2], o[3]); uo.z = bf16x2(o[4], o[5]); uo.w = bf16x2(o[6], o[7]);
@@ -879,6 +963,8 @@ static int launch_up_tc(const vq3d_preact_desc *d, void *ws, size_t ws_size, voi
     float *t1_lo = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(wimg + 2 * (size_t)Cfg::WIMG) + 255) & ~(uintptr_t)255);
     float *s_lo = t1_lo + lo * d->Cb;
 
+    e = zero_c8_planes<C, CB>(t1_hi, &h, st);
+    if (e != cudaSuccess) return check_cuda(e, "preact_up_tc(memset chunk 1)");
     // low-resolution pointwise stage
     {
         constexpr int T = 128;
@@ -896,7 +982,7 @@ static int launch_up_tc(const vq3d_preact_desc *d, void *ws, size_t ws_size, voi
         const unsigned jobs = (unsigned)(Cfg::NCH + (d->Cout + 7) / 8);
         const unsigned patches = (unsigned)(d->B * ceil_div(h.H, kUpPH) * ceil_div(h.W, kUpPW));
         int rc = launch("up_expand", up_expand_kernel, dim3(patches, jobs), dim3(256), 0, stream, (const float *)t1_lo, (const float *)s_lo,
-                        t1_hi, d->y, (int)d->B, (int)d->Cb, (int)d->Cout, (int)d->H, (int)d->W, (int)d->Z, (int)Cfg::NCH);
+                        t1_hi, d->y, (int)d->B, (int)d->Cb, (int)d->Cout, (int)d->H, (int)d->W, (int)d->Z, (int)Cfg::NCH, (int)Cfg::K9);
         if (rc != VQ3D_OK) return rc;
     }
     TcsParams p;

@@ -9,7 +9,8 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout
+# HOT_OUTER=1: attribute inlined code (mbarrier waits, ELU helpers ...) to the line of the kernel body that called it
+dis = subprocess.run(["nvdisasm", "-gi" if os.environ.get("HOT_OUTER") else "-g", cubin], capture_output=True, text=True).stdout
 dis = dis[dis.index(".text." + fun + ":"):]
 nxt = dis.find("\n.text.", 10)
 nxt2 = dis.find("\n\t.section", 10)
