@@ -354,6 +354,67 @@ huber_elu_mask_kernel(const float *__restrict__ dec, const float *__restrict__ x
     }
 }
 
+// The same pass with every statistic the reference logs next to the loss (model.py:143-149: sub_metric_log_dict of the
+// unreduced loss and of the reconstruction, nmse and psnr of metrics/evaluate.py:18-24), as partial sums:
+//   sums[0..7] = sum loss, count, sum (loc - x)^2, sum x^2, sum loc, sum loc^2, sum loss^2, unused
+//   minmax[0..3] = min loc, max loc, min loss, max loss   (caller initialises to +inf, -inf, +inf, -inf)
+__device__ __forceinline__ void atomic_min_f32(float *addr, float v) {      // works for any sign: ordered-int trick
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float *addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256)
+huber_elu_mask_stats_kernel(const float *__restrict__ dec, const float *__restrict__ x, const int *__restrict__ num_valid,
+                            const uint8_t *__restrict__ mask_hw, int64_t B, int HW, int Z, double *sums, float *minmax) {
+    __shared__ double red[7][8];
+    __shared__ float redm[4][8];
+    const int64_t total = B * (int64_t)HW * Z;
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    float lo_loc = __int_as_float(0x7f800000), hi_loc = -lo_loc, lo_l = lo_loc, hi_l = -lo_loc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i % Z);
+        const int64_t r = i / Z;
+        const int hw = (int)(r % HW);
+        const int b = (int)(r / HW);
+        if (mask_hw && !mask_hw[hw]) continue;
+        float loc = elu1(dec[i]);
+        if (num_valid && z >= num_valid[b]) loc = 0.0f;
+        const float xv = x[i];
+        const float df = loc - xv, d = fabsf(df);
+        const float l = d < 1.0f ? 0.5f * d * d : d - 0.5f;
+        a[0] += (double)l; a[1] += 1.0; a[2] += (double)df * df; a[3] += (double)xv * xv; a[4] += (double)loc; a[5] += (double)loc * loc;
+        a[6] += (double)l * l;
+        lo_loc = fminf(lo_loc, loc); hi_loc = fmaxf(hi_loc, loc); lo_l = fminf(lo_l, l); hi_l = fmaxf(hi_l, l);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+        lo_loc = fminf(lo_loc, __shfl_xor_sync(0xffffffffu, lo_loc, o)); hi_loc = fmaxf(hi_loc, __shfl_xor_sync(0xffffffffu, hi_loc, o));
+        lo_l = fminf(lo_l, __shfl_xor_sync(0xffffffffu, lo_l, o)); hi_l = fmaxf(hi_l, __shfl_xor_sync(0xffffffffu, hi_l, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) red[k][warp] = a[k];
+        redm[0][warp] = lo_loc; redm[1][warp] = hi_loc; redm[2][warp] = lo_l; redm[3][warp] = hi_l;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+        atomicAdd(sums + threadIdx.x, t);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
+        const int k = threadIdx.x - 32;
+        float t = redm[k][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = (k & 1) ? fmaxf(t, redm[k][w]) : fminf(t, redm[k][w]);
+        if (t == t && fabsf(t) != __int_as_float(0x7f800000)) { if (k & 1) atomic_max_f32(minmax + k, t); else atomic_min_f32(minmax + k, t); }
+    }
+}
+
 }  // namespace vq3d
 
 using namespace vq3d;
@@ -507,4 +568,14 @@ extern "C" int vq3d_huber_elu_mask(const float *decoded, const float *x, const i
     if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
     return launch("huber_elu_mask", huber_elu_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x,
                   (const int *)num_valid, mask_hw, B, H * W, Z, sum, count);
+}
+
+extern "C" int vq3d_huber_elu_mask_stats(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                                         int64_t B, int H, int W, int Z, double *sums, float *minmax, void *stream) {
+    if (!decoded || !x || !sums || !minmax || B < 1 || H < 1 || W < 1 || Z < 1) return fail(VQ3D_ERR_INVALID, "huber stats: bad arguments");
+    const int64_t total = B * (int64_t)H * W * Z;
+    int64_t blocks = ceil_div(total, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    return launch("huber_elu_mask_stats", huber_elu_mask_stats_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x,
+                  (const int *)num_valid, mask_hw, B, H * W, Z, sums, minmax);
 }

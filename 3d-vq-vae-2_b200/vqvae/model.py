@@ -167,6 +167,24 @@ class VQVAE(_Base):
     def validation_step(self, batch, batch_idx):
         return self.huber(batch, batch_idx)[0]
 
+    @torch.no_grad()
+    def validation_metrics(self, batch) -> dict:
+        """The reference's validation log (model.py:143-160) from ONE fused pass over the reconstruction: recon_loss / loc
+        min, max, mean, std, nmse, psnr (data_range 4), the commitment losses and the total loss.  (The reference's median
+        entries -- torch.median over the whole volume -- are not produced.)"""
+        x, num_valid = batch
+        decoded, (commitment, *_) = self(x)
+        nv = torch.as_tensor(num_valid, dtype=torch.int32, device=x.device).reshape(-1)
+        mask = None
+        if self.extract_center_cylinder:
+            if self._cyl_mask is None or self._cyl_mask.numel() != x.shape[2] * x.shape[3]:
+                self._cyl_mask = center_cylinder_mask(x.shape[2], x.shape[3]).to(torch.uint8).reshape(-1).to(x.device)
+            mask = self._cyl_mask
+        log = _ops.default().huber_metrics(decoded, x, nv, mask)
+        log.update({f"commitment_loss_{i}": c for i, c in enumerate(commitment)})
+        log["loss"] = log["recon_loss_mean"] + sum(commitment)
+        return log
+
     # ---- model.py:165-210 -------------------------------------------------------------
     def _parse_input_args(self, args: Namespace):
         assert args.metric in self.supported_metrics

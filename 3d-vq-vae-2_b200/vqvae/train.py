@@ -67,19 +67,24 @@ def load_checkpoint(model: VQVAE, optimizer, path) -> dict:
 
 
 @torch.no_grad()
-def validate(model: VQVAE, loader, dev, world: int) -> float:
-    """val_recon_loss_mean (model.py:157-160): the mean reconstruction loss over the validation volumes of all ranks."""
+def validate(model: VQVAE, loader, dev, world: int) -> dict:
+    """The validation log of the reference (model.py:143-160), averaged over the validation volumes of all ranks:
+    val_recon_loss_mean (the checkpoint monitor, train.py:56), nmse, psnr -- one fused pass per volume
+    (`VQVAE.validation_metrics`)."""
     was_training = model.training
     model.eval()
-    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    keys = ("recon_loss_mean", "nmse", "psnr")
+    acc = torch.zeros(len(keys) + 1, dtype=torch.float64, device=dev)
     for x, num_valid in loader:
-        _, log = model.huber((x.to(dev, non_blocking=True), num_valid))
-        acc[0] += log["recon_loss_mean"].double()
-        acc[1] += 1
+        log = model.validation_metrics((x.to(dev, non_blocking=True), num_valid))
+        for i, k in enumerate(keys):
+            acc[i] += log[k].double()
+        acc[-1] += 1
     if world > 1:
         dist.all_reduce(acc)
     model.train(was_training)
-    return float(acc[0] / acc[1].clamp(min=1))
+    n = float(acc[-1].clamp(min=1))
+    return {f"val_{k}": float(acc[i]) / n for i, k in enumerate(keys)}
 
 
 def main(args):
@@ -122,9 +127,10 @@ def main(args):
     def run_validation(epoch):
         """ModelCheckpoint(save_top_k=1, save_last=True, monitor='val_recon_loss_mean'), train.py:56."""
         nonlocal best
-        val = validate(model, val_loader, dev, world)
+        log = validate(model, val_loader, dev, world)
+        val = log["val_recon_loss_mean"]
         if rank == 0:
-            print(f"epoch {epoch} step {step} val_recon_loss_mean {val:.6f}", flush=True)
+            print(f"epoch {epoch} step {step} " + " ".join(f"{k} {v:.6f}" for k, v in log.items()), flush=True)
             if val < best:
                 best = val
                 save_checkpoint(model, args, ckpt_dir / "best.ckpt", step, epoch, optimizer, monitor=val)

@@ -321,6 +321,18 @@ int vq3d_huber_elu_mask(const float *decoded, const float *x, const int32_t *num
                         int64_t B, int H, int W, int Z, double *sum, double *count, void *stream);
 
 /*
+ * The same fused pass with every statistic the reference logs beside the loss (model.py:143-149: sub_metric_log_dict of
+ * the unreduced loss and of the masked reconstruction, nmse / psnr of metrics/evaluate.py:18-24) as partial sums, so that the
+ * validation epilogue reads the two volumes once and nothing is materialised:
+ *   sums[0..6]  += sum loss, count, sum (loc - x)^2, sum x^2, sum loc, sum loc^2, sum loss^2   (doubles; caller zeroes 8 entries)
+ *   minmax[0..3] = min loc, max loc, min loss, max loss      (caller initialises to +inf, -inf, +inf, -inf)
+ * loc = mask(ELU(decoded)); voxels outside mask_hw are skipped as in vq3d_huber_elu_mask.  The median entries of the
+ * reference's log (torch.median over the whole volume) are not produced here.
+ */
+int vq3d_huber_elu_mask_stats(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                              int64_t B, int H, int W, int Z, double *sums, float *minmax, void *stream);
+
+/*
  * Output epilogue of vqvae/decode_embeddings.py:43-47, fused: out[i] = rint(ELU(decoded[i]) * scale - offset) as int64
  * (the reference: F.elu, then numpy `res * 1000 - 1000`, np.rint, astype(int)); n elements.
  */

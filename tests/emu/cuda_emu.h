@@ -163,6 +163,15 @@ inline double atomicAdd(double *p, double v) {
     return f;
 }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T emu_atomic_minmax(T *p, T v, bool want_min) {
+    T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while ((want_min ? v < old : v > old) && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {}
+    return old;
+}
+inline int atomicMin(int *p, int v) { return emu_atomic_minmax(p, v, true); }
+inline int atomicMax(int *p, int v) { return emu_atomic_minmax(p, v, false); }
+inline unsigned atomicMin(unsigned *p, unsigned v) { return emu_atomic_minmax(p, v, true); }
+inline unsigned atomicMax(unsigned *p, unsigned v) { return emu_atomic_minmax(p, v, false); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 

@@ -165,6 +165,28 @@ def test_int16_hounsfield_kernels_on_the_emulator():
     assert int(b.reshape(-1)[0]) == 32767 and int(b.reshape(-1)[1]) == -2000
 
 
+@pytest.mark.parametrize("cyl", [False, True])
+def test_validation_metrics_kernel_on_the_emulator(cyl):
+    """vq3d_huber_elu_mask_stats: recon_loss / loc min, max, mean, std + nmse + psnr (model.py:143-149, metrics/evaluate.py:18-24)
+    from one pass, against the oracle's restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu.emu_ops import use_emulator
+    from oracle import vqvae_oracle as O
+    from vqvae import _ops
+    from vqvae.model import center_cylinder_mask
+    torch.manual_seed(3)
+    dec = torch.randn(2, 1, 10, 12, 9) * 1.5
+    x = torch.rand(2, 1, 10, 12, 9) * 4.5 - 0.5
+    nv = [9, 6]
+    ref = O.validation_log(dec, x, nv, cylinder=cyl)
+    mask = center_cylinder_mask(10, 12).to(torch.uint8).reshape(-1) if cyl else None
+    with use_emulator():
+        got = _ops.default().huber_metrics(dec, x, torch.tensor(nv, dtype=torch.int32), mask)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert abs(float(got[k]) - float(ref[k])) <= 2e-5 * max(1.0, abs(float(ref[k]))), (k, float(got[k]), float(ref[k]))
+
+
 def test_decode_database_iteration_and_names():
     from vqvae.decode_embeddings import iter_samples, output_name
     db = {0: {"a": {"data": torch.ones(2, 2, 2, dtype=torch.long), "condition": "t1"},

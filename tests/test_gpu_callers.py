@@ -173,3 +173,18 @@ def test_decoder_tail_with_two_output_channels_falls_back():
     loss, log = m.huber((x.to(DEV), [6]))
     ref_total, ref_recon = O.huber_epilogue(ref_dec, x, [6], list(ref_loss), cylinder=False)
     assert abs(float(log["recon_loss_mean"]) - float(ref_recon)) <= 1e-5 * abs(float(ref_recon)) + 1e-7
+
+
+def test_validation_metrics_fused_pass_vs_oracle():
+    """VQVAE.validation_metrics (vq3d_huber_elu_mask_stats): the reference's validation log -- recon_loss / loc min, max, mean,
+    std, nmse, psnr (model.py:143-149, metrics/evaluate.py:18-24) -- against the oracle on the oracle's own reconstruction."""
+    m = _model()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = O.synthetic_volume((2, 1, 16, 16, 8), seed=5)
+    ref_dec, (ref_loss, _, ref_idx) = O.vqvae_forward(sd, O.ModelConfig(**CFG), x)
+    ref = O.validation_log(ref_dec, x, [8, 5], cylinder=False)
+    m = m.to(DEV)
+    got = m.validation_metrics((x.to(DEV), [8, 5]))
+    for k, v in ref.items():
+        assert abs(float(got[k]) - float(v)) <= 1e-4 * max(1.0, abs(float(v))), (k, float(got[k]), float(v))
+    assert abs(float(got["loss"]) - float(ref["recon_loss_mean"] + sum(ref_loss))) <= 1e-4
