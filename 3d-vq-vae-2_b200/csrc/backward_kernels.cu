@@ -19,6 +19,7 @@ struct BwdParams {
     const float *x1, *x2, *w, *pre_a, *pre_b, *post_scale;
     const float *gy, *raw;
     float *gx1, *gx2, *gw, *gbias, *gscal;      // gscal: [d pre_a, d pre_b, d post_scale, d post_b]
+    int gscal_want_pb;                          // conv1x1_bwd_kernel: the forward had a post_b
 };
 
 __device__ __forceinline__ float block_sum(float v, float *red /* [32] shared */) {
@@ -174,6 +175,324 @@ conv3d_outgrads_kernel(const float *__restrict__ gy, const float *__restrict__ r
         if (gbias) atomicAdd(gbias + co, t1);
         if (gscal && want_pb) atomicAdd(gscal + 3, t1);
         if (gscal && want_scale && raw) atomicAdd(gscal + 2, t2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused backward of a pointwise (k1 s1) convolution: input gradient with the pre-transform chain, weight gradient, bias
+// gradient and the four Fixup scalar gradients in ONE launch (the generic path needs a forward-form dgrad convolution, its
+// finish kernel, the tiled wgrad kernel, the out-grads kernel and -- for d scale -- a recomputed forward convolution).
+// Two of the three convolutions of every PreActFixupResBlock are pointwise (layers.py:134-160).
+//
+// Persistent CTAs loop over tiles of T voxels (thread = voxel): x, the transformed input u, ELU' and gy are staged in shared
+// memory once per tile; each thread then forms gu = scale * W^T gy (-> gx, d pre_a, d pre_b) and raw = W u (-> d scale) for
+// its voxel, and the weight gradient is a [Cout x T] x [T x Cin] product out of the same tiles: every (co, ci) pair -- plus
+// one pseudo pair per output channel for the bias sums -- is owned by one thread, or by T / R threads that split the tile's
+// voxels when there are fewer pairs than threads (the thin 512^3 layers have 8).  Pair sums stay in registers across tiles;
+// one atomicAdd per owner at the end.
+constexpr int kPwT = 128;          // voxels per tile = threads
+constexpr int kPwMaxRows = 24;     // (co, ci) + bias rows per thread: Cin * Cout + Cout <= 24 * 128
+
+__global__ void __launch_bounds__(kPwT)
+conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
+    VQ3D_DYN_SMEM(float, sm);
+    __shared__ float red[32];
+    const int Cin = p.C1 + p.C2, Cout = p.Cout, T = kPwT, LD = kPwT + 1;
+    float *sW = sm;                               // [Cout][Cin]
+    float *sU = sW + Cout * Cin;                  // [Cin][LD]  transformed input
+    float *sD = sU + Cin * LD;                    // [Cin][LD]  ELU' (1 without pre-activation)
+    float *sG = sD + Cin * LD;                    // [Cout][LD] gy
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cout * Cin; i += T) sW[i] = __ldg(p.w + i);
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const int R = Cin * Cout + Cout;              // rows of the pair phase: (co, ci) pairs, then one bias row per co
+    const int nsplit = R < T ? T / R : 1;
+    const int my_row0 = R < T ? (tid < R * nsplit ? tid % R : -1) : tid;
+    const int my_part = R < T ? tid / R : 0;
+    float acc[kPwMaxRows];
+#pragma unroll
+    for (int j = 0; j < kPwMaxRows; ++j) acc[j] = 0.0f;
+    float s_a = 0.0f, s_b = 0.0f, s_s = 0.0f;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t v = tile * T + tid;
+        const bool active = v < total;
+        const int64_t b = active ? v / S : 0, r = active ? v - b * S : 0;
+        __syncthreads();                          // the previous tile's pair phase has read sU / sG
+        // stage the tile: all global loads of a thread are independent -> issue them four channels at a time
+        for (int c0 = 0; c0 < Cin; c0 += 4) {
+            float xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = c0 + j;
+                xv[j] = 0.0f;
+                if (active && ci < Cin)
+                    xv[j] = ci < p.C1 ? __ldg(p.x1 + ((size_t)b * p.C1 + ci) * S + r) : __ldg(p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S + r);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = c0 + j;
+                if (ci >= Cin) break;
+                float u = 0.0f, dd = 0.0f;
+                if (active) {
+                    if (p.pre_act) {
+                        const float t = xv[j] + pa;
+                        const float e = __expf(t);
+                        u = (t > 0.0f ? t : e - 1.0f) + pb;
+                        dd = t > 0.0f ? 1.0f : e;
+                    } else {
+                        u = xv[j] + pb;
+                        dd = 1.0f;
+                    }
+                }
+                sU[ci * LD + tid] = u;
+                sD[ci * LD + tid] = dd;
+            }
+        }
+        for (int c0 = 0; c0 < Cout; c0 += 4) {
+            float gv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[j] = (active && c0 + j < Cout) ? __ldg(p.gy + ((size_t)b * Cout + c0 + j) * S + r) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < Cout) sG[(c0 + j) * LD + tid] = gv[j];
+        }
+        __syncthreads();
+        if (active) {
+            const bool want_in = p.gx1 || p.gx2 || (p.gscal && (p.pre_a || p.pre_b));
+            if (want_in) {
+                for (int c0 = 0; c0 < Cin; c0 += 4) {                 // four input channels per pass: one gy read feeds four FMAs
+                    float gu[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    for (int co = 0; co < Cout; ++co) {
+                        const float g = sG[co * LD + tid];
+                        const float *wr = sW + co * Cin + c0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (c0 + j < Cin) gu[j] = __fmaf_rn(wr[j], g, gu[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ci = c0 + j;
+                        if (ci >= Cin) break;
+                        const float guj = gu[j] * sc;
+                        const float gx = guj * sD[ci * LD + tid];
+                        s_b += guj;
+                        s_a += gx;
+                        float *dst = ci < p.C1 ? (p.gx1 ? p.gx1 + ((size_t)b * p.C1 + ci) * S + r : nullptr)
+                                               : (p.gx2 ? p.gx2 + ((size_t)b * p.C2 + (ci - p.C1)) * S + r : nullptr);
+                        if (dst) *dst = gx;
+                    }
+                }
+            }
+            if (want_scale) {
+                for (int c0 = 0; c0 < Cout; c0 += 4) {
+                    float raw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    for (int ci = 0; ci < Cin; ++ci) {
+                        const float u = sU[ci * LD + tid];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (c0 + j < Cout) raw[j] = __fmaf_rn(sW[(c0 + j) * Cin + ci], u, raw[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + j < Cout) s_s = __fmaf_rn(sG[(c0 + j) * LD + tid], raw[j], s_s);
+                }
+            }
+        }
+        if (p.gw || p.gbias || (p.gscal && p.gscal_want_pb)) {
+            // pair phase: acc[row] += sum over the tile's voxels of gy[co] * u[ci]   (bias rows: u == 1)
+            if (R < T) {
+                if (my_row0 >= 0) {
+                    const int row = my_row0;
+                    float a = 0.0f;
+                    if (row < Cin * Cout) {
+                        const float *g = sG + (row / Cin) * LD, *u = sU + (row % Cin) * LD;
+                        for (int vv = my_part; vv < T; vv += nsplit) a = __fmaf_rn(g[vv], u[vv], a);
+                    } else {
+                        const float *g = sG + (row - Cin * Cout) * LD;
+                        for (int vv = my_part; vv < T; vv += nsplit) a += g[vv];
+                    }
+                    acc[0] += a;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kPwMaxRows; ++j) {
+                    const int row = tid + j * T;
+                    if (row < R) {
+                        float a = 0.0f;
+                        if (row < Cin * Cout) {
+                            const float *g = sG + (row / Cin) * LD, *u = sU + (row % Cin) * LD;
+#pragma unroll 4
+                            for (int vv = 0; vv < T; ++vv) a = __fmaf_rn(g[vv], u[vv], a);
+                        } else {
+                            const float *g = sG + (row - Cin * Cout) * LD;
+#pragma unroll 4
+                            for (int vv = 0; vv < T; ++vv) a += g[vv];
+                        }
+                        acc[j] += a;
+                    }
+                }
+            }
+        }
+    }
+    // ---- flush: one atomicAdd per row and CTA (split mode: the T / R partial sums of a row meet in shared memory first;
+    // per-thread atomics on a handful of addresses were 80 % of this kernel's time on the thin layers) ----
+    if (R < T) {
+        __syncthreads();
+        if (my_row0 >= 0) sU[my_part * R + my_row0] = acc[0];          // nsplit * R <= T floats
+        __syncthreads();
+        if (tid < R) {
+            float a = 0.0f;
+            for (int part = 0; part < nsplit; ++part) a += sU[part * R + tid];
+            acc[0] = a;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kPwMaxRows; ++j) {
+        const int row = R < T ? ((j == 0 && tid < R) ? tid : -1) : tid + j * T;
+        if (row < 0 || row >= R) continue;
+        if (row < Cin * Cout) {
+            if (p.gw) atomicAdd(p.gw + row, acc[j] * sc);                 // gw [Cout][Cin]: row = co * Cin + ci
+        } else {
+            if (p.gbias) atomicAdd(p.gbias + (row - Cin * Cout), acc[j]);
+            if (p.gscal && p.gscal_want_pb) atomicAdd(p.gscal + 3, acc[j]);
+        }
+    }
+    if (p.gscal) {
+        const float ta = block_sum(p.pre_act ? s_a : 0.0f, red);
+        const float tb = block_sum(s_b, red);
+        const float ts = block_sum(s_s, red);
+        if (tid == 0) {
+            if (p.pre_act && p.pre_a) atomicAdd(p.gscal + 0, ta);
+            if (p.pre_b) atomicAdd(p.gscal + 1, tb);
+            if (want_scale) atomicAdd(p.gscal + 2, ts);
+        }
+    }
+}
+
+// Thin pointwise convolutions (C_in, C_out <= 8: every 1x1 of the 512^3 / 256^3 levels and of the 2- / 4- / 8-channel
+// stacks): a streaming variant without shared-memory staging.  Thread = voxel (grid-stride); the (co, ci) pair sums and the
+// bias sums live in registers for the whole kernel and meet in one warp-shuffle + shared-memory reduction at the end, so the
+// kernel reads x and gy once, writes gx once, and issues Cin * Cout + Cout + 3 atomics per CTA.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+conv1x1_bwd_thin_kernel(BwdParams p, int64_t total, int want_scale) {
+    __shared__ float sW[COUT * CIN];
+    __shared__ float red[8][CIN * COUT + COUT + 3];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < COUT * CIN; i += blockDim.x) sW[i] = __ldg(p.w + i);
+    __syncthreads();
+    float w[COUT][CIN];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) w[co][ci] = sW[co * CIN + ci];
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    float acc[COUT][CIN], bacc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        bacc[co] = 0.0f;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) acc[co][ci] = 0.0f;
+    }
+    float s_a = 0.0f, s_b = 0.0f, s_s = 0.0f;
+    const bool want_in = p.gx1 || p.gx2 || (p.gscal && (p.pre_a || p.pre_b));
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + tid; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = v / S, r = v - b * S;
+        float xv[CIN], g[COUT], u[CIN], dd[CIN];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+            xv[ci] = ci < p.C1 ? __ldcs(p.x1 + ((size_t)b * p.C1 + ci) * S + r) : __ldcs(p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S + r);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) g[co] = __ldcs(p.gy + ((size_t)b * COUT + co) * S + r);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            if (p.pre_act) {
+                const float t = xv[ci] + pa, e = __expf(t);
+                u[ci] = (t > 0.0f ? t : e - 1.0f) + pb;
+                dd[ci] = t > 0.0f ? 1.0f : e;
+            } else {
+                u[ci] = xv[ci] + pb;
+                dd[ci] = 1.0f;
+            }
+        }
+        if (want_in) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                float gu = 0.0f;
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) gu = __fmaf_rn(w[co][ci], g[co], gu);
+                gu *= sc;
+                const float gx = gu * dd[ci];
+                s_b += gu;
+                s_a += gx;
+                float *dst = ci < p.C1 ? (p.gx1 ? p.gx1 + ((size_t)b * p.C1 + ci) * S + r : nullptr)
+                                       : (p.gx2 ? p.gx2 + ((size_t)b * p.C2 + (ci - p.C1)) * S + r : nullptr);
+                if (dst) __stcs(dst, gx);
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            if (want_scale) {
+                float raw = 0.0f;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) raw = __fmaf_rn(w[co][ci], u[ci], raw);
+                s_s = __fmaf_rn(g[co], raw, s_s);
+            }
+            bacc[co] += g[co];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) acc[co][ci] = __fmaf_rn(g[co], u[ci], acc[co][ci]);
+        }
+    }
+    // ---- one reduction per CTA ----
+    constexpr int NV = CIN * COUT + COUT + 3;
+    float vals[NV];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) vals[co * CIN + ci] = acc[co][ci];
+        vals[CIN * COUT + co] = bacc[co];
+    }
+    vals[NV - 3] = p.pre_act ? s_a : 0.0f; vals[NV - 2] = s_b; vals[NV - 1] = s_s;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vals[i] += __shfl_xor_sync(0xffffffffu, vals[i], o);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[warp][i] = vals[i];
+    }
+    __syncthreads();
+    if (tid < NV) {
+        float t = 0.0f;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += red[wv][tid];
+        if (tid < CIN * COUT) {
+            if (p.gw) atomicAdd(p.gw + tid, t * sc);
+        } else if (tid < CIN * COUT + COUT) {
+            if (p.gbias) atomicAdd(p.gbias + (tid - CIN * COUT), t);
+            if (p.gscal && p.gscal_want_pb) atomicAdd(p.gscal + 3, t);
+        } else if (p.gscal) {
+            const int k = tid - (CIN * COUT + COUT);
+            if (k == 0 && p.pre_act && p.pre_a) atomicAdd(p.gscal + 0, t);
+            if (k == 1 && p.pre_b) atomicAdd(p.gscal + 1, t);
+            if (k == 2 && want_scale) atomicAdd(p.gscal + 2, t);
+        }
+    }
+}
+
+template <int CIN>
+static int launch_pw_thin(const BwdParams &p, int Cout, int64_t total, int want_scale, void *stream) {
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    const dim3 grid((unsigned)blocks), block(256);
+    switch (Cout) {
+        case 1: return launch("conv1x1_bwd_thin", conv1x1_bwd_thin_kernel<CIN, 1>, grid, block, 0, stream, p, total, want_scale);
+        case 2: return launch("conv1x1_bwd_thin", conv1x1_bwd_thin_kernel<CIN, 2>, grid, block, 0, stream, p, total, want_scale);
+        case 4: return launch("conv1x1_bwd_thin", conv1x1_bwd_thin_kernel<CIN, 4>, grid, block, 0, stream, p, total, want_scale);
+        case 8: return launch("conv1x1_bwd_thin", conv1x1_bwd_thin_kernel<CIN, 8>, grid, block, 0, stream, p, total, want_scale);
+        default: return -1;
     }
 }
 
@@ -516,6 +835,47 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
         if (rc) return rc;
     }
     return VQ3D_OK;
+}
+
+extern "C" int vq3d_conv1x1_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd *g, void *stream) {
+    if (!d || !g || !g->gy) return fail(VQ3D_ERR_INVALID, "conv1x1_backward: null descriptor / gy");
+    if (!d->x1 || !d->w) return fail(VQ3D_ERR_INVALID, "conv1x1_backward: null x1/w");
+    if (d->k != 1 || d->stride != 1 || d->pad != 0) return fail(VQ3D_ERR_INVALID, "conv1x1_backward: pointwise (k1 s1 p0) convolutions only");
+    if (d->post_act) return fail(VQ3D_ERR_UNSUPPORTED, "conv1x1_backward: post_act has no backward in this build");
+    if (d->C2 > 0 && !d->x2) return fail(VQ3D_ERR_INVALID, "conv1x1_backward: C2 > 0 but x2 is NULL");
+    const int Cin = d->C1 + d->C2;
+    if (Cin * d->Cout + d->Cout > kPwMaxRows * kPwT) return fail(VQ3D_ERR_UNSUPPORTED, "conv1x1_backward: %d x %d channels exceed the fused kernel", Cin, d->Cout);
+    const size_t smem = ((size_t)d->Cout * Cin + (size_t)(2 * Cin + d->Cout) * (kPwT + 1)) * sizeof(float);
+    if (smem > 200 * 1024) return fail(VQ3D_ERR_UNSUPPORTED, "conv1x1_backward: channel counts exceed shared memory");
+    BwdParams p = {};
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z; p.C1 = d->C1; p.C2 = d->C2; p.Cout = d->Cout;
+    p.k = 1; p.stride = 1; p.pad = 0; p.circ = 0; p.pre_act = d->pre_act;
+    p.Ho = d->H; p.Wo = d->W; p.Zo = d->Z;
+    p.x1 = d->x1; p.x2 = d->x2; p.w = d->w; p.pre_a = d->pre_a; p.pre_b = d->pre_b; p.post_scale = d->post_scale;
+    p.gy = g->gy; p.raw = nullptr; p.gx1 = g->gx1; p.gx2 = g->gx2; p.gw = g->gw; p.gbias = g->gbias; p.gscal = g->gscalars;
+    p.gscal_want_pb = d->post_b != nullptr;
+    const int64_t total = (int64_t)d->B * d->H * d->W * d->Z;
+    {   // thin layers: streaming kernel, pair sums in registers
+        const int ws = (int)(d->post_scale != nullptr && g->gscalars != nullptr);
+        int rc = -1;
+        if (Cin * d->Cout <= 32)                 // 8 x 8 needs 255 registers: left to the tiled kernel
+        switch (Cin) {
+            case 1: rc = launch_pw_thin<1>(p, d->Cout, total, ws, stream); break;
+            case 2: rc = launch_pw_thin<2>(p, d->Cout, total, ws, stream); break;
+            case 4: rc = launch_pw_thin<4>(p, d->Cout, total, ws, stream); break;
+            case 8: rc = launch_pw_thin<8>(p, d->Cout, total, ws, stream); break;
+            default: break;
+        }
+        if (rc >= 0) return rc;
+    }
+    const int64_t ntiles = ceil_div(total, kPwT);
+    int per_sm = (int)(200 * 1024 / (smem > 1024 ? smem : 1024));
+    if (per_sm > 12) per_sm = 12;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)kNumSMs * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    return launch("conv1x1_bwd", conv1x1_bwd_kernel, dim3((unsigned)grid), dim3(kPwT), smem, stream, p, total, ntiles,
+                  (int)(d->post_scale != nullptr && g->gscalars != nullptr));
 }
 
 extern "C" int vq3d_conv3d_dgrad_finish(const vq3d_conv_desc *d, const float *gu_all, float *gx1, float *gx2, float *gscalars, void *stream) {

@@ -54,6 +54,7 @@ SIGNATURES = {
     "vq3d_conv3d_tc_workspace": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "vq3d_conv3d_tc": (C.c_int, [C.POINTER(ConvDesc), _fp, C.c_size_t, _fp]),
     "vq3d_conv3d_backward": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvBwd), _fp]),
+    "vq3d_conv1x1_backward": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvBwd), _fp]),
     "vq3d_conv3d_dgrad_finish": (C.c_int, [C.POINTER(ConvDesc), _fp, _fp, _fp, _fp, _fp]),
     "vq3d_upsample2x_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp]),
     "vq3d_huber_elu_mask_backward": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),

@@ -32,6 +32,7 @@ class Ops:
         # (0.72 vs 0.52 ms per 4->2->4 block and volume: the im2col copy saturates the shared-memory pipe), so off by default
         self.thin_tc = os.environ.get("VQ3D_THIN_TC", "0") == "1"
         self.up_tc = os.environ.get("VQ3D_UP_TC", "1") == "1"      # wide 'up' blocks on the tensor-core kernel (bf16 mode)
+        self.fused_pointwise_bwd = os.environ.get("VQ3D_FUSED_PW_BWD", "1") == "1"   # k1 convolutions: one fused backward launch
         self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
@@ -193,6 +194,23 @@ class Ops:
         """need: dict of booleans (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b).  Returns the gradients (or None)."""
         D = lambda t: None if t is None else self._t(t.detach())
         x1, x2, w, pre_a, pre_b, post_scale, post_b, gy = D(x1), D(x2), D(w), D(pre_a), D(pre_b), D(post_scale), D(post_b), D(gy)
+        k = w.shape[2]
+        tag = f"{w.shape[1]}->{w.shape[0]} k{k}s{cfg['stride']} @{x1.shape[2]}x{x1.shape[3]}x{x1.shape[4]}"
+        if self.fused_pointwise_bwd and k == 1 and cfg["stride"] == 1 and cfg["pad"] == 0 and w.shape[0] * (w.shape[1] + 1) <= 3072:
+            # pointwise convolution: every gradient from ONE fused launch (the kernel recomputes what d scale needs)
+            dev = x1.device
+            gx1 = torch.empty_like(x1) if need["x1"] else None
+            gx2 = torch.empty_like(x2) if (x2 is not None and need["x2"]) else None
+            gw = torch.zeros_like(w) if need["w"] else None
+            gbias = torch.zeros(w.shape[0], dtype=torch.float32, device=dev) if need["bias"] else None
+            want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
+            gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
+            d = self.conv_desc(x1, x2, w, 1, 0, False, cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
+            g = _cabi.ConvBwd(gy=self._p(gy), raw=None, gx1=self._p(gx1), gx2=self._p(gx2), gw=self._p(gw), gbias=self._p(gbias),
+                              gscalars=self._p(gscal), skip_input_grads=0)
+            if self._call("conv1x1_backward", self.lib.vq3d_conv1x1_backward, (C.byref(d), C.byref(g), self.stream()), tag=tag,
+                          allow_unsupported=True):
+                return gx1, gx2, gw, gbias, gscal
         raw = None
         if need["post_scale"]:        # d scale = sum(gy * conv output before the post transform): recompute it
             raw = self._conv3d_fwd(x1, w, x2=x2, stride=cfg["stride"], pad=cfg["pad"], circular=cfg["circular"], pre_act=cfg["pre_act"],

@@ -171,6 +171,15 @@ typedef struct vq3d_conv_bwd {
 int vq3d_conv3d_backward(const vq3d_conv_desc *desc, const vq3d_conv_bwd *grads, void *stream);
 
 /*
+ * The same gradients for a POINTWISE convolution (k = 1, stride 1, no padding: branch_conv1 / branch_conv3 / the 1x1 skip and
+ * proj / parse_input / out convolutions, layers.py:134-160,377,490,508,535) in ONE launch: gx1 / gx2, gw, gbias and all four
+ * scalar gradients, with the convolution output that d post_scale needs recomputed inside the kernel (grads->raw and
+ * grads->skip_input_grads are ignored).  Same accumulate / overwrite conventions as vq3d_conv3d_backward.
+ * VQ3D_ERR_UNSUPPORTED when (C1 + C2) * Cout + Cout > 3072 (callers use vq3d_conv3d_backward).
+ */
+int vq3d_conv1x1_backward(const vq3d_conv_desc *desc, const vq3d_conv_bwd *grads, void *stream);
+
+/*
  * Input gradient of a stride-1 "same" convolution (k odd, pad = (k-1)/2) as a FORWARD convolution: the caller runs
  * vq3d_conv3d[_tc] on gy with the flipped / transposed weight (C_in <-> C_out, every tap mirrored, same padding mode),
  * which yields gu_all [B, C1+C2, H, W, Z] = d loss / d (conv input) up to the post scale; this entry point finishes it:
