@@ -103,6 +103,96 @@ conv3d_dgrad_kernel(BwdParams p) {
     }
 }
 
+// Input gradient of the two stride-2 convolutions of a 'down' block (layers.py:124-132: k4 s2 p1 branch convolution,
+// k2 s2 p0 skip) in gather form without searching: along each axis input index i is read by at most two outputs of the
+// k4 convolution (taps k = par and par + 2 with par = (i + 1) & 1, outputs (i + 1 - par) / 2 and one less, wrapped when the
+// padding is circular) and by exactly one of the k2 convolution (tap i & 1, output i >> 1).  Thread = input voxel, four input
+// channels per pass, weights in shared memory.  (The shape-generic kernel above spent 13 ms on the 4 -> 4 k4 s2 layer of one
+// 512 x 512 x 128 volume; this one is bound by writing gx.)
+template <int K>
+__global__ void __launch_bounds__(256)
+conv3d_dgrad_s2_kernel(BwdParams p) {
+    VQ3D_DYN_SMEM(float, sw);                          // [Cout][Cin][K^3]
+    __shared__ float red[32];
+    constexpr int K3 = K * K * K, NC = K == 4 ? 2 : 1;
+    const int Cin = p.C1 + p.C2, Cout = p.Cout;
+    for (int i = threadIdx.x; i < Cout * Cin * K3; i += blockDim.x) sw[i] = __ldg(p.w + i);
+    __syncthreads();
+    const int64_t S = (int64_t)p.H * p.W * p.Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f);
+    float s_a = 0.0f, s_b = 0.0f;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < (int64_t)p.B * S; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = v / S;
+        int64_t r = v - b * S;
+        const int ih = (int)(r / ((int64_t)p.W * p.Z));
+        r -= (int64_t)ih * p.W * p.Z;
+        const int iw = (int)(r / p.Z), iz = (int)(r - (int64_t)iw * p.Z);
+        int oh[NC], kh[NC], ow[NC], kw[NC], oz[NC], kz[NC];
+        bool vh[NC], vw[NC], vz[NC];
+        auto axis = [&](int i, int n_out, int *o, int *k, bool *ok) {
+            if (K == 4) {
+                const int par = (i + 1) & 1;
+                o[0] = (i + 1 - par) >> 1; k[0] = par;
+                o[1 % NC] = o[0] - 1; k[1 % NC] = par + 2;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (p.circ) { o[c] = o[c] < 0 ? o[c] + n_out : (o[c] >= n_out ? o[c] - n_out : o[c]); ok[c] = true; }
+                    else ok[c] = o[c] >= 0 && o[c] < n_out;
+                }
+            } else {
+                o[0] = i >> 1; k[0] = i & 1; ok[0] = o[0] < n_out;
+            }
+        };
+        axis(ih, p.Ho, oh, kh, vh); axis(iw, p.Wo, ow, kw, vw); axis(iz, p.Zo, oz, kz, vz);
+        const float *gyb = p.gy + (size_t)b * Cout * So;
+        for (int c0 = 0; c0 < Cin; c0 += 4) {
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int a = 0; a < NC; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int e = 0; e < NC; ++e) {
+                        if (!(vh[a] && vw[c] && vz[e])) continue;
+                        const size_t go = ((size_t)oh[a] * p.Wo + ow[c]) * p.Zo + oz[e];
+                        const int tap = (kh[a] * K + kw[c]) * K + kz[e];
+                        for (int co = 0; co < Cout; ++co) {
+                            const float g = __ldg(gyb + (size_t)co * So + go);
+                            const float *wr = sw + ((size_t)co * Cin + c0) * K3 + tap;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (c0 + j < Cin) acc[j] = __fmaf_rn(wr[j * K3], g, acc[j]);
+                        }
+                    }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = c0 + j;
+                if (ci >= Cin) break;
+                const float gu = acc[j] * sc;
+                const bool first = ci < p.C1;
+                const size_t off = first ? ((size_t)b * p.C1 + ci) * S + (v - b * S) : ((size_t)b * p.C2 + (ci - p.C1)) * S + (v - b * S);
+                float gx = gu;
+                if (p.pre_act) {
+                    const float t = (first ? p.x1 : p.x2)[off] + pa;
+                    gx = t > 0.0f ? gu : gu * __expf(t);
+                }
+                float *dst = first ? p.gx1 : p.gx2;
+                if (dst) dst[off] = gx;
+                s_b += gu;
+                s_a += gx;
+            }
+        }
+    }
+    if (p.gscal) {
+        const float ta = block_sum(p.pre_act ? s_a : 0.0f, red);
+        const float tb = block_sum(s_b, red);
+        if (threadIdx.x == 0) {
+            if (p.pre_act && p.pre_a) atomicAdd(p.gscal + 0, ta);
+            if (p.pre_b) atomicAdd(p.gscal + 1, tb);
+        }
+    }
+}
+
 // grid (voxel chunks, Cin, Cout): every thread accumulates the k^3 taps of one (co, ci) pair over its voxels
 __global__ void __launch_bounds__(128)
 conv3d_wgrad_kernel(BwdParams p) {
@@ -792,7 +882,16 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
     const int Cin = d->C1 + d->C2;
     const int64_t S = (int64_t)d->H * d->W * d->Z, So = (int64_t)p.Ho * p.Wo * p.Zo;
     int rc;
-    if (!g->skip_input_grads && (p.gx1 || p.gx2 || (p.gscal && (d->pre_a || d->pre_b)))) {
+    const bool s2_k4 = d->stride == 2 && d->k == 4 && d->pad == 1, s2_k2 = d->stride == 2 && d->k == 2 && d->pad == 0;
+    const size_t s2_smem = (size_t)d->Cout * Cin * d->k * d->k * d->k * sizeof(float);
+    if (!g->skip_input_grads && (p.gx1 || p.gx2 || (p.gscal && (d->pre_a || d->pre_b))) && (s2_k4 || s2_k2) && s2_smem <= 96 * 1024 &&
+        d->H % 2 == 0 && d->W % 2 == 0 && d->Z % 2 == 0) {
+        int64_t blocks = ceil_div((int64_t)d->B * S, 256);
+        if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+        rc = s2_k4 ? launch("conv3d_dgrad_s2", conv3d_dgrad_s2_kernel<4>, dim3((unsigned)blocks), dim3(256), s2_smem, stream, p)
+                   : launch("conv3d_dgrad_s2", conv3d_dgrad_s2_kernel<2>, dim3((unsigned)blocks), dim3(256), s2_smem, stream, p);
+        if (rc) return rc;
+    } else if (!g->skip_input_grads && (p.gx1 || p.gx2 || (p.gscal && (d->pre_a || d->pre_b)))) {
         rc = launch("conv3d_dgrad", conv3d_dgrad_kernel, dim3((unsigned)ceil_div((int64_t)d->B * S, 128), (unsigned)Cin), dim3(128), 0, stream, p);
         if (rc) return rc;
     }
