@@ -165,11 +165,14 @@ def quantizer_point(dev, pk, N=1 << 20, D=32, K=512, reps=10):
     gc = N / t / 1e9
     hbm = pk["hbm_gbs"] / (8 * D + 8)
     tens = pk.get("bf16_tflops_sustained", 1400.0) * 1e3 / (2.0 * K * D)
-    # third ceiling of this design: every score has to leave TMEM (N*K*4 bytes) at 64 B/clk per SM (guide figure, 148 SMs)
-    tmem = 148 * 64 * 1.965 / (4.0 * K)
+    # third ceiling of this design: every score has to leave TMEM (N*K*4 bytes).  tcgen05.ld measured on this part
+    # (tools/microbench/tc_microbench.cu -> profiles/r02_tc_microbench.txt): 460 B/clk per SM with the kernel's 16 sweep warps
+    # (32x32b.x64), 390 B/clk with its x16 loads -- not the 64 B/clk that round 1 assumed
+    tmem = 148 * 390 * 1.965 / (4.0 * K)
     return {"value": gc, "unit": "Gcodes/s", "config": {"N": N, "D": D, "K": K, "mode": "eval", "path": "tcgen05 bf16 candidate pass + exact fp32 re-rank"},
             "ms": t * 1e3, "roofline": {"bound": "hbm" if hbm < tens else "tensor", "peak": min(hbm, tens), "unit": "Gcodes/s", "frac": gc / min(hbm, tens),
-                                        "tmem_read_ceiling": tmem, "frac_of_tmem_read_ceiling": gc / tmem},
+                                        "tmem_read_ceiling": tmem, "frac_of_tmem_read_ceiling": gc / tmem,
+                                        "tmem_read_ceiling_source": "measured tcgen05.ld throughput, profiles/r02_tc_microbench.txt"},
             "sweep": "profiles/r02_quantizer_sweep.tsv (tools/bench_quantizer.py, N up to 64 M)"}
 
 
@@ -441,7 +444,7 @@ def run_b200(args):
         dom = groups[dom_key]
 
         # ---- end to end through the public API with HOST buffers (pinned): H2D + forward + D2H inside the clock ----
-        e2e_steps = max(3, min(steps, 10))
+        e2e_steps = max(3, min(steps, 20))
 
         def fwd_api(xb):                     # VQVAE.forward: fp32 volume in, fp32 reconstruction + int64 code indices out
             dec, (_, _, idxs) = model(xb)
