@@ -35,6 +35,7 @@
 #include "vq3d_rt.h"
 
 #ifndef VQ3D_EMU
+#include <cuda.h>            // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
 #include <cuda_bf16.h>
 #include <cstdlib>
 
@@ -69,10 +70,22 @@ struct TcsParams {
     float *y;                              // output of every block (updated in place from block 1 on)
     uint4 *t1[2];                          // bf16 t1 ping-pong: [B][NCH][H][W][Z+2] 16-byte units
     const unsigned char *wimg;             // per block [W1 | W2 | W3] bf16 B-operand images (+ one trailing W1 slot)
+    // 5-D tensor maps over the two t1 buffers (dims, fastest first: 8 bf16 | Z+2 | W | H | B*NCH; box 8 x (Z+2) x (tw+2) x (th+2) x 1):
+    // the whole haloed box of an interior tile is ONE cp.async.bulk.tensor per 8-channel chunk, landing in shared memory in
+    // exactly the [h][w][z][16 B] order the shifted-window MMAs read.  Tiles whose halo wraps around the (circular) volume
+    // edge keep the row-by-row bulk copies.
+    int use_tma;
+    alignas(64) CUtensorMap tmap[2];
     TcsBlock blk[kTcsMaxBlocks];
 };
 
 #include "tc_common.cuh"
+
+// TMA tiled load of a 5-D box (UTMALDG): coordinates fastest dimension first; completion as tx bytes on `bar`
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, int c4, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(s_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ int pmodi(int i, int n) {
     int r = i % n;
@@ -421,6 +434,10 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
             uint32_t wbytes = (uint32_t)mine * row_bytes;       // bytes this warp will deliver
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) wbytes += __shfl_xor_sync(0xffffffffu, wbytes, o);
+            // TMA path: chunk kc of an interior tile is one box copy, issued by lane 0 of producer warp kc % 3
+            const int my_boxes = NCH > pw ? (NCH - 1 - pw) / kTcsProdWarps + 1 : 0;
+            const uint32_t box_bytes = (uint32_t)p.NL * 16u;
+            const CUtensorMap *tmap = &p.tmap[blk & 1];
             for (int i = 0; i < my_tiles; ++i) {
                 const uint32_t k = kt + (uint32_t)i, s = k % NBUF, u = k / NBUF;
                 int t = (int)blockIdx.x + i * (int)gridDim.x;
@@ -428,6 +445,16 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                 const int thi = t % p.nth; t /= p.nth;
                 const int b = t, oh0 = thi * p.th, ow0 = twi * p.tw;
                 mbarrier_wait(&bar_sa_empty[s], (u & 1u) ^ 1u);
+                if (p.use_tma && oh0 >= 1 && oh0 + p.th + 1 <= H && ow0 >= 1 && ow0 + p.tw + 1 <= W) {
+                    if (lane == 0) {
+                        mbarrier_arrive_expect_tx(&bar_full[s], (uint32_t)my_boxes * box_bytes);
+                        for (int kc = pw; kc < NCH; kc += kTcsProdWarps)
+                            tma_load_5d(sA_addr + s * sa_bytes + (uint32_t)kc * lbo_a, tmap, 0, 0, ow0 - 1, oh0 - 1, b * NCH + kc, &bar_full[s]);
+                    }
+                    __syncwarp();
+                    if (i == 0 && tid == 32) tc_trace(p.trace, blk, 2);
+                    continue;
+                }
                 if (lane == 0) mbarrier_arrive_expect_tx(&bar_full[s], wbytes);
                 __syncwarp();
                 for (int r = pw * 32 + lane; r < ncopies; r += kTcsProdWarps * 32) {
@@ -619,6 +646,40 @@ static int sm_count() {
     return n;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library links cudart statically and not libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TmapEncodeFn>(ptr);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// tensor maps of the two t1 buffers for a (th, tw) tiling; false = not available (the kernel then copies row by row)
+static bool make_t1_tmaps(TcsParams &p, int NCH) {
+    if (getenv("VQ3D_TC_NO_TMA")) return false;
+    TmapEncodeFn enc = tmap_encoder();
+    if (!enc || p.Z + 2 > 256 || p.tw + 2 > 256 || p.th + 2 > 256) return false;
+    const cuuint64_t dims[5] = {8, (cuuint64_t)(p.Z + 2), (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * NCH};
+    const cuuint64_t strides[4] = {16, 16ull * (p.Z + 2), 16ull * (p.Z + 2) * p.W, 16ull * (p.Z + 2) * p.W * p.H};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(p.Z + 2), (cuuint32_t)(p.tw + 2), (cuuint32_t)(p.th + 2), 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 2; ++i)
+        if (enc(&p.tmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.t1[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    return true;
+}
+
 template <int C, int CB, int NCW, int NBUF>
 static bool plan_tile(const vq3d_preact_desc *d, TcsPlan &best) {
     using Cfg = TcsCfg<C, CB>;
@@ -729,6 +790,8 @@ static int launch_tcs(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws
     unsigned char *wimg = reinterpret_cast<unsigned char *>(p.t1[1] + t1_units<C, CB>(d));
     p.wimg = wimg;
     p.y = blocks[n - 1].y;
+    p.use_tma = make_t1_tmaps(p, Cfg::NCH) ? 1 : 0;
+    if (getenv("VQ3D_TC_DEBUG")) fprintf(stderr, "preact_stack_tc<%d,%d>: tensor-map TMA box loads %s\n", C, CB, p.use_tma ? "on" : "off (row copies)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     e = zero_c8_planes<C, CB>(p.t1[0], d, st);
     if (e == cudaSuccess) e = zero_c8_planes<C, CB>(p.t1[1], d, st);
@@ -998,6 +1061,7 @@ static int launch_up_tc(const vq3d_preact_desc *d, void *ws, size_t ws_size, voi
     p.trace = nullptr;
     p.t1[0] = t1_hi; p.t1[1] = t1_hi;
     p.wimg = wimg;
+    p.use_tma = make_t1_tmaps(p, Cfg::NCH) ? 1 : 0;
     p.x = d->y; p.y = d->y;
     TcsBlock &t = p.blk[0];
     t.w1 = nullptr; t.w2 = d->w2; t.w3 = d->w3;
