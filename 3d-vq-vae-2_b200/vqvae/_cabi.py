@@ -69,6 +69,8 @@ SIGNATURES = {
     "vq3d_preact_stack_thin_tc": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, _fp]),
     "vq3d_preact_stack_tc_workspace": (C.c_size_t, [C.POINTER(PreactDesc)]),
     "vq3d_preact_stack_tc": (C.c_int, [C.POINTER(PreactDesc), C.c_int, _fp, C.c_size_t, _fp]),
+    "vq3d_preact_same_backward_workspace": (C.c_size_t, [C.POINTER(PreactDesc)]),
+    "vq3d_preact_same_backward": (C.c_int, [C.POINTER(PreactDesc), _fp, _fp, C.c_size_t, _fp, _fp, _fp, _fp, _fp, _fp]),
     "vq3d_preact_up_tc_workspace": (C.c_size_t, [C.POINTER(PreactDesc)]),
     "vq3d_preact_up_tc": (C.c_int, [C.POINTER(PreactDesc), _fp, C.c_size_t, _fp]),
     "vq3d_evonorm_s0_stats": (C.c_int, [_fp, C.c_int, C.c_int64, C.c_int, C.c_double, _fp, _fp, _fp]),

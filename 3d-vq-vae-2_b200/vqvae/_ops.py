@@ -32,6 +32,10 @@ class Ops:
         # (0.72 vs 0.52 ms per 4->2->4 block and volume: the im2col copy saturates the shared-memory pipe), so off by default
         self.thin_tc = os.environ.get("VQ3D_THIN_TC", "0") == "1"
         self.up_tc = os.environ.get("VQ3D_UP_TC", "1") == "1"      # wide 'up' blocks on the tensor-core kernel (bf16 mode)
+        # 'same' blocks: fused forward that keeps only x + fused 3-launch backward (vq3d_preact_same_backward).  Exact and 2.4x fewer
+        # kernels per step, but MEASURED SLOWER than the composed path inside a CUDA graph (C2 265 vs 152 ms, C3 413 vs 217 ms: the
+        # two tiled kernels run at 8-16 warps per SM with long per-thread chains), so it is off by default
+        self.fused_block_bwd = os.environ.get("VQ3D_FUSED_BLOCK_BWD", "0") == "1"
         self.fused_pointwise_bwd = os.environ.get("VQ3D_FUSED_PW_BWD", "1") == "1"   # k1 convolutions: one fused backward launch
         self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
@@ -360,6 +364,30 @@ class Ops:
         ok = self._call("preact_block", self.lib.vq3d_preact_block, (C.byref(d), self.stream()), allow_unsupported=True, **meta)
         return y if ok else None
 
+    def preact_same_backward_workspace(self, x: Tensor, blk) -> int:
+        """> 0 when the fused backward covers this 'same' block (no skip convolution, C <= 32, Cb <= 16)."""
+        if not self.fused_block_bwd or blk.skip_conv is not None or blk.branch_conv2.weight.shape[2] != 3:
+            return 0
+        d = self.preact_desc(x, None, blk, 0)
+        return int(self.lib.vq3d_preact_same_backward_workspace(C.byref(d)))
+
+    def preact_same_backward(self, x: Tensor, blk, gy: Tensor, want_x: bool):
+        """Every gradient of a 'same' block from its input x and gy (vq3d_preact_same_backward: 3 launches).
+        -> gx | None, gw1, gw2, gw3, gscal[8] (d bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias4, scale)."""
+        x, gy = self._t(x.detach()), self._t(gy.detach())
+        d = self.preact_desc(x, None, blk, 0)
+        need = int(self.lib.vq3d_preact_same_backward_workspace(C.byref(d)))
+        ws = self._workspace(need, x.device)
+        gx = torch.empty_like(x) if want_x else None
+        w1, w2, w3 = blk.branch_conv1.weight, blk.branch_conv2.weight, blk.branch_conv3.weight
+        gw1, gw2, gw3 = torch.zeros_like(w1), torch.zeros_like(w2), torch.zeros_like(w3)
+        gscal = torch.zeros(8, dtype=torch.float32, device=x.device)
+        B, Cc, H, W, Z = x.shape
+        self._call("preact_same_backward", self.lib.vq3d_preact_same_backward,
+                   (C.byref(d), self._p(gy), self._p(ws), ws.numel(), self._p(gx), self._p(gw1), self._p(gw2), self._p(gw3), self._p(gscal),
+                    self.stream()), kernels=3, tag=f"same {Cc}->{w1.shape[0]}->{Cc} @{H}x{W}x{Z}", nbytes=16 * x.numel())
+        return gx, gw1, gw2, gw3, gscal
+
     # (Cout, Cb) pairs whose 'up' blocks run on the tensor-core kernel in bf16 mode (vq3d_preact_up_tc)
     TC_UP_SHAPES = {(8, 9), (16, 16), (8, 8), (32, 36)}
 
@@ -594,6 +622,32 @@ class _ConvFn(torch.autograd.Function):
         pick = lambda flag, i: gs[i:i + 1].clone() if flag else None
         return (None, None, gx1, gx2, gw, gbias, pick(need["pre_a"], 0), pick(need["pre_b"], 1), pick(need["post_scale"], 2),
                 pick(need["post_b"], 3), gy if (ctx.has_res and n[10]) else None)
+
+
+class _PreactSameFn(torch.autograd.Function):
+    """Autograd edge of a whole 'same' PreActFixupResBlock (layers.py:176-195): one fused forward launch that saves only the
+    block input, and the fused 3-launch backward (vq3d_preact_same_backward).  Parameter order = _PARAMS below."""
+
+    _PARAMS = ("branch_conv1.weight", "branch_conv2.weight", "branch_conv3.weight", "bias1a", "bias1b", "bias2a", "bias2b",
+               "bias3a", "bias3b", "bias4", "scale")
+
+    @staticmethod
+    def forward(ctx, ops, blk, x, *params):
+        y = ops.preact_block(x.detach(), blk, 0)
+        if y is None:                                   # no fused forward kernel for the shape: the composed kernels (still no graph)
+            y = blk.forward_composed(x.detach())
+        ctx.ops, ctx.blk = ops, blk
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gx, gw1, gw2, gw3, gs = ctx.ops.preact_same_backward(x, ctx.blk, gy.contiguous(), ctx.needs_input_grad[2])
+        scal = [gs[i:i + 1].clone() for i in range(8)]
+        grads = [gw1, gw2, gw3] + scal
+        need = ctx.needs_input_grad[3:]
+        return (None, None, gx) + tuple(g if n else None for g, n in zip(grads, need))
 
 
 class _EvoNormFn(torch.autograd.Function):

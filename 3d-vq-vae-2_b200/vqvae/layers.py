@@ -99,6 +99,11 @@ class PreActFixupResBlock(nn.Module):
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         if _recording(input, *self._params()):
+            o = ops()
+            if self.mode in ("same", "out") and self.skip_conv is None and o.preact_same_backward_workspace(input, self) > 0:
+                # 'same' block: ONE fused forward launch that keeps only the input + the fused 3-launch backward
+                names = _ops._PreactSameFn._PARAMS
+                return _ops._PreactSameFn.apply(o, self, input, *(self.get_parameter(n) for n in names))
             return self.forward_composed(input)          # training: differentiable generic ops
         o = ops()
         # wide down blocks: the fused SIMT kernel keeps all branch channels of the (2t+2)^3 input window in

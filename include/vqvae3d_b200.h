@@ -280,6 +280,20 @@ size_t vq3d_preact_stack_tc_workspace(const vq3d_preact_desc *first_block);
 int vq3d_preact_stack_tc(const vq3d_preact_desc *blocks, int n, void *ws, size_t ws_bytes, void *stream);
 
 /*
+ * Fused backward of a 'same' PreActFixupResBlock without skip convolution (autograd of layers.py:176-195 for the blocks of
+ * the 50 / 150-deep stacks): the training forward keeps only the block input x; two tiled kernels recompute the intermediates
+ * (a2 on a 1-voxel halo, c2, the activations) and produce every gradient, exchanging gt3 and c1 through `ws`; d W2 comes from
+ * the tiled weight-gradient kernel of vq3d_conv3d_backward.  desc: the forward descriptor (mode 0, wskip NULL, Cin == Cout
+ * <= 32, Cb <= 16; y / out_* / pre_* unused).  gy [B, C, S]; gx [B, C, S] written (may be NULL); gw1 [Cb, C], gw2 [Cb, Cb, 27],
+ * gw3 [C, Cb] and gscalars[8] = d bias1a, bias1b, bias2a, bias2b, bias3a, bias3b, bias4, scale are ACCUMULATED (caller zeroes;
+ * any may be NULL).  ws: vq3d_preact_same_backward_workspace(desc) bytes (0 = shape not covered: compose the block from the
+ * generic entry points).  fp32 throughout.
+ */
+size_t vq3d_preact_same_backward_workspace(const vq3d_preact_desc *desc);
+int vq3d_preact_same_backward(const vq3d_preact_desc *desc, const float *gy, void *ws, size_t ws_bytes, float *gx, float *gw1, float *gw2,
+                              float *gw3, float *gscalars, void *stream);
+
+/*
  * One 'up' PreActFixupResBlock (mode 2: trilinear x2 + k3 circular convolution, skip = ResizeConv3D k1; layers.py:124-132,
  * 176-195,591-597) with the k3 convolution on the tensor cores.  Same descriptor as vq3d_preact_block (mode must be 2).
  * The pointwise low-resolution stage (conv1 and the 1x1 skip convolution, which commutes with the interpolation) and the

@@ -145,3 +145,38 @@ def test_evonorm_block_gradients_vs_oracle_autograd(cin, cout, mode, shape):
             else:
                 p.copy_(torch.randn(p.shape) * 0.3)
     _grads_vs_oracle(blk, O.evonorm_block, mode, torch.randn(shape), 9, tol=2e-3)
+
+
+@pytest.mark.parametrize("C,shape", [(4, (1, 4, 5, 6, 7)), (18, (2, 18, 4, 5, 3)), (2, (1, 2, 8, 8, 2))])
+def test_fused_same_block_backward_on_the_emulator(C, shape):
+    """vq3d_preact_same_backward (fused forward keeping only x + two tiled recompute kernels + tiled d W2; off by default) against
+    autograd on the oracle: partial tiles, batch 2, wrap on a size-2 axis."""
+    from vqvae import _ops
+    torch.manual_seed(C)
+    blk = L.PreActFixupResBlock(C, C, "same")
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        blk.scale.fill_(0.9)
+    x = torch.randn(shape)
+    sd = {"b." + k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    yr = O.preact_block(sd, "b.", xr, "same")
+    r = torch.randn(yr.shape, generator=torch.Generator().manual_seed(3))
+    (yr * r).sum().backward()
+    with use_emulator():
+        o = _ops.default()
+        prev, o.fused_block_bwd = o.fused_block_bwd, True
+        try:
+            l0 = o.launches
+            xg = x.clone().requires_grad_(True)
+            y = blk(xg)
+            (y * r).sum().backward()
+            assert o.launches - l0 == 4                      # 1 forward + 3 backward launches
+        finally:
+            o.fused_block_bwd = prev
+    assert torch.allclose(y.detach(), yr.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(xg.grad, xr.grad, rtol=2e-4, atol=2e-5)
+    for k, p in blk.named_parameters():
+        ref = sd["b." + k].grad
+        assert torch.allclose(p.grad, ref, rtol=1e-3, atol=1e-4), (k, float((p.grad - ref).abs().max()))

@@ -446,3 +446,42 @@ def test_optimizer_state_dict_resume_matches_uninterrupted_run(tmp_path):
     run(c, c_p, range(3, 5))
     for pc, pr in zip(c_p, ref_p):
         assert torch.allclose(pc.detach().cpu(), pr.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("C,shape", [(4, (1, 4, 12, 10, 16)), (18, (2, 18, 6, 5, 7)), (2, (1, 2, 8, 8, 2)), (8, (1, 8, 20, 9, 33)), (32, (1, 32, 6, 6, 4))])
+def test_fused_same_block_backward_vs_oracle_autograd(C, shape):
+    """vq3d_preact_same_backward (one fused forward that keeps only x + two tiled backward kernels + the tiled d W2): every
+    gradient of a 'same' block against autograd on the oracle.  (The path is off by default -- slower than the composed one inside
+    a CUDA graph, DESIGN.md 8 -- and enabled here.)"""
+    from vqvae import layers as L, _ops
+    o = _ops.default()
+    torch.manual_seed(C)
+    blk = L.PreActFixupResBlock(C, C, "same")
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.2))
+        blk.scale.fill_(0.9)
+    x = torch.randn(shape)
+    sd = {"b." + k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    yr = O.preact_block(sd, "b.", xr, "same")
+    r = torch.randn(yr.shape, generator=torch.Generator().manual_seed(3))
+    (yr * r).sum().backward()
+    blk = blk.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    prev, o.fused_block_bwd = o.fused_block_bwd, True
+    o.profile = []
+    try:
+        y = blk(xg)
+        (y * r.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+        names = [e[0] for e in o.profile]
+    finally:
+        o.fused_block_bwd = prev
+        o.profile = None
+    assert names == ["preact_block", "preact_same_backward"], names
+    assert torch.allclose(y.detach().cpu(), yr.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(xg.grad.cpu(), xr.grad, rtol=2e-4, atol=2e-5), float((xg.grad.cpu() - xr.grad).abs().max())
+    for k, p in blk.named_parameters():
+        ref = sd["b." + k].grad
+        assert torch.allclose(p.grad.cpu(), ref, rtol=1e-3, atol=1e-4), (k, float((p.grad.cpu() - ref).abs().max()), float(ref.abs().max()))
