@@ -481,6 +481,7 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
             const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
             const uint32_t d3_addr = tmem_grp + (uint32_t)(g * (CP + CBP)), d1_addr = d3_addr + CP;
             const int last_mb = p.NMB > g ? g + ((p.NMB - 1 - g) / NG) * NG : -1;
+            const float inv_iz = 1.0f / (float)IZ, inv_iw = 1.0f / (float)IW;
             mbarrier_wait(&bar_w, (uint32_t)blk & 1u);          // the group leaders issue MMAs that read W3 / W1
             for (int i = 0; i < my_tiles; ++i) {
                 const uint32_t k = kt + (uint32_t)i, s = k % NBUF, u = k / NBUF;
@@ -490,8 +491,10 @@ preact_tc_kernel(const __grid_constant__ TcsParams p) {
                 const int b = t, oh0 = thi * p.th, ow0 = twi * p.tw;
                 for (int mb = g; mb < p.NMB; mb += NG) {
                     const int L = p.L0 + mb * 128 + row;
-                    const int lz = L % IZ, r = L / IZ;
-                    const int lw = r % IW, lh = r / IW;
+                    // box index -> (lh, lw, lz) by reciprocal multiplication (exact: L < 2^15, divisors <= 258; the runtime-divisor
+                    // integer divisions were 7 % of the consumers' samples)
+                    const int r = (int)(((float)L + 0.5f) * inv_iz), lz = L - r * IZ;
+                    const int lh = (int)(((float)r + 0.5f) * inv_iw), lw = r - lh * IW;
                     const int oh = oh0 + lh - 1, ow = ow0 + lw - 1, oz = lz - 1;
                     const bool valid = lh >= 1 && lh <= p.th && lw >= 1 && lw <= p.tw && lz >= 1 && lz <= Z && oh < H && ow < W;
                     const size_t off = valid ? (size_t)b * C * S + ((size_t)oh * W + ow) * Z + oz : 0;
@@ -877,10 +880,16 @@ up_lo_kernel(const float *__restrict__ x, const float *__restrict__ w1, const fl
     for (int64_t v = (int64_t)blockIdx.x * T + tid; v < total; v += (int64_t)gridDim.x * T) {
         const int64_t b = v / S, r = v - b * S;
         const float *px = x + (size_t)b * Cin * S + r;
-        for (int ci = 0; ci < Cin; ++ci) {
-            const float xv = __ldcs(px + (size_t)ci * S);
-            sx[ci * T + tid] = elu1(xv + b1a) + b1b;
-            sr[ci * T + tid] = xv + b1c;
+        for (int c0 = 0; c0 < Cin; c0 += 6) {             // six independent loads in flight per pass
+            float xv[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) xv[j] = c0 + j < Cin ? __ldcs(px + (size_t)(c0 + j) * S) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (c0 + j < Cin) {
+                    sx[(c0 + j) * T + tid] = elu1(xv[j] + b1a) + b1b;
+                    sr[(c0 + j) * T + tid] = xv[j] + b1c;
+                }
         }
         float *pt = t1_lo + (size_t)b * Cb * S + r;
         for (int c0 = 0; c0 < Cb; c0 += 4) {
@@ -942,24 +951,25 @@ up_expand_kernel(const float *__restrict__ t1_lo, const float *__restrict__ s_lo
         if (h2 & 1) { h0 = h2 >> 1; h1 = min(h0 + 1, H - 1); fh0 = 0.75f; fh1 = 0.25f; } else { h1 = h2 >> 1; h0 = max(h1 - 1, 0); fh0 = 0.25f; fh1 = 0.75f; }
         if (w2 & 1) { w0 = w2 >> 1; w1 = min(w0 + 1, W - 1); fw0 = 0.75f; fw1 = 0.25f; } else { w1 = w2 >> 1; w0 = max(w1 - 1, 0); fw0 = 0.25f; fw1 = 0.75f; }
         const int zm = max(zl - 1, 0), zp = min(zl + 1, Z - 1);
-        // 32-bit element offsets inside one channel volume (H * W * Z < 2^31 is checked by the host): one IMAD.WIDE per load
+        // twelve source pointers (4 (h, w) corners x 3 depth taps), advanced by one channel volume per channel: two integer
+        // instructions per load instead of the six a recomputed 64-bit address costs
         const int o00 = (h0 * W + w0) * Z, o01 = (h0 * W + w1) * Z, o10 = (h1 * W + w0) * Z, o11 = (h1 * W + w1) * Z;
-        const int i00m = o00 + zm, i01m = o01 + zm, i10m = o10 + zm, i11m = o11 + zm;
-        const int i00c = o00 + zl, i01c = o01 + zl, i10c = o10 + zl, i11c = o11 + zl;
-        const int i00p = o00 + zp, i01p = o01 + zp, i10p = o10 + zp, i11p = o11 + zp;
         const float f00 = fh0 * fw0, f01 = fh0 * fw1, f10 = fh1 * fw0, f11 = fh1 * fw1;
         float e[8], o[8];                               // even / odd output depth
         const float *pc = src + ((size_t)b * Cs + c0) * S;
+        const float *q00m = pc + o00 + zm, *q01m = pc + o01 + zm, *q10m = pc + o10 + zm, *q11m = pc + o11 + zm;
+        const float *q00c = pc + o00 + zl, *q01c = pc + o01 + zl, *q10c = pc + o10 + zl, *q11c = pc + o11 + zl;
+        const float *q00p = pc + o00 + zp, *q01p = pc + o01 + zp, *q10p = pc + o10 + zp, *q11p = pc + o11 + zp;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             e[j] = 0.0f; o[j] = 0.0f;
             if (j < nc) {
-                const float vm = f00 * __ldg(pc + i00m) + f01 * __ldg(pc + i01m) + f10 * __ldg(pc + i10m) + f11 * __ldg(pc + i11m);
-                const float vc = f00 * __ldg(pc + i00c) + f01 * __ldg(pc + i01c) + f10 * __ldg(pc + i10c) + f11 * __ldg(pc + i11c);
-                const float vp = f00 * __ldg(pc + i00p) + f01 * __ldg(pc + i01p) + f10 * __ldg(pc + i10p) + f11 * __ldg(pc + i11p);
+                const float vm = f00 * __ldg(q00m) + f01 * __ldg(q01m) + f10 * __ldg(q10m) + f11 * __ldg(q11m);
+                const float vc = f00 * __ldg(q00c) + f01 * __ldg(q01c) + f10 * __ldg(q10c) + f11 * __ldg(q11c);
+                const float vp = f00 * __ldg(q00p) + f01 * __ldg(q01p) + f10 * __ldg(q10p) + f11 * __ldg(q11p);
                 e[j] = 0.25f * vm + 0.75f * vc;
                 o[j] = 0.75f * vc + 0.25f * vp;
-                pc += S;
+                q00m += S; q01m += S; q10m += S; q11m += S; q00c += S; q01c += S; q10c += S; q11c += S; q00p += S; q01p += S; q10p += S; q11p += S;
             }
         }
         if (is_t1 && k9 && job == 1) {                 // C_b = 9: the ninth channel and its depth neighbours (TcsCfg::K9)
