@@ -6,7 +6,7 @@ synthetic 512x512x128 volumes (BASELINE.json metric), one process per GPU.
     python bench.py --impl reference ...                     (the oracle on the host cores)
 
 A "step" = one forward pass (Encoder2 -> 3 quantizers -> Decoder, model.py:79-83) over one batch of
---batch independent volumes per GPU (default 8, stacked along B); volumes are independent, so ranks
+--batch independent volumes per GPU (default 16, stacked along B); volumes are independent, so ranks
 shard them with no data-path collective (weak scaling).  Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -627,7 +627,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="full_512x512x128", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=8, help="independent volumes per step and GPU (stacked along B)")
+    ap.add_argument("--batch", type=int, default=16, help="independent volumes per step and GPU (stacked along B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step points (configs[1], configs[2])")
     ap.add_argument("--profile-out", default=None, help="write the per-op CUDA-event table of one eager step here")

@@ -28,6 +28,6 @@ if os.path.exists(out):
     except Exception:
         table = {}
 table[tag] = {"dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_written": wr, "kernel_launches_per_op": per_op, "ncu_ms_per_op": ms,
-              "source": f"{os.path.basename(rep)} (ncu --set full --clock-control none on bench.py itself, batch 8): sum over the {per_op} kernel launches of one call of the op"}
+              "source": f"{os.path.basename(rep)} (ncu --set full --clock-control none on bench.py itself at its default batch): sum over the {per_op} kernel launches of one call of the op"}
 json.dump(table, open(out, "w"), indent=1)
 print(json.dumps(table[tag], indent=1))
