@@ -98,6 +98,34 @@ def test_cabi_library_loads_and_exports_every_symbol():
     assert b"null descriptor" in lib.vq3d_last_error()
 
 
+def test_cabi_argument_validation_of_the_round2_entry_points():
+    """Error behaviour of the new entry points (no GPU needed: validation runs before any CUDA call): null pointers, wrong
+    block mode, geometry the fused kernels do not cover -> VQ3D_ERR_INVALID / VQ3D_ERR_UNSUPPORTED with a message, never a crash."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vq3d_build", os.path.join(ROOT, "3d-vq-vae-2_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    lib = _cabi.declare(ctypes.CDLL(b.build()))
+    C = ctypes
+    assert lib.vq3d_preact_up_tc(None, None, 0, None) == _cabi.ERR_INVALID
+    d = _cabi.PreactDesc(B=1, H=4, W=4, Z=4, Cin=18, Cb=9, Cout=8, mode=0)
+    assert lib.vq3d_preact_up_tc(C.byref(d), None, 0, None) == _cabi.ERR_INVALID and b"mode must be 2" in lib.vq3d_last_error()
+    assert lib.vq3d_preact_up_tc_workspace(C.byref(d)) == 0                       # not an 'up' block with a skip convolution
+    d.mode = 2
+    assert lib.vq3d_preact_up_tc(C.byref(d), None, 0, None) == _cabi.ERR_INVALID and b"null tensor" in lib.vq3d_last_error()
+    assert lib.vq3d_conv1x1_backward(None, None, None) == _cabi.ERR_INVALID
+    cd = _cabi.ConvDesc(B=1, H=4, W=4, Z=4, C1=4, C2=0, Cout=4, k=3, stride=1, pad=1, x1=1, w=1)
+    g = _cabi.ConvBwd(gy=1)
+    assert lib.vq3d_conv1x1_backward(C.byref(cd), C.byref(g), None) == _cabi.ERR_INVALID and b"pointwise" in lib.vq3d_last_error()
+    s = _cabi.PreactDesc(B=1, H=4, W=4, Z=4, Cin=64, Cb=32, Cout=64, mode=0)
+    assert lib.vq3d_preact_same_backward_workspace(C.byref(s)) == 0               # C > 32 / Cb > 16: composed path
+    s = _cabi.PreactDesc(B=1, H=4, W=4, Z=4, Cin=18, Cb=9, Cout=18, mode=0)
+    assert lib.vq3d_preact_same_backward_workspace(C.byref(s)) == 2 * 9 * 64 * 4
+    assert lib.vq3d_preact_same_backward(C.byref(s), None, None, 0, None, None, None, None, None, None) == _cabi.ERR_INVALID
+    assert lib.vq3d_hu_to_network(None, 4, -1500.0, 3000.0, 0.001, 1.0, None, None) == _cabi.ERR_INVALID
+    assert lib.vq3d_elu_hu_rint_i16(None, 4, 1000.0, 1000.0, None, None) == _cabi.ERR_INVALID
+    assert lib.vq3d_huber_elu_mask_stats(None, None, None, None, 1, 2, 2, 2, None, None, None) == _cabi.ERR_INVALID
+
+
 def test_no_cpu_fallback():
     """The product path refuses CPU tensors instead of silently computing somewhere else."""
     q = L.Quantizer(8, 2, 0.1).eval()
