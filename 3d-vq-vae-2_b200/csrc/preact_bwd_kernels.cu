@@ -72,13 +72,21 @@ __device__ __forceinline__ void pb_tile(const PbParams &p, int &b, int &h0, int 
 __device__ __forceinline__ void pb_pairs(const float *sRow, int nrow, const float *sCol, int ncol, int T, int ld, float mul, float *out) {
     for (int pr = threadIdx.x; pr < nrow * ncol; pr += kPbThreads) {
         const float *a = sRow + (pr / ncol) * ld, *c = sCol + (pr % ncol) * ld;
-        float s = 0.0f;
-        for (int tv = 0; tv < T; ++tv) s = __fmaf_rn(a[tv], c[tv], s);
-        atomicAdd(out + pr, s * mul);
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;      // four independent chains
+        int tv = 0;
+        for (; tv + 3 < T; tv += 4) {
+            s0 = __fmaf_rn(a[tv], c[tv], s0); s1 = __fmaf_rn(a[tv + 1], c[tv + 1], s1);
+            s2 = __fmaf_rn(a[tv + 2], c[tv + 2], s2); s3 = __fmaf_rn(a[tv + 3], c[tv + 3], s3);
+        }
+        for (; tv < T; ++tv) s0 = __fmaf_rn(a[tv], c[tv], s0);
+        atomicAdd(out + pr, ((s0 + s1) + (s2 + s3)) * mul);
     }
 }
 
-__global__ void __launch_bounds__(kPbThreads)
+// NZ: depth neighbours per thread in the convolution loops (2 when the tile depth is even: the window values and every weight
+// vector are loaded once for both voxels -- 13 shared loads per 54 FMAs at C_b = 9 instead of 13 per 27)
+template <int NZ>
+__global__ void __launch_bounds__(kPbThreads, 2)
 preact_same_bwd_a_kernel(PbParams p) {
     VQ3D_DYN_SMEM(float, sm);
     __shared__ float red[32];
@@ -131,60 +139,77 @@ preact_same_bwd_a_kernel(PbParams p) {
     __syncthreads();
     // ---- the tile's voxels: c2 -> a3, ELU'(t3); c3, ga3, gt3 ----
     float s_scale = 0.0f, s_b4 = 0.0f, s_b3b = 0.0f, s_b3a = 0.0f;
-    for (int tv = tid; tv < T; tv += kPbThreads) {
-        const int dz = tv % p.TZ, dw = (tv / p.TZ) % p.TW, dh = tv / (p.TZ * p.TW);
-        const int oh = h0 + dh, ow = w0 + dw, oz = z0 + dz;
-        const bool active = oh < p.H && ow < p.W && oz < p.Z;
-        float c2[kPbMaxCb];
+    for (int tq = tid; tq * NZ < T; tq += kPbThreads) {
+        const int tv0 = tq * NZ;
+        const int dz = tv0 % p.TZ, dw = (tv0 / p.TZ) % p.TW, dh = tv0 / (p.TZ * p.TW);
+        const int oh = h0 + dh, ow = w0 + dw;
+        float c2[NZ][kPbMaxCb];
 #pragma unroll
-        for (int j = 0; j < kPbMaxCb; ++j) c2[j] = 0.0f;
-        if (active) {
+        for (int v = 0; v < NZ; ++v)
+#pragma unroll
+            for (int j = 0; j < kPbMaxCb; ++j) c2[v][j] = 0.0f;
+        if (oh < p.H && ow < p.W && z0 + dz < p.Z) {
             for (int ci = 0; ci < Cb; ++ci) {
-                const float *a = sA2 + ci * R1 + (dh * IW + dw) * IZ + dz;       // window origin = tap (0,0,0)
+                const float *a = sA2 + ci * R1 + (dh * IW + dw) * IZ + dz;       // window origin = tap (0,0,0) of voxel 0
 #pragma unroll
-                for (int tap = 0; tap < 27; ++tap) {
-                    const float av = a[((tap / 9) * IW + (tap / 3) % 3) * IZ + tap % 3];
-                    const float *wr = sW2 + (ci * 27 + tap) * Cb4;
+                for (int hw = 0; hw < 9; ++hw) {
+                    const float *ar = a + ((hw / 3) * IW + hw % 3) * IZ;
+                    float av[NZ + 2];
 #pragma unroll
-                    for (int j = 0; j < kPbMaxCb; ++j)
-                        if (j < Cb) c2[j] = __fmaf_rn(wr[j], av, c2[j]);
+                    for (int t = 0; t < NZ + 2; ++t) av[t] = ar[t];
+#pragma unroll
+                    for (int kz = 0; kz < 3; ++kz) {
+                        const float *wr = sW2 + (ci * 27 + hw * 3 + kz) * Cb4;
+#pragma unroll
+                        for (int j = 0; j < kPbMaxCb; ++j)
+                            if (j < Cb) {
+                                const float wv = wr[j];
+#pragma unroll
+                                for (int v = 0; v < NZ; ++v) c2[v][j] = __fmaf_rn(wv, av[v + kz], c2[v][j]);
+                            }
+                    }
                 }
             }
         }
-        float a3[kPbMaxCb], d3[kPbMaxCb], ga3[kPbMaxCb];
 #pragma unroll
-        for (int j = 0; j < kPbMaxCb; ++j) {
-            const float t3 = c2[j] + b3a;
-            const float e = __expf(t3);
-            a3[j] = (active && j < Cb) ? (t3 > 0.0f ? t3 : e - 1.0f) + b3b : 0.0f;
-            d3[j] = t3 > 0.0f ? 1.0f : e;
-            ga3[j] = 0.0f;
-            if (j < Cb) sA3[j * LD + tv] = a3[j];
-        }
-        const size_t off = active ? ((size_t)oh * p.W + ow) * p.Z + oz : 0;
-        for (int c = 0; c < C; ++c) {
-            const float g = active ? __ldg(p.gy + ((size_t)b * C + c) * S + off) : 0.0f;
-            float c3 = 0.0f;
+        for (int v = 0; v < NZ; ++v) {
+            const int tv = tv0 + v, oz = z0 + dz + v;
+            const bool active = oh < p.H && ow < p.W && oz < p.Z;
+            float a3[kPbMaxCb], ga3[kPbMaxCb];
 #pragma unroll
-            for (int j = 0; j < kPbMaxCb; ++j)
-                if (j < Cb) c3 = __fmaf_rn(sW3[c * Cb + j], a3[j], c3);
-            s_scale = __fmaf_rn(g, c3, s_scale);
-            s_b4 += g;
-            const float g3 = g * sc;
-            sG3[c * LD + tv] = g3;
+            for (int j = 0; j < kPbMaxCb; ++j) {
+                const float t3 = c2[v][j] + b3a;
+                const float e = __expf(t3);
+                a3[j] = (active && j < Cb) ? (t3 > 0.0f ? t3 : e - 1.0f) + b3b : 0.0f;
+                c2[v][j] = t3 > 0.0f ? 1.0f : e;           // from here on: ELU'(t3)
+                ga3[j] = 0.0f;
+                if (j < Cb) sA3[j * LD + tv] = a3[j];
+            }
+            const size_t off = active ? ((size_t)oh * p.W + ow) * p.Z + oz : 0;
+            for (int c = 0; c < C; ++c) {
+                const float g = active ? __ldg(p.gy + ((size_t)b * C + c) * S + off) : 0.0f;
+                float c3 = 0.0f;
 #pragma unroll
-            for (int j = 0; j < kPbMaxCb; ++j)
-                if (j < Cb) ga3[j] = __fmaf_rn(sW3[c * Cb + j], g3, ga3[j]);
-        }
-        if (active) {
+                for (int j = 0; j < kPbMaxCb; ++j)
+                    if (j < Cb) c3 = __fmaf_rn(sW3[c * Cb + j], a3[j], c3);
+                s_scale = __fmaf_rn(g, c3, s_scale);
+                s_b4 += g;
+                const float g3 = g * sc;
+                sG3[c * LD + tv] = g3;
 #pragma unroll
-            for (int j = 0; j < kPbMaxCb; ++j)
-                if (j < Cb) {
-                    const float gt3 = ga3[j] * d3[j];
-                    s_b3b += ga3[j];
-                    s_b3a += gt3;
-                    p.g3ws[((size_t)b * Cb + j) * S + off] = gt3;
-                }
+                for (int j = 0; j < kPbMaxCb; ++j)
+                    if (j < Cb) ga3[j] = __fmaf_rn(sW3[c * Cb + j], g3, ga3[j]);
+            }
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < kPbMaxCb; ++j)
+                    if (j < Cb) {
+                        const float gt3 = ga3[j] * c2[v][j];
+                        s_b3b += ga3[j];
+                        s_b3a += gt3;
+                        p.g3ws[((size_t)b * Cb + j) * S + off] = gt3;
+                    }
+            }
         }
     }
     __syncthreads();
@@ -197,7 +222,8 @@ preact_same_bwd_a_kernel(PbParams p) {
     }
 }
 
-__global__ void __launch_bounds__(kPbThreads)
+template <int NZ>
+__global__ void __launch_bounds__(kPbThreads, 2)
 preact_same_bwd_b_kernel(PbParams p) {
     VQ3D_DYN_SMEM(float, sm);
     __shared__ float red[32];
@@ -226,58 +252,75 @@ preact_same_bwd_b_kernel(PbParams p) {
     }
     __syncthreads();
     float s_b2b = 0.0f, s_b2a = 0.0f, s_b1b = 0.0f, s_b1a = 0.0f;
-    for (int tv = tid; tv < T; tv += kPbThreads) {
-        const int dz = tv % p.TZ, dw = (tv / p.TZ) % p.TW, dh = tv / (p.TZ * p.TW);
-        const int oh = h0 + dh, ow = w0 + dw, oz = z0 + dz;
-        const bool active = oh < p.H && ow < p.W && oz < p.Z;
-        const size_t off = active ? ((size_t)oh * p.W + ow) * p.Z + oz : 0;
-        float ga2[kPbMaxCb];
+    for (int tq = tid; tq * NZ < T; tq += kPbThreads) {
+        const int tv0 = tq * NZ;
+        const int dz = tv0 % p.TZ, dw = (tv0 / p.TZ) % p.TW, dh = tv0 / (p.TZ * p.TW);
+        const int oh = h0 + dh, ow = w0 + dw;
+        float ga2[NZ][kPbMaxCb];
 #pragma unroll
-        for (int j = 0; j < kPbMaxCb; ++j) ga2[j] = 0.0f;
-        if (active) {
+        for (int v = 0; v < NZ; ++v)
+#pragma unroll
+            for (int j = 0; j < kPbMaxCb; ++j) ga2[v][j] = 0.0f;
+        if (oh < p.H && ow < p.W && z0 + dz < p.Z) {
             for (int co = 0; co < Cb; ++co) {
                 // ga2(u) += W2[co][.][k] gt3[co](u - k + 1): box coordinate of u - k + 1 is (d + 1) - (k - 1) = d + 2 - k
                 const float *g = sG + co * R1 + ((dh + 2) * IW + (dw + 2)) * IZ + (dz + 2);
 #pragma unroll
-                for (int tap = 0; tap < 27; ++tap) {
-                    const float gv = g[-(((tap / 9) * IW + (tap / 3) % 3) * IZ + tap % 3)];
-                    const float *wr = sW2 + (co * 27 + tap) * Cb4;
+                for (int hw = 0; hw < 9; ++hw) {
+                    const float *gr = g - ((hw / 3) * IW + hw % 3) * IZ;
+                    float gv[NZ + 2];                      // gv[t] = gt3 at depth offset t - 2 (t = 0 .. NZ + 1)
+#pragma unroll
+                    for (int t = 0; t < NZ + 2; ++t) gv[t] = gr[t - 2];
+#pragma unroll
+                    for (int kz = 0; kz < 3; ++kz) {
+                        const float *wr = sW2 + (co * 27 + hw * 3 + kz) * Cb4;
+#pragma unroll
+                        for (int j = 0; j < kPbMaxCb; ++j)
+                            if (j < Cb) {
+                                const float wv = wr[j];
+#pragma unroll
+                                for (int v = 0; v < NZ; ++v) ga2[v][j] = __fmaf_rn(wv, gv[v + 2 - kz], ga2[v][j]);
+                            }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NZ; ++v) {
+            const int tv = tv0 + v, oz = z0 + dz + v;
+            const bool active = oh < p.H && ow < p.W && oz < p.Z;
+            const size_t off = active ? ((size_t)oh * p.W + ow) * p.Z + oz : 0;
+            float gt2[kPbMaxCb];
+#pragma unroll
+            for (int j = 0; j < kPbMaxCb; ++j) {
+                gt2[j] = 0.0f;
+                if (j < Cb) {
+                    if (active) {
+                        const float t2 = __ldg(p.c1ws + ((size_t)b * Cb + j) * S + off) + b2a;
+                        gt2[j] = ga2[v][j] * (t2 > 0.0f ? 1.0f : __expf(t2));
+                        s_b2b += ga2[v][j];
+                        s_b2a += gt2[j];
+                    }
+                    sG1[j * LD + tv] = gt2[j];
+                }
+            }
+            for (int c = 0; c < C; ++c) {
+                float a1 = 0.0f;
+                if (active) {
+                    const float t1 = __ldg(p.x + ((size_t)b * C + c) * S + off) + b1a;
+                    const float e = __expf(t1);
+                    a1 = (t1 > 0.0f ? t1 : e - 1.0f) + b1b;
+                    float ga1 = 0.0f;
 #pragma unroll
                     for (int j = 0; j < kPbMaxCb; ++j)
-                        if (j < Cb) ga2[j] = __fmaf_rn(wr[j], gv, ga2[j]);
+                        if (j < Cb) ga1 = __fmaf_rn(sW1[j * C + c], gt2[j], ga1);
+                    const float gt1 = ga1 * (t1 > 0.0f ? 1.0f : e);
+                    s_b1b += ga1;
+                    s_b1a += gt1;
+                    if (p.gx) p.gx[((size_t)b * C + c) * S + off] = gt1 + __ldg(p.gy + ((size_t)b * C + c) * S + off);
                 }
+                sA1[c * LD + tv] = a1;
             }
-        }
-        float gt2[kPbMaxCb];
-#pragma unroll
-        for (int j = 0; j < kPbMaxCb; ++j) {
-            gt2[j] = 0.0f;
-            if (j < Cb) {
-                if (active) {
-                    const float t2 = __ldg(p.c1ws + ((size_t)b * Cb + j) * S + off) + b2a;
-                    gt2[j] = ga2[j] * (t2 > 0.0f ? 1.0f : __expf(t2));
-                    s_b2b += ga2[j];
-                    s_b2a += gt2[j];
-                }
-                sG1[j * LD + tv] = gt2[j];
-            }
-        }
-        for (int c = 0; c < C; ++c) {
-            float a1 = 0.0f;
-            if (active) {
-                const float t1 = __ldg(p.x + ((size_t)b * C + c) * S + off) + b1a;
-                const float e = __expf(t1);
-                a1 = (t1 > 0.0f ? t1 : e - 1.0f) + b1b;
-                float ga1 = 0.0f;
-#pragma unroll
-                for (int j = 0; j < kPbMaxCb; ++j)
-                    if (j < Cb) ga1 = __fmaf_rn(sW1[j * C + c], gt2[j], ga1);
-                const float gt1 = ga1 * (t1 > 0.0f ? 1.0f : e);
-                s_b1b += ga1;
-                s_b1a += gt1;
-                if (p.gx) p.gx[((size_t)b * C + c) * S + off] = gt1 + __ldg(p.gy + ((size_t)b * C + c) * S + off);
-            }
-            sA1[c * LD + tv] = a1;
         }
     }
     __syncthreads();
@@ -342,9 +385,12 @@ extern "C" int vq3d_preact_same_backward(const vq3d_preact_desc *d, const float 
     p.g3ws = p.c1ws + (size_t)d->B * d->Cb * S;
     p.gx = gx; p.gw1 = gw1; p.gw3 = gw3; p.gscal = gscalars;
     const dim3 grid((unsigned)((int64_t)d->B * p.nth * p.ntw * p.ntz));
-    int rc = launch("preact_same_bwd_a", preact_same_bwd_a_kernel, grid, dim3(kPbThreads), sa, stream, p);
+    const bool pairz = p.TZ % 2 == 0;        // even tile depth: two depth neighbours per thread
+    int rc = pairz ? launch("preact_same_bwd_a", preact_same_bwd_a_kernel<2>, grid, dim3(kPbThreads), sa, stream, p)
+                   : launch("preact_same_bwd_a", preact_same_bwd_a_kernel<1>, grid, dim3(kPbThreads), sa, stream, p);
     if (rc) return rc;
-    rc = launch("preact_same_bwd_b", preact_same_bwd_b_kernel, grid, dim3(kPbThreads), sb, stream, p);
+    rc = pairz ? launch("preact_same_bwd_b", preact_same_bwd_b_kernel<2>, grid, dim3(kPbThreads), sb, stream, p)
+               : launch("preact_same_bwd_b", preact_same_bwd_b_kernel<1>, grid, dim3(kPbThreads), sb, stream, p);
     if (rc) return rc;
     if (gw2) {      // d W2: the tiled weight-gradient kernel on (c1 with its pre-activation, gt3)
         vq3d_conv_desc cd;

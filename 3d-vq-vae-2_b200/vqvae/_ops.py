@@ -33,9 +33,10 @@ class Ops:
         self.thin_tc = os.environ.get("VQ3D_THIN_TC", "0") == "1"
         self.up_tc = os.environ.get("VQ3D_UP_TC", "1") == "1"      # wide 'up' blocks on the tensor-core kernel (bf16 mode)
         # 'same' blocks: fused forward that keeps only x + fused 3-launch backward (vq3d_preact_same_backward).  Exact and 2.4x fewer
-        # kernels per step, but MEASURED SLOWER than the composed path inside a CUDA graph (C2 265 vs 152 ms, C3 413 vs 217 ms: the
-        # two tiled kernels run at 8-16 warps per SM with long per-thread chains), so it is off by default
+        # kernels per step, but MEASURED SLOWER than the composed path inside a CUDA graph (C2 188 vs 152 ms, C3 310 vs 217 ms, and
+        # never faster when restricted to small tensors: DESIGN.md 8), so it is off by default
         self.fused_block_bwd = os.environ.get("VQ3D_FUSED_BLOCK_BWD", "0") == "1"
+        self.fused_block_bwd_max_voxels = int(os.environ.get("VQ3D_FUSED_BLOCK_BWD_MAXVOX", "300000"))
         self.fused_pointwise_bwd = os.environ.get("VQ3D_FUSED_PW_BWD", "1") == "1"   # k1 convolutions: one fused backward launch
         self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
@@ -367,6 +368,8 @@ class Ops:
     def preact_same_backward_workspace(self, x: Tensor, blk) -> int:
         """> 0 when the fused backward covers this 'same' block (no skip convolution, C <= 32, Cb <= 16)."""
         if not self.fused_block_bwd or blk.skip_conv is not None or blk.branch_conv2.weight.shape[2] != 3:
+            return 0
+        if x.shape[0] * x[0, 0].numel() > self.fused_block_bwd_max_voxels:      # big thin tensors: the composed kernels win clearly
             return 0
         d = self.preact_desc(x, None, blk, 0)
         return int(self.lib.vq3d_preact_same_backward_workspace(C.byref(d)))

@@ -38,7 +38,7 @@ for k, g in sorted(groups.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:28s} calls {g[0]:6d}  {g[1]:9.2f} ms  {g[1] / g[0] * 1e3:8.1f} us/call")
 tags = {}
 for name, tag, nbytes, flops, e0, e1 in prof:
-    if name in ("conv3d_backward", "conv3d", "conv3d_tc", "conv1x1_backward"):
+    if name in ("conv3d_backward", "conv3d", "conv3d_tc", "conv1x1_backward", "preact_same_backward", "preact_block"):
         g = tags.setdefault((name, tag), [0, 0.0])
         g[0] += 1; g[1] += e0.elapsed_time(e1)
 for k, g in sorted(tags.items(), key=lambda kv: -kv[1][1])[:24]:
