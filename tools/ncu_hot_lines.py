@@ -31,6 +31,9 @@ h = rows[1]
 si, ii, so = h.index("# Samples"), h.index("Instructions Executed"), h.index("Source")
 stall_cols = [i for i, k in enumerate(h) if k.startswith("stall_") and "Not Issued" not in k]
 data = rows[2:]
+if len(data) > len(lines):          # several kernels in the report: KERNEL_INDEX-th block of this function's length (default the first)
+    k0 = int(os.environ.get("KERNEL_OFFSET", "0"))
+    data = data[k0:k0 + len(lines)]
 assert len(data) == len(lines), (len(data), len(lines))
 agg = {}
 for r, ln in zip(data, lines):
