@@ -687,6 +687,12 @@ def test_thin_tensor_core_stack_matches_fp32(C, n, shape, tail):
     (50000, 32, 512, "outlier"),       # a few codes with 100x the norm of the rest (dead codes after EMA updates)
     (40000, 128, 512, "scaled"),       # latents 1000x smaller than the codebook
     (40000, 32, 300, "nonfinite"),     # NaN / inf / all-zero latent vectors: torch.argmin's answer (index 0 on all-NaN rows)
+    # every element of x and e sits exactly half-way between two bf16 values and rounds the same way (to even): the rounding
+    # errors of the tensor-core operands (2^-9 .. 2^-8 relative, each) add up instead of averaging out, and the codes are
+    # nearly equidistant: the stress case of the candidate margin
+    (65536, 32, 512, "midpoint"),
+    (65536, 64, 512, "midpoint"),
+    (65536, 128, 1024, "midpoint"),
 ])
 def test_quantizer_tensor_core_path_regimes(N, D, K, kind):
     """Index exactness of the tensor-core candidate pass + exact re-rank outside the Gaussian sweep regime."""
@@ -700,6 +706,13 @@ def test_quantizer_tensor_core_path_regimes(N, D, K, kind):
         x = rs.standard_normal((N, D)).astype(np.float32)
     elif kind == "scaled":
         x = 1e-3 * rs.standard_normal((N, D)).astype(np.float32)
+    elif kind == "midpoint":
+        def mid(v):          # bf16 value with an even last mantissa bit plus half a bf16 ulp: an exact tie, rounds back to it
+            bits = (np.ascontiguousarray(v, dtype=np.float32).view(np.uint32) & np.uint32(0xfffe0000)) | np.uint32(0x8000)
+            return bits.view(np.float32).copy()
+        centre = 2.0 + rs.standard_normal((1, D)).astype(np.float32)
+        e = mid(centre + 0.05 * rs.standard_normal((K, D)).astype(np.float32))
+        x = mid(centre + 0.05 * rs.standard_normal((N, D)).astype(np.float32))
     elif kind == "nonfinite":
         x = rs.standard_normal((N, D)).astype(np.float32)
         x[5:40] = np.nan
