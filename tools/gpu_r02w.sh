@@ -1,5 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-VQ3D_FUSED_BLOCK_BWD=1 python tools/prof_bwd.py 18 18 same 64 64 32 2 > gpurun_out/r02w_plain.log 2>&1 &&
-VQ3D_FUSED_BLOCK_BWD=1 ncu --set full --clock-control none --import-source on -k regex:preact_same_bwd -s 2 -c 2 -f -o gpurun_out/r02w_same_bwd python tools/prof_bwd.py 18 18 same 64 64 32 2 > gpurun_out/r02w_ncu.log 2>&1
-echo rc=$?; tail -2 gpurun_out/r02w_ncu.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=8 -p no:cacheprovider > gpurun_out/r02w_pytest.log 2>&1; echo "pytest rc=$?"
+tail -n 16 gpurun_out/r02w_pytest.log
+( time timeout 900 python bench.py --profile-out gpurun_out/r02w_ops.tsv > gpurun_out/r02w_bench.json 2> gpurun_out/r02w_bench.err ) 2>&1 | grep real; echo "bench rc=$?"
+tail -c 800 gpurun_out/r02w_bench.err
+python - <<'P'
+import json
+l=json.loads(open('gpurun_out/r02w_bench.json').read().strip().splitlines()[-1])
+print({k:l[k] for k in ('value','ms_per_step','steps')}); print('e2e', l['e2e']['value'], 'copy_only', l['e2e']['copy_only']['value'], 'hu', l['e2e_hu_int16']['value'], 'batch1', l['batch1']['value'])
+print('roofline', {k:l['roofline'][k] for k in ('achieved','frac','traffic','avg_launch_us','share_of_step')})
+print('extract', l['extract']['value'], l['extract']['e2e']['value'], l['extract'].get('index_mismatch_vs_oracle'))
+print('quantizer', l['quantizer']['value'], l['quantizer']['second_point']['value'])
+print('train', {k:(v.get('ms_per_step'), v.get('cuda_graph')) for k,v in l['train_step'].items()})
+print('cpu', l['cpu_baseline'])
+P
+( time timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02w_ref.json 2> gpurun_out/r02w_ref.err ) 2>&1 | grep real
+cat gpurun_out/r02w_ref.json | head -c 1200
