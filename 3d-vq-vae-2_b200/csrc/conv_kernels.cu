@@ -415,6 +415,91 @@ huber_elu_mask_stats_kernel(const float *__restrict__ dec, const float *__restri
     }
 }
 
+// ---- exact medians of the two logged tensors (utils/logging_helpers.py:13: torch.median = the LOWER middle element) ----
+// Radix select, four passes of 8 bits over an order-preserving 32-bit key of the value; a pass recomputes loc and loss from
+// (decoded, x) like the statistics kernel, so that neither tensor is ever materialised.  State per quantity q (0 = loc,
+// 1 = loss) in the workspace: [0] key prefix found so far, [1] rank still to go inside that prefix (u64 in [2..3]),
+// [4] number of NaNs (u64 in [4..5]); then hist[q][256] (u64).
+constexpr int kMedStateWords = 8;
+__device__ __forceinline__ unsigned med_key(float v) {          // ascending floats <-> ascending keys
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float med_value(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+__global__ void __launch_bounds__(256)
+huber_elu_mask_median_pass_kernel(const float *__restrict__ dec, const float *__restrict__ x, const int *__restrict__ num_valid,
+                                  const uint8_t *__restrict__ mask_hw, int64_t B, int HW, int Z, int pass, unsigned *state,
+                                  unsigned long long *hist) {
+    __shared__ unsigned wh[8][2][256];           // per warp and quantity: no contention between warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * 2 * 256; i += blockDim.x) (&wh[0][0][0])[i] = 0u;
+    __syncthreads();
+    const int shift = 24 - 8 * pass;
+    const unsigned pmask = pass == 0 ? 0u : 0xffffffffu << (shift + 8);
+    const unsigned prefix[2] = {state[0], state[kMedStateWords]};
+    unsigned long long nan_n[2] = {0ull, 0ull};
+    const int64_t total = B * (int64_t)HW * Z;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i % Z);
+        const int64_t r = i / Z;
+        const int hw = (int)(r % HW);
+        const int b = (int)(r / HW);
+        if (mask_hw && !mask_hw[hw]) continue;
+        float loc = elu1(dec[i]);
+        if (num_valid && z >= num_valid[b]) loc = 0.0f;
+        const float df = loc - x[i], d = fabsf(df);
+        const float l = d < 1.0f ? 0.5f * d * d : d - 0.5f;
+        const float val[2] = {loc, l};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (val[q] != val[q]) { if (pass == 0) ++nan_n[q]; continue; }        // torch.median: any NaN -> NaN
+            const unsigned key = med_key(val[q]);
+            if ((key & pmask) == prefix[q]) atomicAdd(&wh[warp][q][(key >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x) {
+        unsigned long long t = 0ull;
+        for (int w = 0; w < 8; ++w) t += wh[w][i >> 8][i & 255];
+        if (t) atomicAdd(hist + i, t);
+    }
+    if (pass == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            unsigned long long t = nan_n[q];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0 && t) atomicAdd(reinterpret_cast<unsigned long long *>(state + q * kMedStateWords + 4), t);
+        }
+    }
+}
+
+// after a pass: the digit whose bucket holds the wanted rank extends the prefix; the last pass writes the values
+__global__ void huber_elu_mask_median_step_kernel(int pass, unsigned *state, unsigned long long *hist, float *medians) {
+    const int q = threadIdx.x;
+    if (q >= 2) return;
+    unsigned *st = state + q * kMedStateWords;
+    unsigned long long *h = hist + q * 256;
+    unsigned long long *rank = reinterpret_cast<unsigned long long *>(st + 2);
+    const unsigned long long nans = *reinterpret_cast<unsigned long long *>(st + 4);
+    if (pass == 0) {
+        unsigned long long n = nans;
+        for (int d = 0; d < 256; ++d) n += h[d];
+        *rank = n ? (n - 1) / 2 : 0;             // index of torch.median's element in sorted order
+        if (n == 0) st[6] = 1u;                  // empty selection
+    }
+    unsigned long long k = *rank, acc = 0;
+    int d = 0;
+    for (; d < 255; ++d) {
+        if (acc + h[d] > k) break;
+        acc += h[d];
+    }
+    *rank = k - acc;
+    st[0] |= (unsigned)d << (24 - 8 * pass);
+    for (int e = 0; e < 256; ++e) h[e] = 0ull;
+    if (pass == 3) medians[q] = (nans || st[6]) ? __int_as_float(0x7fc00000) : med_value(st[0]);
+}
+
 }  // namespace vq3d
 
 using namespace vq3d;
@@ -578,4 +663,28 @@ extern "C" int vq3d_huber_elu_mask_stats(const float *decoded, const float *x, c
     if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
     return launch("huber_elu_mask_stats", huber_elu_mask_stats_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x,
                   (const int *)num_valid, mask_hw, B, H * W, Z, sums, minmax);
+}
+
+extern "C" size_t vq3d_huber_elu_mask_medians_workspace(void) { return (size_t)2 * kMedStateWords * 4 + (size_t)2 * 256 * 8; }
+
+extern "C" int vq3d_huber_elu_mask_medians(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                                           int64_t B, int H, int W, int Z, float *medians, void *ws, size_t ws_bytes, void *stream) {
+    if (!decoded || !x || !medians || !ws || B < 1 || H < 1 || W < 1 || Z < 1) return fail(VQ3D_ERR_INVALID, "huber medians: bad arguments");
+    if (ws_bytes < vq3d_huber_elu_mask_medians_workspace() || (reinterpret_cast<uintptr_t>(ws) & 7) != 0)
+        return fail(VQ3D_ERR_INVALID, "huber medians: workspace too small or not 8-byte aligned");
+    unsigned *state = static_cast<unsigned *>(ws);
+    unsigned long long *hist = reinterpret_cast<unsigned long long *>(state + 2 * kMedStateWords);
+    cudaError_t e = cudaMemsetAsync(ws, 0, vq3d_huber_elu_mask_medians_workspace(), static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return check_cuda(e, "huber medians(memset)");
+    const int64_t total = B * (int64_t)H * W * Z;
+    int64_t blocks = ceil_div(total, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    for (int pass = 0; pass < 4; ++pass) {
+        int rc = launch("huber_elu_mask_median_pass", huber_elu_mask_median_pass_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, decoded, x,
+                        (const int *)num_valid, mask_hw, B, H * W, Z, pass, state, hist);
+        if (rc != VQ3D_OK) return rc;
+        rc = launch("huber_elu_mask_median_step", huber_elu_mask_median_step_kernel, dim3(1), dim3(32), 0, stream, pass, state, hist, medians);
+        if (rc != VQ3D_OK) return rc;
+    }
+    return VQ3D_OK;
 }

@@ -80,6 +80,8 @@ SIGNATURES = {
     "vq3d_hu_to_network": (C.c_int, [_fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _fp, _fp]),
     "vq3d_huber_elu_mask": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "vq3d_huber_elu_mask_stats": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
+    "vq3d_huber_elu_mask_medians_workspace": (C.c_size_t, []),
+    "vq3d_huber_elu_mask_medians": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),
 }
 
 

@@ -583,9 +583,11 @@ class Ops:
         return acc
 
 
-    def huber_metrics(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor], data_range: float = 4.0) -> dict:
-        """One pass over (decoded, x): the reference's validation log (model.py:143-149) -- recon_loss_{min,max,mean,std},
-        loc_{min,max,mean,std}, nmse, psnr (metrics/evaluate.py:18-24, data_range 4 as model.py:25) -- as 0-d tensors."""
+    def huber_metrics(self, decoded: Tensor, x: Tensor, num_valid: Optional[Tensor], mask_hw: Optional[Tensor], data_range: float = 4.0,
+                      medians: bool = True) -> dict:
+        """The reference's validation log (model.py:143-149) -- recon_loss_{min,max,mean,median,std}, loc_{min,max,mean,median,std}
+        (utils/logging_helpers.py:4-15), nmse, psnr (metrics/evaluate.py:18-24, data_range 4 as model.py:25) -- as 0-d tensors:
+        one fused pass over (decoded, x) for the sums, four more for the exact medians (radix select; `medians=False` skips them)."""
         decoded, x = self._t(decoded.detach()), self._t(x.detach())
         B, H, W, Z, num_valid = self._huber_extent(decoded, x, num_valid)
         sums = torch.zeros(8, dtype=torch.float64, device=x.device)
@@ -596,9 +598,18 @@ class Ops:
                     B, H, W, Z, self._p(sums), self._p(minmax), self.stream()), nbytes=8 * x.numel())
         s_l, n, s_d2, s_x2, s_loc, s_loc2, s_l2 = (sums[i] for i in range(7))
         std = lambda s1, s2: torch.sqrt(torch.clamp((s2 - s1 * s1 / n) / (n - 1), min=0.0)).float()          # torch.std: unbiased
-        return {"recon_loss_min": minmax[2], "recon_loss_max": minmax[3], "recon_loss_mean": (s_l / n).float(), "recon_loss_std": std(s_l, s_l2),
-                "loc_min": minmax[0], "loc_max": minmax[1], "loc_mean": (s_loc / n).float(), "loc_std": std(s_loc, s_loc2),
-                "nmse": (s_d2 / s_x2).float(), "psnr": (10.0 * torch.log10(data_range ** 2 / (s_d2 / n))).float()}
+        log = {"recon_loss_min": minmax[2], "recon_loss_max": minmax[3], "recon_loss_mean": (s_l / n).float(), "recon_loss_std": std(s_l, s_l2),
+               "loc_min": minmax[0], "loc_max": minmax[1], "loc_mean": (s_loc / n).float(), "loc_std": std(s_loc, s_loc2),
+               "nmse": (s_d2 / s_x2).float(), "psnr": (10.0 * torch.log10(data_range ** 2 / (s_d2 / n))).float()}
+        if medians:
+            med = torch.empty(2, dtype=torch.float32, device=x.device)
+            nws = int(self.lib.vq3d_huber_elu_mask_medians_workspace())
+            ws = self._workspace(nws, x.device)
+            self._call("huber_elu_mask_medians", self.lib.vq3d_huber_elu_mask_medians,
+                       (self._p(decoded), self._p(x), self._p(self._t(num_valid, torch.int32)), self._p(self._t(mask_hw, torch.uint8)),
+                        B, H, W, Z, self._p(med), self._p(ws), ws.numel(), self.stream()), nbytes=5 * 8 * x.numel())
+            log["loc_median"], log["recon_loss_median"] = med[0], med[1]
+        return log
 
 
 class _ConvFn(torch.autograd.Function):

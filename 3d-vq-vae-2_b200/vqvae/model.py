@@ -169,9 +169,9 @@ class VQVAE(_Base):
 
     @torch.no_grad()
     def validation_metrics(self, batch) -> dict:
-        """The reference's validation log (model.py:143-160) from ONE fused pass over the reconstruction: recon_loss / loc
-        min, max, mean, std, nmse, psnr (data_range 4), the commitment losses and the total loss.  (The reference's median
-        entries -- torch.median over the whole volume -- are not produced.)"""
+        """The reference's validation log (model.py:143-160) without materialising the masked reconstruction or the unreduced
+        loss: recon_loss / loc min, max, mean, median, std (utils/logging_helpers.py:4-15), nmse, psnr (data_range 4), the
+        commitment losses and the total loss -- one fused pass for the sums, a four-pass radix select for the exact medians."""
         x, num_valid = batch
         decoded, (commitment, *_) = self(x)
         nv = torch.as_tensor(num_valid, dtype=torch.int32, device=x.device).reshape(-1)

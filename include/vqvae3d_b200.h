@@ -350,10 +350,21 @@ int vq3d_huber_elu_mask(const float *decoded, const float *x, const int32_t *num
  *   sums[0..6]  += sum loss, count, sum (loc - x)^2, sum x^2, sum loc, sum loc^2, sum loss^2   (doubles; caller zeroes 8 entries)
  *   minmax[0..3] = min loc, max loc, min loss, max loss      (caller initialises to +inf, -inf, +inf, -inf)
  * loc = mask(ELU(decoded)); voxels outside mask_hw are skipped as in vq3d_huber_elu_mask.  The median entries of the
- * reference's log (torch.median over the whole volume) are not produced here.
+ * reference's log come from vq3d_huber_elu_mask_medians below.
  */
 int vq3d_huber_elu_mask_stats(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
                               int64_t B, int H, int W, int Z, double *sums, float *minmax, void *stream);
+
+/*
+ * The median entries of the same log (utils/logging_helpers.py:13, torch.median = the LOWER middle element of the flattened
+ * tensor; NaN when it holds a NaN): medians[0] = median of loc, medians[1] = median of the unreduced smooth-L1 loss, over the
+ * same voxels as vq3d_huber_elu_mask_stats.  Exact (the result is an element of the tensor): a radix select of four 8-bit
+ * passes over an order-preserving key, each pass recomputing loc and loss from (decoded, x), so nothing is materialised or
+ * sorted.  ws: vq3d_huber_elu_mask_medians_workspace() bytes of device scratch, 8-byte aligned (zeroed by the call).
+ */
+size_t vq3d_huber_elu_mask_medians_workspace(void);
+int vq3d_huber_elu_mask_medians(const float *decoded, const float *x, const int32_t *num_valid, const uint8_t *mask_hw,
+                                int64_t B, int H, int W, int Z, float *medians, void *ws, size_t ws_bytes, void *stream);
 
 /*
  * Output epilogue of vqvae/decode_embeddings.py:43-47, fused: out[i] = rint(ELU(decoded[i]) * scale - offset) as int64

@@ -423,7 +423,7 @@ def huber_epilogue(decoded: Tensor, x: Tensor, num_valid_slices: Sequence[int],
 def validation_log(decoded: Tensor, x: Tensor, num_valid_slices: Sequence[int], cylinder: bool = False,
                    data_range: float = 4.0) -> Dict[str, Tensor]:
     """What VQVAE.loc_metric logs beside the loss (model.py:120-149): utils/logging_helpers.py:4-15 over the unreduced loss
-    and over the masked reconstruction (min / max / mean / std; the median entries are left out), and
+    and over the masked reconstruction (min / max / mean / median / std), and
     metrics/evaluate.py:18-24 (nmse = ||pred - orig||^2 / ||orig||^2, psnr = 10 log10(data_range^2 / mse), data_range 4
     as model.py:25)."""
     loc = F.elu(decoded)
@@ -437,7 +437,8 @@ def validation_log(decoded: Tensor, x: Tensor, num_valid_slices: Sequence[int], 
     unreduced = F.smooth_l1_loss(loc, x, reduction="none")
     log = {}
     for name, t in (("recon_loss", unreduced), ("loc", loc)):
-        log.update({f"{name}_min": t.min(), f"{name}_max": t.max(), f"{name}_mean": t.mean(), f"{name}_std": t.std()})
+        log.update({f"{name}_min": t.min(), f"{name}_max": t.max(), f"{name}_mean": t.mean(), f"{name}_median": t.median(),
+                    f"{name}_std": t.std()})
     log["nmse"] = torch.norm(loc - x) ** 2 / torch.norm(x) ** 2
     log["psnr"] = 10 * torch.log10((data_range ** 2) / F.mse_loss(loc, x))
     return log

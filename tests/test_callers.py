@@ -187,6 +187,50 @@ def test_validation_metrics_kernel_on_the_emulator(cyl):
         assert abs(float(got[k]) - float(ref[k])) <= 2e-5 * max(1.0, abs(float(ref[k]))), (k, float(got[k]), float(ref[k]))
 
 
+@pytest.mark.parametrize("shape,nv,cyl", [((1, 1, 6, 5, 7), [7], False),      # 210 voxels: even count -> the LOWER middle element
+                                          ((1, 1, 5, 5, 7), [4], False),      # 175 voxels, 75 of them masked to exactly 0
+                                          ((2, 1, 8, 8, 5), [5, 2], True)])   # centre cylinder: a subset of the voxels
+def test_validation_medians_are_the_tensor_elements_torch_median_returns(shape, nv, cyl):
+    """vq3d_huber_elu_mask_medians (utils/logging_helpers.py:13): a radix select, so the result must be bit-identical to
+    torch.median of the materialised tensors.  decoded >= 0 keeps ELU exact (loc == decoded), so the only arithmetic left is
+    the smooth-L1 formula, restated here with the kernel's operations."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu.emu_ops import use_emulator
+    from vqvae import _ops
+    from vqvae.model import center_cylinder_mask
+    g = torch.Generator().manual_seed(sum(shape))
+    dec = torch.rand(*shape, generator=g) * 3.0
+    dec.reshape(-1)[::7] = 1.25                                               # ties around the middle
+    x = torch.rand(*shape, generator=g) * 4.5 - 0.5
+    loc = dec.clone()
+    for b, n in enumerate(nv):
+        loc[b, ..., n:] = 0.0
+    d = (loc - x).abs()
+    loss = torch.where(d < 1.0, 0.5 * d * d, d - 0.5)
+    mask = None
+    if cyl:
+        keep = center_cylinder_mask(shape[2], shape[3])
+        mask = keep.to(torch.uint8).reshape(-1)
+        loc, loss = loc[:, :, keep], loss[:, :, keep]
+    with use_emulator():
+        got = _ops.default().huber_metrics(dec, x, torch.tensor(nv, dtype=torch.int32), mask)
+    assert float(got["loc_median"]) == float(loc.median()), (float(got["loc_median"]), float(loc.median()))
+    assert float(got["recon_loss_median"]) == float(loss.median()), (float(got["recon_loss_median"]), float(loss.median()))
+
+
+def test_validation_medians_propagate_nan_like_torch_median():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu.emu_ops import use_emulator
+    from vqvae import _ops
+    dec = torch.rand(1, 1, 4, 4, 4)
+    dec[0, 0, 1, 2, 3] = float("nan")
+    x = torch.rand(1, 1, 4, 4, 4)
+    with use_emulator():
+        got = _ops.default().huber_metrics(dec, x, torch.tensor([4], dtype=torch.int32), None)
+    assert torch.isnan(got["loc_median"]) and torch.isnan(got["recon_loss_median"])
+    assert torch.isnan(torch.nn.functional.elu(dec).median())
+
+
 def test_decode_database_iteration_and_names():
     from vqvae.decode_embeddings import iter_samples, output_name
     db = {0: {"a": {"data": torch.ones(2, 2, 2, dtype=torch.long), "condition": "t1"},

@@ -175,9 +175,42 @@ def test_decoder_tail_with_two_output_channels_falls_back():
     assert abs(float(log["recon_loss_mean"]) - float(ref_recon)) <= 1e-5 * abs(float(ref_recon)) + 1e-7
 
 
+def test_validation_medians_radix_select_is_exact_at_full_size():
+    """vq3d_huber_elu_mask_medians on one 512x512x128 volume with the centre cylinder and 100 valid slices: bit-identical to
+    torch.median of the materialised tensors (decoded >= 0, so loc == decoded and only the smooth-L1 formula is restated)."""
+    import time
+    from vqvae import _ops
+    from vqvae.model import center_cylinder_mask
+    g = torch.Generator(device=DEV).manual_seed(11)
+    shape = (1, 1, 512, 512, 128)
+    dec = torch.rand(*shape, generator=g, device=DEV) * 3.0
+    x = torch.rand(*shape, generator=g, device=DEV) * 4.5 - 0.5
+    nv = torch.tensor([100], dtype=torch.int32, device=DEV)
+    keep = center_cylinder_mask(512, 512).to(DEV)
+    o = _ops.default()
+    got = o.huber_metrics(dec, x, nv, keep.to(torch.uint8).reshape(-1))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = o.huber_metrics(dec, x, nv, keep.to(torch.uint8).reshape(-1))
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    loc = dec.clone()
+    loc[..., 100:] = 0.0
+    d = (loc - x).abs()
+    loss = torch.where(d < 1.0, 0.5 * d * d, d - 0.5)
+    loc, loss = loc[:, :, keep], loss[:, :, keep]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ref_loc, ref_loss = loc.median(), loss.median()
+    torch.cuda.synchronize()
+    t_ref = time.perf_counter() - t0
+    print(f"\nvalidation log of one 512x512x128 volume incl. exact medians: {t_all * 1e3:.2f} ms; the two torch.median calls alone: {t_ref * 1e3:.2f} ms")
+    assert float(got["loc_median"]) == float(ref_loc) and float(got["recon_loss_median"]) == float(ref_loss)
+
+
 def test_validation_metrics_fused_pass_vs_oracle():
-    """VQVAE.validation_metrics (vq3d_huber_elu_mask_stats): the reference's validation log -- recon_loss / loc min, max, mean,
-    std, nmse, psnr (model.py:143-149, metrics/evaluate.py:18-24) -- against the oracle on the oracle's own reconstruction."""
+    """VQVAE.validation_metrics (vq3d_huber_elu_mask_stats + _medians): the reference's validation log -- recon_loss / loc min, max,
+    mean, median, std, nmse, psnr (model.py:143-149, metrics/evaluate.py:18-24) -- against the oracle on the oracle's own reconstruction."""
     m = _model()
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     x = O.synthetic_volume((2, 1, 16, 16, 8), seed=5)

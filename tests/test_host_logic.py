@@ -124,6 +124,11 @@ def test_cabi_argument_validation_of_the_round2_entry_points():
     assert lib.vq3d_hu_to_network(None, 4, -1500.0, 3000.0, 0.001, 1.0, None, None) == _cabi.ERR_INVALID
     assert lib.vq3d_elu_hu_rint_i16(None, 4, 1000.0, 1000.0, None, None) == _cabi.ERR_INVALID
     assert lib.vq3d_huber_elu_mask_stats(None, None, None, None, 1, 2, 2, 2, None, None, None) == _cabi.ERR_INVALID
+    assert lib.vq3d_huber_elu_mask_medians_workspace() == 2 * 8 * 4 + 2 * 256 * 8
+    assert lib.vq3d_huber_elu_mask_medians(None, None, None, None, 1, 2, 2, 2, None, None, 0, None) == _cabi.ERR_INVALID
+    one = (C.c_float * 8)()
+    assert lib.vq3d_huber_elu_mask_medians(one, one, None, None, 1, 2, 2, 2, one, one, 16, None) == _cabi.ERR_INVALID \
+        and b"workspace" in lib.vq3d_last_error()
 
 
 def test_no_cpu_fallback():
