@@ -423,8 +423,9 @@ def run_b200(args):
             k[0] += g[0]; k[1] += g[1]
         prof_total = sum(g[1] for g in groups.values())
 
-        # the measured path: the public API with CUDA graphs on
-        model.enable_cuda_graphs()
+        # the measured path: the public API with CUDA graphs on (VQ3D_BENCH_NO_GRAPH=1: eager launches, so that an ncu
+        # launch list of this command sees the step's kernels one by one -- tools/gpu_launch_list.sh; never a bench value)
+        model.enable_cuda_graphs(not os.environ.get("VQ3D_BENCH_NO_GRAPH"))
         for _ in range(warmup):
             model(x_dev)
         barrier()
