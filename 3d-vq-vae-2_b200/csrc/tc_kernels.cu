@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // threads = 128 * G: thread (row r = tid % 128, group g = tid / 128); a stage holds K = 64 = 8 chunks
 // of 8 elements (16 B); group g packs chunks g, g+G, ...
 template <int KS>       // kernel size as a compile-time constant: the (ci, kh, kw, kz) decode of the gather folds to shifts / constant divisions
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)      // two CTAs per SM: the gather is latency-bound
 conv3d_tc_kernel(TcParams p) {
     VQ3D_DYN_SMEM(unsigned char, smem_raw);
     __shared__ __align__(8) uint64_t mma_done[kTcStages];
@@ -129,6 +129,16 @@ conv3d_tc_kernel(TcParams p) {
         oz = rem - ow * p.Zo;
     }
     const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad, iz0 = oz * p.stride - p.pad;
+    // k = 4 / 2: this thread's input z of every kz tap, wrapped (circular) or -1 (zero padding, outside): fixed for the whole kernel
+    int zoff[KS == 4 || KS == 2 ? KS : 1];
+    if constexpr (KS == 4 || KS == 2) {
+#pragma unroll
+        for (int jz = 0; jz < KS; ++jz) {
+            int iz = iz0 + jz;
+            if (p.circ) iz = wrap(iz, p.Z); else if (iz < 0 || iz >= p.Z) iz = -1;
+            zoff[jz] = iz;
+        }
+    }
     const float pa = ld_scalar(p.pre_a, 0.f), pb = ld_scalar(p.pre_b, 0.f);
     // instruction descriptor: D fp32 (1<<4), A/B bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
@@ -142,7 +152,69 @@ conv3d_tc_kernel(TcParams p) {
         unsigned char *sa = smem + (size_t)s * stage_bytes;
         unsigned char *sb = sa + a_bytes;
         const int kbase = (chunk0 + it) * kTcBK;
+        // ---- B (first item of this thread): the weight loads are issued before the gather and packed after it, so that
+        // both wait for the same memory round trip ----
+        float wv0[8];
+        const bool w_has = tid < Npad * 8;
+        {
+            const int n = tid >> 3, k0 = kbase + (tid & 7) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) wv0[e] = (w_has && n < p.Cout && k0 + e < Ktot) ? __ldg(p.w + (size_t)n * Ktot + k0 + e) : 0.0f;
+        }
         // ---- A: gather + transform + bf16 pack, one 16-byte chunk (8 k's) at a time ----------
+        if constexpr (KS == 4 || KS == 2) {
+            // a 16-byte chunk is 2 x 4 (k = 4: two kw, all four kz) or 2 x 2 x 2 (k = 2: one input channel) taps with a common
+            // (ci, kh[, kw]) prefix: one plane base per chunk, 32-bit offsets from the row bases and the thread's pre-wrapped z
+            // instead of the per-element decode + wrap + 64-bit address of the generic path (the gather was instruction-bound:
+            // 69 % issue active, tensor pipe < 1 %, profiles/r01x_down16_128.summary.txt).  Keeping two chunks' loads in flight was
+            // measured too: same time (1.73 vs 1.74 ms at 16->16 @128x128x32, batch 16) for 86 registers, not kept
+            auto addrs = [&](int c, const float *&base, int (&off)[8]) {
+                const int kidx = kbase + c * 8;
+                const int ci = kidx / k3, t = kidx - ci * k3;
+                const int kh = t / kk, kw = (t - kh * kk) / k;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) off[e] = -1;
+                base = p.x1;
+                if (row_ok && ci < Cin) {
+                    base = ci < p.C1 ? p.x1 + ((size_t)b * p.C1 + ci) * S : p.x2 + ((size_t)b * p.C2 + (ci - p.C1)) * S;
+                    constexpr int NH = KS == 4 ? 1 : 2, NW = 2;               // kh values, kw values of a chunk
+#pragma unroll
+                    for (int jh = 0; jh < NH; ++jh) {
+                        int ih = ih0 + kh + jh;
+                        bool okh = true;
+                        if (p.circ) ih = wrap(ih, p.H); else okh = ih >= 0 && ih < p.H;
+#pragma unroll
+                        for (int jw = 0; jw < NW; ++jw) {
+                            int iw = iw0 + kw + jw;
+                            bool okw = okh;
+                            if (p.circ) iw = wrap(iw, p.W); else okw = okh && iw >= 0 && iw < p.W;
+                            const int rowo = (ih * p.W + iw) * p.Z;
+#pragma unroll
+                            for (int jz = 0; jz < KS; ++jz)
+                                if (okw && zoff[jz] >= 0) off[(jh * NW + jw) * KS + jz] = rowo + zoff[jz];
+                        }
+                    }
+                }
+            };
+            auto finish = [&](int c, const int (&off)[8], float (&vals)[8]) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (off[e] >= 0) vals[e] = p.pre_act ? elu1(vals[e] + pa) + pb : vals[e] + pb;
+                uint4 pk;
+                pk.x = pack_bf16(vals[0], vals[1]); pk.y = pack_bf16(vals[2], vals[3]);
+                pk.z = pack_bf16(vals[4], vals[5]); pk.w = pack_bf16(vals[6], vals[7]);
+                *reinterpret_cast<uint4 *>(sa + (size_t)c * a_lbo + (size_t)(r >> 3) * sbo + (size_t)(r & 7) * 16) = pk;
+            };
+            for (int c = g; c < 8; c += G) {
+                const float *b0;
+                int o0[8];
+                float v0[8];
+                addrs(c, b0, o0);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v0[e] = o0[e] >= 0 ? __ldg(b0 + o0[e]) : 0.0f;
+                finish(c, o0, v0);
+            }
+        } else {
         for (int c = g; c < 8; c += G) {
             int kidx = kbase + c * 8;
             int ci = kidx / k3, t = kidx - ci * k3;
@@ -176,13 +248,14 @@ conv3d_tc_kernel(TcParams p) {
             pk.z = pack_bf16(vals[4], vals[5]); pk.w = pack_bf16(vals[6], vals[7]);
             *reinterpret_cast<uint4 *>(sa + (size_t)c * a_lbo + (size_t)(r >> 3) * sbo + (size_t)(r & 7) * 16) = pk;
         }
+        }
         // ---- B: weight rows, fp32 -> bf16 -------------------------------------------------------
         for (int i = tid; i < Npad * 8; i += blockDim.x) {
             const int n = i >> 3, c = i & 7;
             const int k0 = kbase + c * 8;
             float wv[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) wv[e] = (n < p.Cout && k0 + e < Ktot) ? __ldg(p.w + (size_t)n * Ktot + k0 + e) : 0.0f;
+            for (int e = 0; e < 8; ++e) wv[e] = i == tid ? wv0[e] : ((n < p.Cout && k0 + e < Ktot) ? __ldg(p.w + (size_t)n * Ktot + k0 + e) : 0.0f);
             uint4 pk;
             pk.x = pack_bf16(wv[0], wv[1]); pk.y = pack_bf16(wv[2], wv[3]);
             pk.z = pack_bf16(wv[4], wv[5]); pk.w = pack_bf16(wv[6], wv[7]);

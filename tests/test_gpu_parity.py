@@ -381,6 +381,11 @@ def test_huber_epilogue_vs_oracle():
     (128, 0, 128, 3, 1, True, (1, 8, 8, 2), True, False),      # one 128-row tile, wrap on a size-2 axis
     (128, 0, 128, 4, 2, True, (1, 16, 16, 4), True, False),    # down block conv2
     (64, 0, 128, 2, 2, False, (1, 16, 16, 4), False, False),   # down block skip (k2 s2, no padding)
+    (16, 0, 16, 4, 2, True, (1, 32, 32, 16), True, False),     # the 16-channel down block's conv2 (specialised k4 gather)
+    (16, 0, 16, 4, 2, False, (2, 8, 12, 6), True, False),      # k4 s2 with zero padding: taps outside are skipped, batch 2
+    (12, 4, 16, 4, 2, True, (1, 8, 8, 4), False, True),        # k4 s2 over two sources, wrap on a size-4 axis, residual
+    (16, 0, 32, 2, 2, False, (1, 16, 16, 8), False, False),    # its skip convolution (specialised k2 gather)
+    (8, 8, 16, 2, 2, False, (2, 6, 10, 4), True, False),       # k2 s2 over two sources
     (9, 0, 9, 3, 1, True, (2, 12, 10, 6), True, False),        # ragged: N padded 9 -> 16, K 243 -> 256, batch 2
     (16, 0, 24, 3, 1, False, (1, 5, 7, 9), True, True),        # zero padding, odd extents, partial M tile
 ])
