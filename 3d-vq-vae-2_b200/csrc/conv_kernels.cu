@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(kCtThreads)
 conv3d_tiled_kernel(ConvParams p, int tilesH, int tilesW, int tilesZ) {
     VQ3D_DYN_SMEM(float, smem);
     constexpr int HH = kCtTH + 2, HW = kCtTW + 2, HZ = kCtTZ + 2, HV = HH * HW * HZ, TV = kCtTH * kCtTW * kCtTZ;
+    constexpr int CO_P = (CO_T + 3) & ~3;                      // weight row padded to whole float4s (128-bit broadcast loads)
     const int Cin = p.C1 + p.C2;
-    float *su = smem, *s_w = smem + (size_t)Cin * HV;          // s_w: [ci][tap][CO_T]
+    float *su = smem, *s_w = smem + (((size_t)Cin * HV + 3) & ~(size_t)3);      // s_w: [ci][tap][CO_P], 16-byte aligned
     int tile = blockIdx.x;
     const int tz = tile % tilesZ; tile /= tilesZ;
     const int tw = tile % tilesW; tile /= tilesW;
@@ -135,9 +136,9 @@ conv3d_tiled_kernel(ConvParams p, int tilesH, int tilesW, int tilesZ) {
     const int h0 = th * kCtTH, w0 = tw * kCtTW, z0 = tz * kCtTZ, co0 = blockIdx.y * CO_T;
     const int64_t S = (int64_t)p.H * p.W * p.Z;
     const float pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
-    for (int i = threadIdx.x; i < Cin * 27 * CO_T; i += kCtThreads) {
-        const int j = i % CO_T, t = (i / CO_T) % 27, ci = i / (CO_T * 27), co = co0 + j;
-        s_w[i] = co < p.Cout ? p.w[((size_t)co * Cin + ci) * 27 + t] : 0.0f;
+    for (int i = threadIdx.x; i < Cin * 27 * CO_P; i += kCtThreads) {
+        const int j = i % CO_P, t = (i / CO_P) % 27, ci = i / (CO_P * 27), co = co0 + j;
+        s_w[i] = (j < CO_T && co < p.Cout) ? p.w[((size_t)co * Cin + ci) * 27 + t] : 0.0f;
     }
     for (int i = threadIdx.x; i < Cin * HV; i += kCtThreads) {
         const int ci = i / HV;
@@ -169,7 +170,7 @@ conv3d_tiled_kernel(ConvParams p, int tilesH, int tilesW, int tilesZ) {
         for (int j = 0; j < CO_T; ++j) acc[j] = 0.0f;
         for (int ci = 0; ci < Cin; ++ci) {
             const float *ub = su + (size_t)ci * HV + (dh * HW + dw) * HZ + dz;
-            const float *wp = s_w + (size_t)ci * 27 * CO_T;
+            const float *wp = s_w + (size_t)ci * 27 * CO_P;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -177,9 +178,15 @@ conv3d_tiled_kernel(ConvParams p, int tilesH, int tilesW, int tilesZ) {
 #pragma unroll
                     for (int kz = 0; kz < 3; ++kz) {
                         const float xv = ub[(kh * HW + kw) * HZ + kz];
-                        const float *wt = wp + ((kh * 3 + kw) * 3 + kz) * CO_T;
+                        const float4 *wt = reinterpret_cast<const float4 *>(wp + ((kh * 3 + kw) * 3 + kz) * CO_P);
 #pragma unroll
-                        for (int j = 0; j < CO_T; ++j) acc[j] = __fmaf_rn(wt[j], xv, acc[j]);
+                        for (int j4 = 0; j4 < CO_P / 4; ++j4) {
+                            const float4 w4 = wt[j4];
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int l = 0; l < 4; ++l)
+                                if (j4 * 4 + l < CO_T) acc[j4 * 4 + l] = __fmaf_rn(wv[l], xv, acc[j4 * 4 + l]);
+                        }
                     }
         }
         if (oh < p.H && ow < p.W && oz < p.Z) {
@@ -203,7 +210,8 @@ conv3d_tiled_kernel(ConvParams p, int tilesH, int tilesW, int tilesZ) {
 template <int CO_T>
 static int launch_conv_tiled(const ConvParams &p, void *stream) {
     const int tH = (int)ceil_div(p.H, kCtTH), tW = (int)ceil_div(p.W, kCtTW), tZ = (int)ceil_div(p.Z, kCtTZ);
-    const size_t smem = ((size_t)(p.C1 + p.C2) * (kCtTH + 2) * (kCtTW + 2) * (kCtTZ + 2) + (size_t)(p.C1 + p.C2) * 27 * CO_T) * sizeof(float);
+    constexpr int CO_P = (CO_T + 3) & ~3;
+    const size_t smem = ((((size_t)(p.C1 + p.C2) * (kCtTH + 2) * (kCtTW + 2) * (kCtTZ + 2) + 3) & ~(size_t)3) + (size_t)(p.C1 + p.C2) * 27 * CO_P) * sizeof(float);
     return launch("conv3d_tiled", conv3d_tiled_kernel<CO_T>, dim3((unsigned)((int64_t)p.B * tH * tW * tZ), (unsigned)ceil_div(p.Cout, CO_T)),
                   dim3(kCtThreads), smem, stream, p, tH, tW, tZ);
 }
@@ -624,6 +632,7 @@ extern "C" int vq3d_conv3d(const vq3d_conv_desc *d, void *stream) {
         return launch_pointwise<16>(p, stream);
     }
     if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->C1 + d->C2 <= kCtMaxCin && d->H >= 3 && d->W >= 3 && d->Z >= 3 && total >= 16384) {
+        if (p.Cout % 9 == 0) return launch_conv_tiled<9>(p, stream);        // the 9- / 18- / 36-channel branches: no padded second pass
         if (p.Cout >= 8) return launch_conv_tiled<8>(p, stream);
         if (p.Cout >= 3) return launch_conv_tiled<4>(p, stream);
         if (p.Cout == 2) return launch_conv_tiled<2>(p, stream);
