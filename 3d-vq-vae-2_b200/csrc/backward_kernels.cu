@@ -820,6 +820,105 @@ conv3d_wgrad_tiled_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int c
     }
 }
 
+// Weight gradient of k3 s1 "same" convolutions with few output channels (the 9-, 4-, 2- and 1-channel conv2 of the residual
+// branches: the bulk of a training step's conv3d_backward time).  Same staging as conv3d_wgrad_tiled_kernel (input halo tile +
+// scaled output-gradient tile of a 4 x 4 x 32 box), different work split: a thread owns one (ci, kh, kw) and a subset of the 16
+// (dh, dw) rows, slides a three-value window along z (ONE new shared-memory load per voxel) and accumulates all COUT x 3 kz
+// products -- 1 + COUT loads feed 3 COUT FMAs, the output-gradient loads are broadcasts, and the window loads of a warp fall
+// into different banks (the tiled kernel's (co, tap)-block split needs 8 loads per 16 FMAs and its window loads conflict).
+// The groups' partial sums meet in shared memory; one global atomic per (ci, tap, co) and CTA.
+template <int COUT>
+__global__ void __launch_bounds__(kWgThreads)
+conv3d_wgrad_rows_kernel(BwdParams p, int tilesH, int tilesW, int tilesZ, int cic) {
+    constexpr int TH = 4, TW = 4, TZ = 32, HH = TH + 2, HW = TW + 2, HZ = TZ + 2, HV = HH * HW * HZ, TV = TH * TW * TZ;
+    VQ3D_DYN_SMEM(float, smem);
+    const int CinAll = p.C1 + p.C2, ci0 = blockIdx.y * cic;
+    const int Cin = min(cic, CinAll - ci0);
+    float *su = smem, *sg = smem + (size_t)Cin * HV;
+    int tile = blockIdx.x;
+    const int tz = tile % tilesZ; tile /= tilesZ;
+    const int tw = tile % tilesW; tile /= tilesW;
+    const int th = tile % tilesH;
+    const int b = tile / tilesH;
+    const int h0 = th * TH, w0 = tw * TW, z0 = tz * TZ;
+    const int64_t S = (int64_t)p.H * p.W * p.Z;
+    const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
+    for (int i = threadIdx.x; i < Cin * HV; i += kWgThreads) {
+        const int ci = i / HV;
+        int r = i - ci * HV;
+        const int hh = r / (HW * HZ); r -= hh * HW * HZ;
+        const int ww = r / HZ, zz = r - ww * HZ;
+        int ih = h0 - 1 + hh, iw = w0 - 1 + ww, iz = z0 - 1 + zz;
+        if (p.circ) {                      // boxes may reach far past the edge (partial tiles): full modulo
+            ih %= p.H; if (ih < 0) ih += p.H;
+            iw %= p.W; if (iw < 0) iw += p.W;
+            iz %= p.Z; if (iz < 0) iz += p.Z;
+        }
+        const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && iz >= 0 && iz < p.Z;
+        float u = 0.0f;
+        if (ok) {
+            const int cg = ci0 + ci;
+            const float *src = cg < p.C1 ? p.x1 + ((size_t)b * p.C1 + cg) * S : p.x2 + ((size_t)b * p.C2 + (cg - p.C1)) * S;
+            u = src[((size_t)ih * p.W + iw) * p.Z + iz];
+            u = p.pre_act ? elu1(u + pa) + pb : u + pb;
+        }
+        su[i] = u;
+    }
+    for (int i = threadIdx.x; i < COUT * TV; i += kWgThreads) {
+        const int co = i / TV;
+        int r = i - co * TV;
+        const int dh = r / (TW * TZ); r -= dh * TW * TZ;
+        const int dw = r / TZ, dz = r - dw * TZ;
+        const int oh = h0 + dh, ow = w0 + dw, oz = z0 + dz;
+        sg[i] = (oh < p.H && ow < p.W && oz < p.Z) ? p.gy[((size_t)b * COUT + co) * S + ((size_t)oh * p.W + ow) * p.Z + oz] * sc : 0.0f;
+    }
+    __syncthreads();
+    const int NI = Cin * 9;                              // (ci, kh, kw) items; the host keeps NI <= kWgThreads
+    const int G = min(kWgThreads / NI, TH * TW);          // row groups
+    const int item = threadIdx.x % NI, grp = threadIdx.x / NI;
+    float acc[COUT][3];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co][0] = acc[co][1] = acc[co][2] = 0.0f;
+    const int ci = item / 9, kh = (item % 9) / 3, kw = item % 3;
+    if (grp < G) {
+#pragma unroll 1
+        for (int row = grp; row < TH * TW; row += G) {
+            const int dh = row / TW, dw = row - dh * TW;
+            const float *ub = su + (size_t)ci * HV + ((dh + kh) * HW + dw + kw) * HZ;
+            const float *gb = sg + row * TZ;
+            float u0 = ub[0], u1 = ub[1];
+#pragma unroll 4
+            for (int dz = 0; dz < TZ; ++dz) {
+                const float u2 = ub[dz + 2];
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float g = gb[co * TV + dz];
+                    acc[co][0] = __fmaf_rn(g, u0, acc[co][0]);
+                    acc[co][1] = __fmaf_rn(g, u1, acc[co][1]);
+                    acc[co][2] = __fmaf_rn(g, u2, acc[co][2]);
+                }
+                u0 = u1; u1 = u2;
+            }
+        }
+    }
+    __syncthreads();                                      // the tiles have been read: their memory holds the groups' sums now
+    float *sacc = smem;                                   // [NI][COUT * 3]
+    for (int i = threadIdx.x; i < NI * COUT * 3; i += kWgThreads) sacc[i] = 0.0f;
+    __syncthreads();
+    if (grp < G) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+#pragma unroll
+            for (int kz = 0; kz < 3; ++kz) atomicAdd(&sacc[(item * COUT + co) * 3 + kz], acc[co][kz]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NI * COUT * 3; i += kWgThreads) {
+        const int kz = i % 3, co = (i / 3) % COUT, it = i / (3 * COUT);
+        const int cl = it / 9, hw = it % 9;
+        atomicAdd(p.gw + ((size_t)co * CinAll + ci0 + cl) * 27 + hw * 3 + kz, sacc[i]);
+    }
+}
+
 // grid (chunks, Cin, B): finish of the forward-convolution form of dgrad (see vq3d_conv3d_dgrad_finish)
 __global__ void __launch_bounds__(256)
 conv3d_dgrad_finish_kernel(BwdParams p, const float *__restrict__ gu_all) {
@@ -907,6 +1006,23 @@ extern "C" int vq3d_conv3d_backward(const vq3d_conv_desc *d, const vq3d_conv_bwd
     int cic = co_blocks <= kWgThreads ? ((kWgThreads / co_blocks) * kWgTB) / k3 : 0;     // (ci, tap) blocks per output-channel block
     if (cic > Cin) cic = Cin;
     while (cic > 0 && wg_gtile + (size_t)cic * wg_halo > 150 * 1024) --cic;
+    // k3 s1 with few output channels on deep tensors: the row-sliding kernel (input channels in chunks of <= 28 = 256 / 9 items)
+    int ric = Cin < kWgThreads / 9 ? Cin : kWgThreads / 9;
+    while (ric > 0 && wg_gtile + (size_t)ric * wg_halo > 150 * 1024) --ric;
+    const bool rows_ok = p.gw && d->k == 3 && st == 1 && d->pad == 1 && wtz == 32 && ric > 0 && getenv("VQ3D_WGRAD_TILED") == nullptr &&
+                         (d->Cout == 9 || d->Cout == 4 || d->Cout == 2 || d->Cout == 1 || d->Cout == 8) &&
+                         (!d->pad_circular || (d->H >= 3 && d->W >= 3 && d->Z >= 3));
+    if (rows_ok) {
+        const int tH = (int)ceil_div(p.Ho, 4), tW = (int)ceil_div(p.Wo, 4), tZ = (int)ceil_div(p.Zo, 32);
+        const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ), (unsigned)ceil_div(Cin, ric));
+        size_t rsmem = wg_gtile + (size_t)ric * wg_halo;
+        const size_t racc = (size_t)ric * 9 * d->Cout * 3 * sizeof(float);
+        if (rsmem < racc) rsmem = racc;
+#define VQ3D_WR_LAUNCH(CO) launch("conv3d_wgrad_rows", conv3d_wgrad_rows_kernel<CO>, grid, dim3(kWgThreads), rsmem, stream, p, tH, tW, tZ, ric)
+        rc = d->Cout == 9 ? VQ3D_WR_LAUNCH(9) : (d->Cout == 8 ? VQ3D_WR_LAUNCH(8) : (d->Cout == 4 ? VQ3D_WR_LAUNCH(4) : (d->Cout == 2 ? VQ3D_WR_LAUNCH(2) : VQ3D_WR_LAUNCH(1))));
+#undef VQ3D_WR_LAUNCH
+        if (rc) return rc;
+    } else
     if (p.gw && cic > 0 && (!d->pad_circular || (d->H >= d->k && d->W >= d->k && d->Z >= d->k))) {
         const int tH = (int)ceil_div(p.Ho, wth), tW = (int)ceil_div(p.Wo, wth), tZ = (int)ceil_div(p.Zo, wtz);
         const dim3 grid((unsigned)((int64_t)d->B * tH * tW * tZ), (unsigned)ceil_div(Cin, cic));

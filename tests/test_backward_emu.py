@@ -24,6 +24,7 @@ def _block_grads(blk, x, r, emu):
     (6, 3, "same", (2, 6, 4, 3, 5)),        # skip conv, batch 2
     (4, 8, "down", (1, 4, 6, 4, 8)),
     (8, 4, "up", (1, 8, 3, 4, 2)),
+    (8, 8, "same", (1, 8, 5, 3, 33)),       # depth >= 32: conv2's weight gradient on the row-sliding kernel (4 channels), partial tiles
 ])
 def test_preact_block_gradients_vs_oracle_autograd(cin, cout, mode, shape):
     torch.manual_seed(cin * 13 + cout)

@@ -246,6 +246,12 @@ def test_graphed_training_step_matches_eager_steps():
     (36, 36, 3, True, (1, 36, 6, 5, 40)),      # accumulators split over input-channel chunks, partial tiles on every axis
     (72, 36, 1, False, (2, 72, 5, 4, 33)),     # k = 1, batch 2, halo tile bounded by shared memory
     (5, 7, 3, False, (1, 5, 9, 6, 35)),        # zero padding, odd channel counts
+    (9, 9, 3, True, (1, 9, 9, 10, 40)),        # the row-sliding weight-gradient kernel (k3 s1, 9 / 8 / 4 / 2 / 1 output channels, depth >= 32)
+    (18, 9, 3, True, (2, 18, 5, 6, 33)),       # 162 (ci, kh, kw) items, one row group, batch 2
+    (30, 8, 3, False, (1, 30, 4, 7, 32)),      # input channels in two chunks (28 + 2), zero padding
+    (4, 4, 3, True, (1, 4, 8, 8, 64)),         # 7 row groups
+    (2, 2, 3, True, (1, 2, 6, 4, 32)),
+    (1, 1, 3, True, (1, 1, 5, 5, 32)),         # 9 items, 16 row groups
 ])
 def test_conv_gradients_tiled_wgrad_and_forward_dgrad(cin, cout, k, circ, shape):
     """The shared-memory tiled weight gradient and the forward-convolution input gradient against torch.autograd."""
