@@ -281,19 +281,24 @@ conv3d_outgrads_kernel(const float *__restrict__ gy, const float *__restrict__ r
 // voxels when there are fewer pairs than threads (the thin 512^3 layers have 8).  Pair sums stay in registers across tiles;
 // one atomicAdd per owner at the end.
 constexpr int kPwT = 128;          // voxels per tile = threads
+constexpr int kPwLD = kPwT + 4;    // shared-memory row length of the staged tile
 constexpr int kPwMaxRows = 24;     // (co, ci) + bias rows per thread: Cin * Cout + Cout <= 24 * 128
 
 __global__ void __launch_bounds__(kPwT)
 conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
     VQ3D_DYN_SMEM(float, sm);
     __shared__ float red[32];
-    const int Cin = p.C1 + p.C2, Cout = p.Cout, T = kPwT, LD = kPwT + 1;
-    float *sW = sm;                               // [Cout][Cin]
-    float *sU = sW + Cout * Cin;                  // [Cin][LD]  transformed input
+    // rows of 132 floats: 16-byte aligned (128-bit loads along the voxels in the pair phase; 8 consecutive rows fall into 8
+    // different 16-byte bank groups), weights padded to whole float4s in both orientations (128-bit broadcasts)
+    const int Cin = p.C1 + p.C2, Cout = p.Cout, T = kPwT, LD = kPwLD, CinP = (Cin + 3) & ~3, CoutP = (Cout + 3) & ~3;
+    float *sW = sm;                               // [Cout][CinP]
+    float *sWt = sW + Cout * CinP;                // [Cin][CoutP]
+    float *sU = sWt + Cin * CoutP;                // [Cin][LD]  transformed input
     float *sD = sU + Cin * LD;                    // [Cin][LD]  ELU' (1 without pre-activation)
     float *sG = sD + Cin * LD;                    // [Cout][LD] gy
     const int tid = threadIdx.x;
-    for (int i = tid; i < Cout * Cin; i += T) sW[i] = __ldg(p.w + i);
+    for (int i = tid; i < Cout * CinP; i += T) { const int co = i / CinP, ci = i - co * CinP; sW[i] = ci < Cin ? __ldg(p.w + co * Cin + ci) : 0.0f; }
+    for (int i = tid; i < Cin * CoutP; i += T) { const int ci = i / CoutP, co = i - ci * CoutP; sWt[i] = co < Cout ? __ldg(p.w + co * Cin + ci) : 0.0f; }
     const float sc = ld_scalar(p.post_scale, 1.0f), pa = ld_scalar(p.pre_a, 0.0f), pb = ld_scalar(p.pre_b, 0.0f);
     const int64_t S = (int64_t)p.H * p.W * p.Z;
     const int R = Cin * Cout + Cout;              // rows of the pair phase: (co, ci) pairs, then one bias row per co
@@ -355,10 +360,9 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
                     float gu[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                     for (int co = 0; co < Cout; ++co) {
                         const float g = sG[co * LD + tid];
-                        const float *wr = sW + co * Cin + c0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (c0 + j < Cin) gu[j] = __fmaf_rn(wr[j], g, gu[j]);
+                        const float4 w4 = *reinterpret_cast<const float4 *>(sW + co * CinP + c0);      // padded with zeros
+                        gu[0] = __fmaf_rn(w4.x, g, gu[0]); gu[1] = __fmaf_rn(w4.y, g, gu[1]);
+                        gu[2] = __fmaf_rn(w4.z, g, gu[2]); gu[3] = __fmaf_rn(w4.w, g, gu[3]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -379,9 +383,9 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
                     float raw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                     for (int ci = 0; ci < Cin; ++ci) {
                         const float u = sU[ci * LD + tid];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (c0 + j < Cout) raw[j] = __fmaf_rn(sW[(c0 + j) * Cin + ci], u, raw[j]);
+                        const float4 w4 = *reinterpret_cast<const float4 *>(sWt + ci * CoutP + c0);    // padded with zeros
+                        raw[0] = __fmaf_rn(w4.x, u, raw[0]); raw[1] = __fmaf_rn(w4.y, u, raw[1]);
+                        raw[2] = __fmaf_rn(w4.z, u, raw[2]); raw[3] = __fmaf_rn(w4.w, u, raw[3]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -411,9 +415,13 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
                     if (row < R) {
                         float a = 0.0f;
                         if (row < Cin * Cout) {
-                            const float *g = sG + (row / Cin) * LD, *u = sU + (row % Cin) * LD;
+                            const float4 *g = reinterpret_cast<const float4 *>(sG + (row / Cin) * LD), *u = reinterpret_cast<const float4 *>(sU + (row % Cin) * LD);
 #pragma unroll 4
-                            for (int vv = 0; vv < T; ++vv) a = __fmaf_rn(g[vv], u[vv], a);
+                            for (int vv = 0; vv < T / 4; ++vv) {          // same summation order as the scalar loop
+                                const float4 g4 = g[vv], u4 = u[vv];
+                                a = __fmaf_rn(g4.x, u4.x, a); a = __fmaf_rn(g4.y, u4.y, a);
+                                a = __fmaf_rn(g4.z, u4.z, a); a = __fmaf_rn(g4.w, u4.w, a);
+                            }
                         } else {
                             const float *g = sG + (row - Cin * Cout) * LD;
 #pragma unroll 4
@@ -1060,7 +1068,7 @@ extern "C" int vq3d_conv1x1_backward(const vq3d_conv_desc *d, const vq3d_conv_bw
     if (d->C2 > 0 && !d->x2) return fail(VQ3D_ERR_INVALID, "conv1x1_backward: C2 > 0 but x2 is NULL");
     const int Cin = d->C1 + d->C2;
     if (Cin * d->Cout + d->Cout > kPwMaxRows * kPwT) return fail(VQ3D_ERR_UNSUPPORTED, "conv1x1_backward: %d x %d channels exceed the fused kernel", Cin, d->Cout);
-    const size_t smem = ((size_t)d->Cout * Cin + (size_t)(2 * Cin + d->Cout) * (kPwT + 1)) * sizeof(float);
+    const size_t smem = ((size_t)d->Cout * ((Cin + 3) & ~3) + (size_t)Cin * ((d->Cout + 3) & ~3) + (size_t)(2 * Cin + d->Cout) * kPwLD) * sizeof(float);
     if (smem > 200 * 1024) return fail(VQ3D_ERR_UNSUPPORTED, "conv1x1_backward: channel counts exceed shared memory");
     BwdParams p = {};
     p.B = d->B; p.H = d->H; p.W = d->W; p.Z = d->Z; p.C1 = d->C1; p.C2 = d->C2; p.Cout = d->Cout;
