@@ -284,6 +284,8 @@ constexpr int kPwT = 128;          // voxels per tile = threads
 constexpr int kPwLD = kPwT + 4;    // shared-memory row length of the staged tile
 constexpr int kPwMaxRows = 24;     // (co, ci) + bias rows per thread: Cin * Cout + Cout <= 24 * 128
 
+// NR: (co, ci) + bias rows per thread (2 for the 9 <-> 18 pair, 24 at most): the accumulators and the unrolled row loop are sized by it
+template <int NR>
 __global__ void __launch_bounds__(kPwT)
 conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
     VQ3D_DYN_SMEM(float, sm);
@@ -305,9 +307,9 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
     const int nsplit = R < T ? T / R : 1;
     const int my_row0 = R < T ? (tid < R * nsplit ? tid % R : -1) : tid;
     const int my_part = R < T ? tid / R : 0;
-    float acc[kPwMaxRows];
+    float acc[NR];
 #pragma unroll
-    for (int j = 0; j < kPwMaxRows; ++j) acc[j] = 0.0f;
+    for (int j = 0; j < NR; ++j) acc[j] = 0.0f;
     float s_a = 0.0f, s_b = 0.0f, s_s = 0.0f;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t v = tile * T + tid;
@@ -410,7 +412,7 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < kPwMaxRows; ++j) {
+                for (int j = 0; j < NR; ++j) {
                     const int row = tid + j * T;
                     if (row < R) {
                         float a = 0.0f;
@@ -446,7 +448,7 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
         }
     }
 #pragma unroll
-    for (int j = 0; j < kPwMaxRows; ++j) {
+    for (int j = 0; j < NR; ++j) {
         const int row = R < T ? ((j == 0 && tid < R) ? tid : -1) : tid + j * T;
         if (row < 0 || row >= R) continue;
         if (row < Cin * Cout) {
@@ -1097,8 +1099,11 @@ extern "C" int vq3d_conv1x1_backward(const vq3d_conv_desc *d, const vq3d_conv_bw
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)kNumSMs * per_sm;
     if (grid > ntiles) grid = ntiles;
-    return launch("conv1x1_bwd", conv1x1_bwd_kernel, dim3((unsigned)grid), dim3(kPwT), smem, stream, p, total, ntiles,
-                  (int)(d->post_scale != nullptr && g->gscalars != nullptr));
+    const int rows = (Cin * d->Cout + d->Cout + kPwT - 1) / kPwT, want_scale = (int)(d->post_scale != nullptr && g->gscalars != nullptr);
+#define VQ3D_PW_LAUNCH(NR) launch("conv1x1_bwd", conv1x1_bwd_kernel<NR>, dim3((unsigned)grid), dim3(kPwT), smem, stream, p, total, ntiles, want_scale)
+    const int rc = rows <= 2 ? VQ3D_PW_LAUNCH(2) : (rows <= 6 ? VQ3D_PW_LAUNCH(6) : (rows <= 12 ? VQ3D_PW_LAUNCH(12) : VQ3D_PW_LAUNCH(kPwMaxRows)));
+#undef VQ3D_PW_LAUNCH
+    return rc;
 }
 
 extern "C" int vq3d_conv3d_dgrad_finish(const vq3d_conv_desc *d, const float *gu_all, float *gx1, float *gx2, float *gscalars, void *stream) {
