@@ -255,6 +255,9 @@ def test_emu_up_row_kernel(cin, cout, shape):
 @pytest.mark.parametrize("cin,cout,circ,shape,pre_act,res", [
     (2, 2, True, (1, 2, 24, 22, 33), True, False),        # partial tiles on every axis, circular wrap
     (5, 3, False, (1, 5, 21, 24, 35), True, True),        # zero padding, residual, CO_T = 4 with a ragged last chunk
+    (9, 9, True, (1, 9, 10, 9, 40), True, False),         # the 9-channel output block
+    (3, 4, True, (1, 3, 40, 36, 12), True, False),        # depth < 32: one partial z tile
+    (4, 18, False, (2, 4, 9, 7, 33), False, True),        # two 9-channel blocks, batch 2, no pre-activation
 ])
 def test_emu_tiled_conv_matches_torch(cin, cout, circ, shape, pre_act, res):
     """conv3d_tiled_kernel (k3 s1 p1, few input channels, >= 16384 output voxels) against torch's conv3d."""
