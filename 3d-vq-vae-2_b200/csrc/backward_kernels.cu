@@ -290,6 +290,9 @@ __global__ void __launch_bounds__(kPwT)
 conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
     VQ3D_DYN_SMEM(float, sm);
     __shared__ float red[32];
+    __shared__ float s_pbsum;
+    if (threadIdx.x == 0) s_pbsum = 0.0f;
+    __syncthreads();
     // rows of 132 floats: 16-byte aligned (128-bit loads along the voxels in the pair phase; 8 consecutive rows fall into 8
     // different 16-byte bank groups), weights padded to whole float4s in both orientations (128-bit broadcasts)
     const int Cin = p.C1 + p.C2, Cout = p.Cout, T = kPwT, LD = kPwLD, CinP = (Cin + 3) & ~3, CoutP = (Cout + 3) & ~3;
@@ -455,8 +458,12 @@ conv1x1_bwd_kernel(BwdParams p, int64_t total, int64_t ntiles, int want_scale) {
             if (p.gw) atomicAdd(p.gw + row, acc[j] * sc);                 // gw [Cout][Cin]: row = co * Cin + ci
         } else {
             if (p.gbias) atomicAdd(p.gbias + (row - Cin * Cout), acc[j]);
-            if (p.gscal && p.gscal_want_pb) atomicAdd(p.gscal + 3, acc[j]);
-        }
+            if (p.gscal && p.gscal_want_pb) atomicAdd(&s_pbsum, acc[j]);     // d post_b = the sum of the bias rows: ONE global atomic per CTA below
+        }                                                                      // (C_out atomics per CTA on one address were half of this kernel's time)
+    }
+    if (p.gscal && p.gscal_want_pb) {
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.gscal + 3, s_pbsum);
     }
     if (p.gscal) {
         const float ta = block_sum(p.pre_act ? s_a : 0.0f, red);
