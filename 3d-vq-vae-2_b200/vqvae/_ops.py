@@ -39,6 +39,10 @@ class Ops:
         self.fused_block_bwd_max_voxels = int(os.environ.get("VQ3D_FUSED_BLOCK_BWD_MAXVOX", "300000"))
         self.fused_pointwise_bwd = os.environ.get("VQ3D_FUSED_PW_BWD", "1") == "1"   # k1 convolutions: one fused backward launch
         self.dgrad_as_forward = True # input gradients of stride-1 same convolutions run as forward convolutions
+        # parameter gradients are added straight into an existing contiguous fp32 `.grad` (the flat buffer of FusedAdamAMSGrad):
+        # the kernels accumulate with atomics anyway, so the zero-filled temporary, the per-scalar clones and autograd's
+        # AccumulateGrad additions (~17 one-element kernels per residual block) disappear
+        self.grad_inplace = os.environ.get("VQ3D_GRAD_INPLACE", "1") != "0"
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
 
@@ -195,8 +199,9 @@ class Ops:
                               x1=self._p(x1), x2=self._p(x2), w=self._p(w), bias=self._p(bias), pre_a=self._p(pre_a), pre_b=self._p(pre_b),
                               post_scale=self._p(post_scale), post_b=self._p(post_b), residual=self._p(residual), y=self._p(y))
 
-    def conv3d_backward(self, cfg, x1, x2, w, pre_a, pre_b, post_scale, post_b, gy, need):
-        """need: dict of booleans (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b).  Returns the gradients (or None)."""
+    def conv3d_backward(self, cfg, x1, x2, w, pre_a, pre_b, post_scale, post_b, gy, need, acc_w=None, acc_bias=None):
+        """need: dict of booleans (x1, x2, w, bias, pre_a, pre_b, post_scale, post_b).  Returns the gradients (or None).
+        acc_w / acc_bias: existing gradient buffers to ADD the weight / bias gradient to (then None is returned for them)."""
         D = lambda t: None if t is None else self._t(t.detach())
         x1, x2, w, pre_a, pre_b, post_scale, post_b, gy = D(x1), D(x2), D(w), D(pre_a), D(pre_b), D(post_scale), D(post_b), D(gy)
         k = w.shape[2]
@@ -206,8 +211,8 @@ class Ops:
             dev = x1.device
             gx1 = torch.empty_like(x1) if need["x1"] else None
             gx2 = torch.empty_like(x2) if (x2 is not None and need["x2"]) else None
-            gw = torch.zeros_like(w) if need["w"] else None
-            gbias = torch.zeros(w.shape[0], dtype=torch.float32, device=dev) if need["bias"] else None
+            gw = (acc_w if acc_w is not None else torch.zeros_like(w)) if need["w"] else None
+            gbias = (acc_bias if acc_bias is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=dev)) if need["bias"] else None
             want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
             gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
             d = self.conv_desc(x1, x2, w, 1, 0, False, cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
@@ -215,7 +220,7 @@ class Ops:
                               gscalars=self._p(gscal), skip_input_grads=0)
             if self._call("conv1x1_backward", self.lib.vq3d_conv1x1_backward, (C.byref(d), C.byref(g), self.stream()), tag=tag,
                           allow_unsupported=True):
-                return gx1, gx2, gw, gbias, gscal
+                return gx1, gx2, None if acc_w is not None else gw, None if acc_bias is not None else gbias, gscal
         raw = None
         if need["post_scale"]:        # d scale = sum(gy * conv output before the post transform): recompute it
             raw = self._conv3d_fwd(x1, w, x2=x2, stride=cfg["stride"], pad=cfg["pad"], circular=cfg["circular"], pre_act=cfg["pre_act"],
@@ -223,8 +228,8 @@ class Ops:
         dev = x1.device
         gx1 = torch.empty_like(x1) if need["x1"] else None
         gx2 = torch.empty_like(x2) if (x2 is not None and need["x2"]) else None
-        gw = torch.zeros_like(w) if need["w"] else None
-        gbias = torch.zeros(w.shape[0], dtype=torch.float32, device=dev) if need["bias"] else None
+        gw = (acc_w if acc_w is not None else torch.zeros_like(w)) if need["w"] else None
+        gbias = (acc_bias if acc_bias is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=dev)) if need["bias"] else None
         want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
         gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
         d = self.conv_desc(x1, x2, w, cfg["stride"], cfg["pad"], cfg["circular"], cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
@@ -243,7 +248,7 @@ class Ops:
             g = _cabi.ConvBwd(gy=self._p(gy), raw=self._p(raw), gx1=self._p(gx1), gx2=self._p(gx2), gw=self._p(gw), gbias=self._p(gbias),
                               gscalars=self._p(gscal), skip_input_grads=int(fwd_dgrad))
             self._call("conv3d_backward", self.lib.vq3d_conv3d_backward, (C.byref(d), C.byref(g), self.stream()), kernels=3, tag=tag)
-        return gx1, gx2, gw, gbias, gscal
+        return gx1, gx2, None if acc_w is not None else gw, None if acc_bias is not None else gbias, gscal
 
     def _conv3d_fwd(self, x1: Tensor, w: Tensor, *, x2: Optional[Tensor] = None, bias: Optional[Tensor] = None, stride: int = 1,
                     pad: int = 0, circular: bool = False, pre_act: bool = False, pre_a: Optional[Tensor] = None,
@@ -621,7 +626,18 @@ class _ConvFn(torch.autograd.Function):
         ctx.ops, ctx.cfg = ops, cfg
         ctx.save_for_backward(x1, x2, w, pre_a, pre_b, post_scale, post_b, y if cfg.get("post_act") else None)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.bias_ref = bias
         return y
+
+    @staticmethod
+    def _acc_target(ops, t, wanted):
+        """The existing gradient buffer of parameter `t` when the kernels may add to it directly (Ops.grad_inplace), else None."""
+        if not (wanted and ops.grad_inplace and t is not None and t.is_leaf and t.requires_grad):
+            return None
+        g = t.grad
+        if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous() or g.shape != t.shape or g.requires_grad:
+            return None
+        return g
 
     @staticmethod
     def backward(ctx, gy):
@@ -632,10 +648,21 @@ class _ConvFn(torch.autograd.Function):
         need = dict(x1=n[2], x2=n[3] and x2 is not None, w=n[4], bias=n[5] and ctx.has_bias, pre_a=n[6] and pre_a is not None,
                     pre_b=n[7] and pre_b is not None, post_scale=n[8] and post_scale is not None, post_b=n[9] and post_b is not None)
         gy = gy.contiguous()
-        gx1, gx2, gw, gbias, gs = ctx.ops.conv3d_backward(ctx.cfg, x1, x2, w, pre_a, pre_b, post_scale, post_b, gy, need)
-        pick = lambda flag, i: gs[i:i + 1].clone() if flag else None
-        return (None, None, gx1, gx2, gw, gbias, pick(need["pre_a"], 0), pick(need["pre_b"], 1), pick(need["post_scale"], 2),
-                pick(need["post_b"], 3), gy if (ctx.has_res and n[10]) else None)
+        acc_w = _ConvFn._acc_target(ctx.ops, w, need["w"])
+        acc_bias = _ConvFn._acc_target(ctx.ops, ctx.bias_ref, need["bias"])
+        gx1, gx2, gw, gbias, gs = ctx.ops.conv3d_backward(ctx.cfg, x1, x2, w, pre_a, pre_b, post_scale, post_b, gy, need,
+                                                          acc_w=acc_w, acc_bias=acc_bias)
+        # the four Fixup scalars: ONE multi-tensor addition into their .grad instead of a clone + an AccumulateGrad kernel each
+        outs, tgt, src = [], [], []
+        for t, flag, i in ((pre_a, need["pre_a"], 0), (pre_b, need["pre_b"], 1), (post_scale, need["post_scale"], 2), (post_b, need["post_b"], 3)):
+            a = _ConvFn._acc_target(ctx.ops, t, flag) if (flag and t.numel() == 1) else None
+            if a is not None:
+                tgt.append(a.view(1)); src.append(gs[i:i + 1]); outs.append(None)
+            else:
+                outs.append(gs[i:i + 1].clone() if flag else None)
+        if tgt:
+            torch._foreach_add_(tgt, src)
+        return (None, None, gx1, gx2, gw, gbias, outs[0], outs[1], outs[2], outs[3], gy if (ctx.has_res and n[10]) else None)
 
 
 class _PreactSameFn(torch.autograd.Function):
