@@ -43,6 +43,9 @@ class Ops:
         # the kernels accumulate with atomics anyway, so the zero-filled temporary, the per-scalar clones and autograd's
         # AccumulateGrad additions (~17 one-element kernels per residual block) disappear
         self.grad_inplace = os.environ.get("VQ3D_GRAD_INPLACE", "1") != "0"
+        # scalar-gradient scratch of the convolution backwards ([4] floats each, zero on entry): slots of one pool that
+        # `begin_step()` zeroes with a single launch; without begin_step (or when the pool runs out) each call allocates its own
+        self._gscal_pool, self._gscal_next = {}, 0
         self.vq_tensor_cores = True  # large quantizer problems: tcgen05 candidate pass + exact re-rank (index-identical)
         self._ws = {}                # (device, stream) -> uint8 workspace of the kernels that need scratch (grown on demand)
 
@@ -93,6 +96,30 @@ class Ops:
             ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws
+
+    def begin_step(self, device, slots: int = 4096) -> None:
+        """Called once per training step before the backward pass (vqvae.parallel.training_step): zeroes the pool of
+        scalar-gradient scratch slots with ONE launch, so that the ~1 000 convolution backwards of a step do not each
+        launch a fill kernel for their four floats.  Slots are handed out in call order and are valid until the next begin_step."""
+        key = (device, self.stream())
+        pool = self._gscal_pool.get(key)
+        if pool is None or pool.shape[0] < slots:
+            pool = torch.zeros(slots, 4, dtype=torch.float32, device=device)
+            self._gscal_pool = {key: pool}
+        else:
+            pool.zero_()
+        self._gscal_next = 0
+
+    def _gscal(self, device) -> Tensor:
+        pool = self._gscal_pool.get((device, self.stream()))
+        if pool is not None and self._gscal_next < pool.shape[0]:
+            self._gscal_next += 1
+            return pool[self._gscal_next - 1]
+        return torch.zeros(4, dtype=torch.float32, device=device)
+
+    def end_step(self) -> None:
+        """The pool's slots are spent: later backward calls (outside a training_step) allocate their own scratch again."""
+        self._gscal_next = 1 << 60
 
     def _check(self, rc: int, allow_unsupported: bool = False) -> bool:
         if rc == _cabi.OK:
@@ -214,7 +241,7 @@ class Ops:
             gw = (acc_w if acc_w is not None else torch.zeros_like(w)) if need["w"] else None
             gbias = (acc_bias if acc_bias is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=dev)) if need["bias"] else None
             want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
-            gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
+            gscal = self._gscal(dev) if want_scal else None
             d = self.conv_desc(x1, x2, w, 1, 0, False, cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
             g = _cabi.ConvBwd(gy=self._p(gy), raw=None, gx1=self._p(gx1), gx2=self._p(gx2), gw=self._p(gw), gbias=self._p(gbias),
                               gscalars=self._p(gscal), skip_input_grads=0)
@@ -231,7 +258,7 @@ class Ops:
         gw = (acc_w if acc_w is not None else torch.zeros_like(w)) if need["w"] else None
         gbias = (acc_bias if acc_bias is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=dev)) if need["bias"] else None
         want_scal = need["pre_a"] or need["pre_b"] or need["post_scale"] or need["post_b"]
-        gscal = torch.zeros(4, dtype=torch.float32, device=dev) if want_scal else None
+        gscal = self._gscal(dev) if want_scal else None
         d = self.conv_desc(x1, x2, w, cfg["stride"], cfg["pad"], cfg["circular"], cfg["pre_act"], pre_a, pre_b, post_scale, post_b)
         k = w.shape[2]
         tag = f"{w.shape[1]}->{w.shape[0]} k{k}s{cfg['stride']} @{x1.shape[2]}x{x1.shape[3]}x{x1.shape[4]}"

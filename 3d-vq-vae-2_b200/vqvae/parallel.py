@@ -8,6 +8,8 @@ from typing import Iterable
 import torch
 import torch.distributed as dist
 
+from . import _ops
+
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: int = None, flat: torch.Tensor = None) -> None:
     """Average the gradients of `params` over the ranks with ONE all-reduce of a flat fp32 buffer (7.5 M floats = 30 MB
@@ -39,8 +41,11 @@ def training_step(model, optimizer, batch) -> torch.Tensor:
     """One data-parallel optimisation step of the reference's training loop (model.py:95-113 + DDP + Adam):
     forward in training mode (EMA statistics all-reduced inside the quantizers), backward, gradient average, step."""
     optimizer.zero_grad(set_to_none=True)
+    ops = _ops.default()
     loss = model.training_step(batch, 0)
+    ops.begin_step(loss.device)            # one launch zeroes the scalar-gradient scratch of every convolution backward of the step
     loss.backward()
+    ops.end_step()
     allreduce_gradients(model.parameters(), flat=getattr(optimizer, "flat_grad", None))
     optimizer.step()
     return loss.detach()
