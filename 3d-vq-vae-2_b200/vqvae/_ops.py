@@ -662,7 +662,7 @@ class _ConvFn(torch.autograd.Function):
         if not (wanted and ops.grad_inplace and t is not None and t.is_leaf and t.requires_grad):
             return None
         g = t.grad
-        if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous() or g.shape != t.shape or g.requires_grad:
+        if g is None or g.dtype != torch.float32 or g.device != t.device or not g.is_contiguous() or g.shape != t.shape or g.requires_grad:
             return None
         return g
 

@@ -181,3 +181,34 @@ def test_fused_same_block_backward_on_the_emulator(C, shape):
     for k, p in blk.named_parameters():
         ref = sd["b." + k].grad
         assert torch.allclose(p.grad, ref, rtol=1e-3, atol=1e-4), (k, float((p.grad - ref).abs().max()))
+
+
+@pytest.mark.parametrize("mode,cin,cout,shape", [("same", 6, 3, (1, 6, 4, 3, 5)), ("down", 4, 8, (1, 4, 6, 4, 8)), ("up", 8, 4, (1, 8, 3, 4, 2))])
+def test_parameter_gradients_accumulate_in_place_like_autograd(mode, cin, cout, shape):
+    """Ops.grad_inplace: with existing contiguous fp32 `.grad` buffers (the flat buffer of FusedAdamAMSGrad) the kernels add the
+    weight / bias gradients straight into them and the Fixup scalars arrive through one multi-tensor add -- the same values as
+    autograd's AccumulateGrad path, accumulated on top of what the buffers held, over two backward passes."""
+    from vqvae import _ops
+    torch.manual_seed(cin + cout)
+    blk = L.PreActFixupResBlock(cin, cout, mode)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn(p.shape) * 0.2)
+    x = torch.randn(shape)
+    grads = {}
+    with use_emulator():
+        o = _ops.default()
+        for inplace in (False, True):
+            prev, o.grad_inplace = o.grad_inplace, inplace
+            try:
+                for p in blk.parameters():
+                    p.grad = torch.full_like(p, 0.25)              # pre-existing content must be kept
+                for _ in range(2):
+                    xi = x.clone().requires_grad_(True)
+                    y = blk(xi)
+                    (y * y).sum().backward()
+                grads[inplace] = [p.grad.clone() for p in blk.parameters()] + [xi.grad.clone()]
+            finally:
+                o.grad_inplace = prev
+    for a, b in zip(grads[False], grads[True]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), float((a - b).abs().max())
