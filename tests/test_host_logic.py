@@ -153,3 +153,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "emu_ops" not in src, f
+
+
+def test_scalar_gradient_scratch_pool_hands_out_zeroed_slots_and_falls_back():
+    """Ops.begin_step / _gscal / end_step: slots of one pool zeroed by a single launch per step, distinct per call, re-zeroed by the
+    next begin_step, and a private zeros(4) once the pool is spent or the step is over (a stale slot would corrupt gradients)."""
+    from vqvae import _ops
+    o = _ops.Ops.__new__(_ops.Ops)
+    o._gscal_pool, o._gscal_next = {}, 0
+    o.stream = lambda: 0
+    dev = torch.device("cpu")
+    a = o._gscal(dev)                                   # no begin_step yet: private scratch
+    assert a.shape == (4,) and float(a.abs().sum()) == 0.0
+    o.begin_step(dev, slots=2)
+    s0, s1, s2 = o._gscal(dev), o._gscal(dev), o._gscal(dev)
+    assert s0.data_ptr() != s1.data_ptr() and s0.untyped_storage().data_ptr() == s1.untyped_storage().data_ptr()
+    assert s2.untyped_storage().data_ptr() != s0.untyped_storage().data_ptr()          # pool spent: fallback
+    s0.add_(3.0); s1.add_(5.0)
+    o.end_step()
+    assert o._gscal(dev).untyped_storage().data_ptr() != s0.untyped_storage().data_ptr()
+    o.begin_step(dev, slots=2)
+    t0 = o._gscal(dev)
+    assert t0.data_ptr() == s0.data_ptr() and float(t0.abs().sum()) == 0.0             # the same slot, zeroed again
